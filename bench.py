@@ -1,0 +1,298 @@
+#!/usr/bin/env python
+"""bench.py - BASELINE.json metric: MPC QP solves/sec (Go2, horizon 10, batch N) on 1/2/4/8 B200.
+
+Workload (config.workload): BASELINE.json configs[1] = batched condensed Go2 trot MPC, horizon 10, 4096 randomised
+states per GPU, ADMM kernel.  One "step" = one pass of the hot path (schedule->QP assembly->solve->GRFs) over one
+batch.  `value` counts only CONVERGED problems (status 0 and all four KKT inf-norms <= 1e-6, FP64).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--batch B] [--horizon H]
+For N > 1 launch with torchrun (one rank per GPU); problems are sharded as independent slices, no collective on the
+solve path (weak scaling: every rank gets its own batch of B problems).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+KKT_TOL = 1e-6
+WORKLOAD = "go2_trot_condensed_mpc_h10_admm"
+
+
+def algorithmic_bytes(N):
+    """minimal MPC-level I/O per solve, FP64: inputs + contact bytes + GRFs + predicted states + info."""
+    return 8 * (26 + 13 * (N + 1) + 12 * N) + 4 * N + 8 * (12 * N + 13 * (N + 1)) + 48
+
+
+def algorithmic_flops(N, n_free, iters, rounds):
+    """FP64 FLOPs of the algorithm as implemented: closed-form assembly + Gauss-Jordan K^-1 (2 n^3) +
+    ADMM iterations (2 n^2 + ~60 n each) + per polish round (reduced assembly 24 n^2, GJ 2 nr^3 ~ 2 (0.7 n)^3,
+    three H mat-vecs 6 n^2)."""
+    n = float(n_free)
+    return 20 * n * n + 2 * n ** 3 + iters * (2 * n * n + 60 * n) + rounds * (30 * n * n + 2 * (0.7 * n) ** 3)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+            self.t.join(timeout=2)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def dist_env():
+    return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+
+
+# ----------------------------------------------------------------------------------------------------- reference arm
+def cpu_reference(N, rec, contact, budget_s, threads=None):
+    """Times the restated reference CPU path (oracle/: C port of the OSQP-style condensed solve with OpenMP when
+    built, else the numpy port) on a bounded sample of the same workload.  Returns dict for `cpu_baseline`."""
+    from oracle import cpu_baseline as cb
+
+    return cb.time_sample(N, rec, contact, budget_s, threads)
+
+
+def run_reference(args):
+    rank, local, world = dist_env()
+    if rank != 0:
+        return
+    from dfki_quad_b200 import sequencer  # host-side input generator only
+    from oracle import mpc_oracle as mo
+    from oracle import cpu_baseline as cb
+
+    N, B = args.horizon, args.batch
+    batch = cb.make_batch_cpu(B, N, seed=20261019 + 2)
+    per_step_budget = 8.0
+    total_solved, total_t = 0, 0.0
+    res = None
+    for s in range(args.warmup + args.steps):
+        res = cb.time_sample(N, batch["rec"], batch["contact"], per_step_budget, None)
+        if s >= args.warmup:
+            total_solved += res["solved"]
+            total_t += res["seconds"]
+    value = total_solved / total_t
+    line = {
+        "impl": "reference", "metric": "MPC QP solves/sec (Go2, horizon 10, batch N)", "value": value, "unit": "solves/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total_t / max(args.steps, 1),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "horizon": N, "batch_per_gpu": B, "gait": "TROT", "solver": res["solver"]},
+        "cpu_baseline": {"value": value, "unit": "solves/s", "cores": res["cores"], "kind": res["kind"], "sample": res["sample"]},
+        "e2e": {"value": value, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------------------- B200 arm
+def run_b200(args):
+    import ctypes
+
+    import torch
+
+    from dfki_quad_b200 import BatchedMPC, _lib, sequencer
+
+    rank, local, world = dist_env()
+    if world > 1:
+        import torch.distributed as dist
+
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = local
+    torch.cuda.set_device(dev)
+    N, B = args.horizon, args.batch
+    cfg = sequencer.GO2_MPC
+    # every rank gets its own batch (weak scaling): seed offset by rank
+    batch = sequencer.random_batch(B, N, seed=20261019 + 2 + 1000 * rank, gaits=("TROT",), device=dev)
+    mpc = BatchedMPC(cfg["alpha"], cfg["state_weights_move"], cfg["mu"], cfg["fmin"], cfg["fmax"], "CONDENSED_ADMM",
+                     horizon=N, dt=cfg["dt"], max_batch=B, device=dev)
+    ext = torch.cuda.ExternalStream(mpc.stream(), device=dev)
+    rec_h = torch.from_numpy(batch["rec"]).pin_memory()
+    ct_h = torch.from_numpy(batch["contact"]).pin_memory()
+    with torch.cuda.stream(ext):
+        d_in = rec_h.to(dev, non_blocking=True)
+        d_ct = ct_h.to(dev, non_blocking=True)
+        d_f = torch.zeros((B, N, 12), dtype=torch.float64, device=dev)
+        d_x = torch.zeros((B, N + 1, 13), dtype=torch.float64, device=dev)
+        d_info = torch.zeros((B, 48), dtype=torch.uint8, device=dev)
+        flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    ext.synchronize()
+
+    def step_device():
+        mpc.solve_device(B, d_in.data_ptr(), d_ct.data_ptr(), d_f.data_ptr(), d_x.data_ptr(), d_info.data_ptr(), sync=False)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- device-resident throughput (`value`) ------------------------------------------------------------------
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+    evs = []
+    kernel_ms = []
+    with ClockSampler(dev) as clocks:
+        barrier()
+        for _ in range(args.steps):
+            with torch.cuda.stream(ext):
+                flush.zero_()  # L2 flush between timed iterations (outside the event pair)
+                e0 = torch.cuda.Event(enable_timing=True)
+                e1 = torch.cuda.Event(enable_timing=True)
+                e0.record(ext)
+                step_device()
+                e1.record(ext)
+            evs.append((e0, e1))
+        barrier()
+    step_ms = [a.elapsed_time(b) for a, b in evs]
+    total_ms = float(sum(step_ms))
+    info = np.frombuffer(d_info.cpu().numpy().tobytes(), dtype=np.dtype(
+        [("status", "i4"), ("iterations", "i4"), ("polish_rounds", "i4"), ("n_free", "i4"), ("kkt", "f8", (4,))]))
+    conv = (info["status"] == 0) & (info["kkt"].max(axis=1) <= KKT_TOL)
+    n_conv = int(conv.sum())
+    launches_per_step = mpc.last_timing()[1]
+
+    # ---- end-to-end through the host-buffer C ABI call (`e2e`) ----------------------------------------------------
+    f_h = np.zeros((B, N, 12))
+    x_h = np.zeros((B, N + 1, 13))
+    for _ in range(max(1, args.warmup // 2)):
+        mpc.solve_records(batch["rec"], batch["contact"], f_h, x_h)
+    barrier()
+    t0 = time.perf_counter()
+    conv_e2e = 0
+    for _ in range(args.steps):
+        _, _, inf = mpc.solve_records(batch["rec"], batch["contact"], f_h, x_h)
+        conv_e2e += int((inf.success & (inf.kkt.max(axis=1) <= KKT_TOL)).sum())
+    torch.cuda.synchronize(dev)
+    e2e_s = time.perf_counter() - t0
+
+    # ---- max over ranks, whole-job aggregate -----------------------------------------------------------------------
+    stats = torch.tensor([total_ms, e2e_s], dtype=torch.float64, device=dev)
+    counts = torch.tensor([n_conv * args.steps, conv_e2e, B * args.steps], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(stats, op=dist.ReduceOp.MAX)
+        dist.all_reduce(counts, op=dist.ReduceOp.SUM)
+    total_ms_max, e2e_s_max = stats.tolist()
+    conv_all, conv_e2e_all, issued_all = counts.tolist()
+    value = conv_all / (total_ms_max * 1e-3)
+    e2e_value = conv_e2e_all / e2e_s_max
+
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        ab = algorithmic_bytes(N)
+        # dominant kernel = mpc_admm_kernel<64,64> (all trot problems land in the n<=64 bin); the step's event time
+        # also contains the bin kernel and two empty-bin launches (a few microseconds)
+        kern_s = (total_ms / args.steps) * 1e-3
+        achieved = ab * B / kern_s / 1e9
+        fl = float(sum(algorithmic_flops(N, r["n_free"], r["iterations"], r["polish_rounds"]) for r in info))
+        cpu = None
+        if not args.no_cpu_baseline:
+            try:
+                cpu = cpu_reference(N, batch["rec"], batch["contact"], args.cpu_budget)
+            except Exception as e:  # the CPU baseline is a reported extra, never a reason to lose the GPU line
+                cpu = {"error": repr(e)}
+        line = {
+            "metric": "MPC QP solves/sec (Go2, horizon 10, batch N)", "value": value, "unit": "solves/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms_max / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "horizon": N, "batch_per_gpu": B, "gait": "TROT", "solver": "CONDENSED_ADMM",
+                       "l2": "256 MiB flush between timed iterations", "converged_fraction": conv_all / issued_all,
+                       "mean_iterations": float(info["iterations"].mean()), "mean_polish_rounds": float(info["polish_rounds"].mean()),
+                       "kkt_max": float(info["kkt"][conv].max()) if n_conv else None, "parallelism": f"shard{world}"},
+            "e2e": {"value": e2e_value, "unit": "solves/s", "h2d_bytes_per_step": int(B * (8 * (26 + 13 * (N + 1) + 12 * N) + 4 * N)),
+                    "d2h_bytes_per_step": int(B * (8 * (12 * N + 13 * (N + 1)) + 48))},
+            "gpu_launches": int(launches_per_step * args.steps),
+            "clocks": clocks.summary(),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src, "kernel": "mpc_admm_kernel<64,64>",
+                         "algorithmic_bytes_per_solve": ab,
+                         "note": "latency/FP64-bound on-chip solve: HBM fraction is tiny by design (SURVEY.md 8d)"},
+            "fp64": {"flops_per_step": fl, "achieved_tflops": fl / kern_s / 1e12, "nominal_peak_tflops": 37.0},
+        }
+        if cpu is not None and "error" not in cpu:
+            line["cpu_baseline"] = {"value": cpu["solved"] / cpu["seconds"], "unit": "solves/s", "cores": cpu["cores"],
+                                    "kind": cpu["kind"], "sample": cpu["sample"]}
+        elif cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=4096)
+    ap.add_argument("--horizon", type=int, default=10)
+    ap.add_argument("--cpu-budget", type=float, default=15.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

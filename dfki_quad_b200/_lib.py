@@ -1,0 +1,96 @@
+"""ctypes binding of libb200qp.so (include/b200qp.h).  Fails loudly when the CUDA library is missing: there is no
+CPU fallback anywhere in this package."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb200qp.so")
+
+OK, ERR_ARG, ERR_CUDA, ERR_UNSUPPORTED = 0, -1, -2, -3
+ACADOS_SUCCESS, ACADOS_NAN_DETECTED, ACADOS_MAXITER, ACADOS_MINSTEP, ACADOS_QP_FAILURE, ACADOS_READY = range(6)
+NAN_AFTER_SUCCESS = -7777
+SOLVER_CONDENSED_ADMM, SOLVER_SPARSE_RICCATI = 0, 1
+SOLVERS = {"CONDENSED_ADMM": 0, "SPARSE_RICCATI": 1,
+           # the reference's acados plan names (mit_controller_node.cpp:502-519) map onto the two kernels
+           "PARTIAL_CONDENSING_OSQP": 0, "FULL_CONDENSING_HPIPM": 0, "FULL_CONDENSING_QPOASES": 0,
+           "FULL_CONDENSING_DAQP": 0, "PARTIAL_CONDENSING_HPIPM": 1}
+
+
+class MpcConfig(C.Structure):
+    _fields_ = [
+        ("horizon", C.c_int32), ("solver", C.c_int32), ("max_batch", C.c_int32), ("device", C.c_int32),
+        ("dt", C.c_double), ("alpha", C.c_double), ("state_weights", C.c_double * 12),
+        ("mu", C.c_double), ("fmin", C.c_double), ("fmax", C.c_double),
+        ("admm_rho", C.c_double), ("admm_sigma", C.c_double), ("admm_alpha", C.c_double), ("admm_eps", C.c_double),
+        ("kkt_tol", C.c_double),
+        ("admm_max_iter", C.c_int32), ("admm_check_every", C.c_int32), ("polish_max_rounds", C.c_int32),
+        ("ipm_max_iter", C.c_int32),
+    ]
+
+
+class SolverInfo(C.Structure):
+    _fields_ = [("status", C.c_int32), ("iterations", C.c_int32), ("polish_rounds", C.c_int32), ("n_free", C.c_int32),
+                ("kkt", C.c_double * 4)]
+
+
+EXPORTS = [
+    "b200qp_version", "b200qp_device_count", "b200qp_last_error", "b200qp_mpc_create", "b200qp_mpc_destroy",
+    "b200qp_mpc_set_state_weights", "b200qp_mpc_set_input_weights", "b200qp_mpc_set_fmax", "b200qp_mpc_set_mu",
+    "b200qp_mpc_solve_batch", "b200qp_mpc_solve_batch_device", "b200qp_mpc_get_duals", "b200qp_mpc_get_condensed",
+    "b200qp_mpc_last_timing", "b200qp_mpc_stream", "b200qp_gait_schedule", "b200qp_gait_schedule_device",
+]
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` or "
+            "`make -C dfki_quad_b200/csrc` (sm_100a CUDA library; this package has no CPU fallback)")
+    lib = C.CDLL(LIB_PATH)
+    p, i32, dbl, vp = C.POINTER, C.c_int32, C.c_double, C.c_void_p
+    lib.b200qp_version.restype = C.c_char_p
+    lib.b200qp_last_error.restype = C.c_char_p
+    lib.b200qp_device_count.restype = i32
+    lib.b200qp_mpc_create.argtypes = [p(MpcConfig), p(vp)]
+    lib.b200qp_mpc_create.restype = i32
+    lib.b200qp_mpc_destroy.argtypes = [vp]
+    lib.b200qp_mpc_destroy.restype = None
+    lib.b200qp_mpc_set_state_weights.argtypes = [vp, p(dbl)]
+    lib.b200qp_mpc_set_input_weights.argtypes = [vp, dbl]
+    lib.b200qp_mpc_set_fmax.argtypes = [vp, dbl]
+    lib.b200qp_mpc_set_mu.argtypes = [vp, dbl]
+    lib.b200qp_mpc_solve_batch.argtypes = [vp, i32, vp, vp, vp, vp, vp]
+    lib.b200qp_mpc_solve_batch_device.argtypes = [vp, i32, vp, vp, vp, vp, vp, i32]
+    lib.b200qp_mpc_get_duals.argtypes = [vp, i32, vp, vp]
+    lib.b200qp_mpc_get_condensed.argtypes = [vp, i32, vp, i32, vp]
+    lib.b200qp_mpc_last_timing.argtypes = [vp, p(C.c_float), p(i32)]
+    lib.b200qp_mpc_stream.argtypes = [vp]
+    lib.b200qp_mpc_stream.restype = vp
+    lib.b200qp_gait_schedule.argtypes = [i32, i32, i32, dbl, vp, vp, vp, vp, vp, dbl, dbl, vp, vp, vp, vp]
+    lib.b200qp_gait_schedule_device.argtypes = [i32, i32, dbl, vp, vp, vp, vp, vp, dbl, dbl, vp, vp, vp, vp, vp]
+    for name in EXPORTS:
+        fn = getattr(lib, name)
+        if fn.restype is C.c_int:  # default restype
+            fn.restype = i32
+    _lib = lib
+    return lib
+
+
+def last_error() -> str:
+    return load().b200qp_last_error().decode()
+
+
+class B200QPError(RuntimeError):
+    pass
+
+
+def check(rc: int, what: str):
+    if rc != OK:
+        raise B200QPError(f"{what} failed with code {rc}: {last_error()}")

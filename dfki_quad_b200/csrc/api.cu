@@ -1,0 +1,466 @@
+// C ABI of libb200qp.so (include/b200qp.h): handle management, staging buffers, kernel launches.
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+
+#include "common.cuh"
+
+namespace b200qp {
+cudaError_t launch_gait_schedule(int n, int steps, double dt, const double *period, const double *duty,
+                                 const double *offset, const double *phase, const uint8_t *measured, double fmin,
+                                 double fmax, uint8_t *contact, double *swing_time, double *lbu, double *ubu,
+                                 cudaStream_t st);
+cudaError_t launch_mpc_bin(int n, int N, const uint8_t *contact, int *bin_count, int *bin_lists,
+                           b200qp_solver_info *info, cudaStream_t st);
+cudaError_t launch_mpc_admm(int bin, const MpcParams &P, const MpcBuffers &B, int grid, cudaStream_t st);
+int admm_block_size(int bin);
+int admm_occupancy(int bin);
+cudaError_t launch_mpc_riccati(const MpcParams &P, int n, const double *in, const uint8_t *contact, double *forces,
+                               double *xpred, b200qp_solver_info *info, double *lam_box, double *lam_g,
+                               cudaStream_t st);
+}  // namespace b200qp
+
+using namespace b200qp;
+
+static thread_local std::string g_err;
+static void set_err(const char *where, cudaError_t e) {
+  g_err = std::string(where) + ": " + cudaGetErrorString(e);
+}
+#define CK(call)                     \
+  do {                               \
+    cudaError_t e__ = (call);        \
+    if (e__ != cudaSuccess) {        \
+      set_err(#call, e__);           \
+      return B200QP_ERR_CUDA;        \
+    }                                \
+  } while (0)
+
+struct b200qp_mpc {
+  b200qp_mpc_config cfg;
+  MpcParams P;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  int num_sms = 0;
+  // device buffers sized for max_batch
+  double *d_in = nullptr, *d_forces = nullptr, *d_xpred = nullptr, *d_lam_box = nullptr, *d_lam_g = nullptr;
+  uint8_t *d_contact = nullptr;
+  b200qp_solver_info *d_info = nullptr;
+  int *d_bin_count = nullptr;  // [4] counts + [4] next
+  int *d_bin_lists = nullptr;  // [3][max_batch]
+  double *d_hscratch[3] = {nullptr, nullptr, nullptr};
+  int grid[3] = {0, 0, 0};
+  // pinned staging
+  double *h_in = nullptr, *h_forces = nullptr, *h_xpred = nullptr;
+  uint8_t *h_contact = nullptr;
+  b200qp_solver_info *h_info = nullptr;
+  // last call
+  const double *last_in = nullptr;
+  const uint8_t *last_contact = nullptr;
+  int last_n = 0;
+  int last_launches = 0;
+  bool want_duals = false;
+};
+
+static void fill_params(b200qp_mpc *h) {
+  const b200qp_mpc_config &c = h->cfg;
+  MpcParams &P = h->P;
+  P.N = c.horizon;
+  P.in_stride = b200qp_mpc_in_doubles(c.horizon);
+  P.dt = c.dt;
+  P.alpha = c.alpha;
+  for (int i = 0; i < 12; ++i) P.w[i] = c.state_weights[i];
+  P.mu = c.mu;
+  P.fmin = c.fmin;
+  P.fmax = c.fmax;
+  P.rho0 = c.admm_rho > 0 ? c.admm_rho : 1e-3;
+  P.sigma = c.admm_sigma > 0 ? c.admm_sigma : 1e-6;
+  P.relax = c.admm_alpha > 0 ? c.admm_alpha : 1.6;
+  P.eps = c.admm_eps > 0 ? c.admm_eps : 1e-3;
+  P.kkt_tol = c.kkt_tol > 0 ? c.kkt_tol : 1e-7;
+  P.max_iter = c.admm_max_iter > 0 ? c.admm_max_iter : 2000;
+  P.check_every = c.admm_check_every > 0 ? c.admm_check_every : 10;
+  P.polish_rounds = c.polish_max_rounds > 0 ? c.polish_max_rounds : 8;
+  P.ipm_max_iter = c.ipm_max_iter > 0 ? c.ipm_max_iter : 40;
+}
+
+extern "C" {
+
+const char *b200qp_version(void) { return "b200qp 0.1 (sm_100a)"; }
+const char *b200qp_last_error(void) { return g_err.c_str(); }
+int32_t b200qp_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+int32_t b200qp_mpc_create(const b200qp_mpc_config *cfg, b200qp_mpc **out) {
+  if (!cfg || !out) return B200QP_ERR_ARG;
+  *out = nullptr;
+  if (cfg->horizon < 1 || cfg->horizon > B200QP_MAX_HORIZON || cfg->max_batch < 1 || !(cfg->dt > 0) ||
+      !(cfg->alpha > 0) || !(cfg->mu >= 0) || !(cfg->fmax >= cfg->fmin)) {
+    g_err = "b200qp_mpc_create: invalid configuration";
+    return B200QP_ERR_ARG;
+  }
+  if (cfg->solver != B200QP_SOLVER_CONDENSED_ADMM && cfg->solver != B200QP_SOLVER_SPARSE_RICCATI) {
+    g_err = "b200qp_mpc_create: unknown solver";
+    return B200QP_ERR_ARG;
+  }
+  int ndev = 0;
+  CK(cudaGetDeviceCount(&ndev));
+  if (cfg->device < 0 || cfg->device >= ndev) {
+    g_err = "b200qp_mpc_create: no such CUDA device (there is no CPU fallback)";
+    return B200QP_ERR_CUDA;
+  }
+  CK(cudaSetDevice(cfg->device));
+  b200qp_mpc *h = new (std::nothrow) b200qp_mpc();
+  if (!h) return B200QP_ERR_ARG;
+  h->cfg = *cfg;
+  fill_params(h);
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, cfg->device));
+  h->num_sms = prop.multiProcessorCount;
+  const size_t nb = (size_t)cfg->max_batch;
+  const int N = cfg->horizon;
+  const size_t in_d = (size_t)b200qp_mpc_in_doubles(N);
+  CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  CK(cudaEventCreate(&h->ev0));
+  CK(cudaEventCreate(&h->ev1));
+  CK(cudaMalloc(&h->d_in, nb * in_d * sizeof(double)));
+  CK(cudaMalloc(&h->d_contact, nb * N * 4));
+  CK(cudaMalloc(&h->d_forces, nb * N * 12 * sizeof(double)));
+  CK(cudaMalloc(&h->d_xpred, nb * (N + 1) * 13 * sizeof(double)));
+  CK(cudaMalloc(&h->d_lam_box, nb * N * 12 * sizeof(double)));
+  CK(cudaMalloc(&h->d_lam_g, nb * N * 16 * sizeof(double)));
+  CK(cudaMalloc(&h->d_info, nb * sizeof(b200qp_solver_info)));
+  CK(cudaMalloc(&h->d_bin_count, 8 * sizeof(int)));
+  CK(cudaMalloc(&h->d_bin_lists, 3 * nb * sizeof(int)));
+  CK(cudaMemset(h->d_forces, 0, nb * N * 12 * sizeof(double)));
+  CK(cudaMemset(h->d_xpred, 0, nb * (N + 1) * 13 * sizeof(double)));
+  if (cfg->solver == B200QP_SOLVER_CONDENSED_ADMM) {
+    for (int b = 0; b < 3; ++b) {
+      const int bs = admm_block_size(b);
+      int g = h->num_sms * admm_occupancy(b);
+      if ((size_t)g > nb) g = (int)nb;
+      h->grid[b] = g;
+      CK(cudaMalloc(&h->d_hscratch[b], (size_t)g * bs * bs * sizeof(double)));
+    }
+  }
+  CK(cudaMallocHost(&h->h_in, nb * in_d * sizeof(double)));
+  CK(cudaMallocHost(&h->h_contact, nb * N * 4));
+  CK(cudaMallocHost(&h->h_forces, nb * N * 12 * sizeof(double)));
+  CK(cudaMallocHost(&h->h_xpred, nb * (N + 1) * 13 * sizeof(double)));
+  CK(cudaMallocHost(&h->h_info, nb * sizeof(b200qp_solver_info)));
+  *out = h;
+  return B200QP_OK;
+}
+
+void b200qp_mpc_destroy(b200qp_mpc *h) {
+  if (!h) return;
+  cudaSetDevice(h->cfg.device);
+  cudaFree(h->d_in);
+  cudaFree(h->d_contact);
+  cudaFree(h->d_forces);
+  cudaFree(h->d_xpred);
+  cudaFree(h->d_lam_box);
+  cudaFree(h->d_lam_g);
+  cudaFree(h->d_info);
+  cudaFree(h->d_bin_count);
+  cudaFree(h->d_bin_lists);
+  for (int b = 0; b < 3; ++b) cudaFree(h->d_hscratch[b]);
+  cudaFreeHost(h->h_in);
+  cudaFreeHost(h->h_contact);
+  cudaFreeHost(h->h_forces);
+  cudaFreeHost(h->h_xpred);
+  cudaFreeHost(h->h_info);
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+int32_t b200qp_mpc_set_state_weights(b200qp_mpc *h, const double weights[12]) {
+  if (!h || !weights) return B200QP_ERR_ARG;
+  for (int i = 0; i < 12; ++i) h->cfg.state_weights[i] = weights[i];
+  fill_params(h);
+  return B200QP_OK;
+}
+int32_t b200qp_mpc_set_input_weights(b200qp_mpc *h, double alpha) {
+  if (!h || !(alpha > 0)) return B200QP_ERR_ARG;
+  h->cfg.alpha = alpha;
+  fill_params(h);
+  return B200QP_OK;
+}
+int32_t b200qp_mpc_set_fmax(b200qp_mpc *h, double fmax) {
+  if (!h || !(fmax >= h->cfg.fmin)) return B200QP_ERR_ARG;
+  h->cfg.fmax = fmax;
+  fill_params(h);
+  return B200QP_OK;
+}
+int32_t b200qp_mpc_set_mu(b200qp_mpc *h, double mu) {
+  if (!h || !(mu >= 0)) return B200QP_ERR_ARG;
+  h->cfg.mu = mu;
+  fill_params(h);
+  return B200QP_OK;
+}
+
+static int32_t solve_device_impl(b200qp_mpc *h, int32_t n, const double *d_in, const uint8_t *d_contact,
+                                 double *d_forces, double *d_xpred, b200qp_solver_info *d_info, int dbg_index,
+                                 double *dbg_H, double *dbg_g) {
+  const int N = h->cfg.horizon;
+  int launches = 0;
+  CK(cudaEventRecord(h->ev0, h->stream));
+  if (h->cfg.solver == B200QP_SOLVER_CONDENSED_ADMM) {
+    CK(cudaMemsetAsync(h->d_bin_count, 0, 8 * sizeof(int), h->stream));
+    CK(launch_mpc_bin(n, N, d_contact, h->d_bin_count, h->d_bin_lists, d_info, h->stream));
+    ++launches;
+    for (int b = 0; b < 3; ++b) {
+      MpcBuffers B;
+      B.in = d_in;
+      B.contact = d_contact;
+      B.forces = d_forces;
+      B.xpred = d_xpred;
+      B.info = d_info;
+      B.lam_box = h->want_duals ? h->d_lam_box : nullptr;
+      B.lam_g = h->want_duals ? h->d_lam_g : nullptr;
+      B.bin_list = h->d_bin_lists + (size_t)b * n;
+      B.bin_count = h->d_bin_count + b;
+      B.bin_next = h->d_bin_count + 4 + b;
+      B.hscratch = h->d_hscratch[b];
+      B.dbg_index = dbg_index;
+      B.dbg_H = dbg_H;
+      B.dbg_g = dbg_g;
+      int g = h->grid[b];
+      if (g > n) g = n;
+      CK(launch_mpc_admm(b, h->P, B, g, h->stream));
+      ++launches;
+    }
+  } else {
+    CK(launch_mpc_riccati(h->P, n, d_in, d_contact, d_forces, d_xpred, d_info,
+                          h->want_duals ? h->d_lam_box : nullptr, h->want_duals ? h->d_lam_g : nullptr, h->stream));
+    ++launches;
+  }
+  CK(cudaEventRecord(h->ev1, h->stream));
+  h->last_launches = launches;
+  h->last_in = d_in;
+  h->last_contact = d_contact;
+  h->last_n = n;
+  return B200QP_OK;
+}
+
+int32_t b200qp_mpc_solve_batch_device(b200qp_mpc *h, int32_t n, const double *d_in, const uint8_t *d_contact,
+                                      double *d_forces, double *d_xpred, b200qp_solver_info *d_info, int32_t sync) {
+  if (!h || n < 0 || n > h->cfg.max_batch || (n > 0 && (!d_in || !d_contact || !d_forces || !d_xpred || !d_info))) {
+    g_err = "b200qp_mpc_solve_batch_device: bad arguments";
+    return B200QP_ERR_ARG;
+  }
+  if (n == 0) return B200QP_OK;
+  CK(cudaSetDevice(h->cfg.device));
+  int32_t rc = solve_device_impl(h, n, d_in, d_contact, d_forces, d_xpred, d_info, -1, nullptr, nullptr);
+  if (rc != B200QP_OK) return rc;
+  if (sync) CK(cudaStreamSynchronize(h->stream));
+  return B200QP_OK;
+}
+
+int32_t b200qp_mpc_solve_batch(b200qp_mpc *h, int32_t n, const double *in, const uint8_t *contact, double *forces,
+                               double *xpred, b200qp_solver_info *info) {
+  if (!h || n < 0 || n > h->cfg.max_batch || (n > 0 && (!in || !contact || !forces || !xpred || !info))) {
+    g_err = "b200qp_mpc_solve_batch: bad arguments";
+    return B200QP_ERR_ARG;
+  }
+  if (n == 0) return B200QP_OK;
+  CK(cudaSetDevice(h->cfg.device));
+  const int N = h->cfg.horizon;
+  const size_t in_b = (size_t)n * b200qp_mpc_in_doubles(N) * sizeof(double);
+  const size_t f_b = (size_t)n * N * 12 * sizeof(double), x_b = (size_t)n * (N + 1) * 13 * sizeof(double);
+  // stage through pinned memory so the copies are asynchronous DMA
+  memcpy(h->h_in, in, in_b);
+  memcpy(h->h_contact, contact, (size_t)n * N * 4);
+  CK(cudaMemcpyAsync(h->d_in, h->h_in, in_b, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->d_contact, h->h_contact, (size_t)n * N * 4, cudaMemcpyHostToDevice, h->stream));
+  int32_t rc = solve_device_impl(h, n, h->d_in, h->d_contact, h->d_forces, h->d_xpred, h->d_info, -1, nullptr, nullptr);
+  if (rc != B200QP_OK) return rc;
+  CK(cudaMemcpyAsync(h->h_forces, h->d_forces, f_b, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(h->h_xpred, h->d_xpred, x_b, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(h->h_info, h->d_info, (size_t)n * sizeof(b200qp_solver_info), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  // failed problems leave the caller's output slots untouched (mpc.cpp:447-455)
+  const size_t f1 = (size_t)N * 12, x1 = (size_t)(N + 1) * 13;
+  bool all_ok = true;
+  for (int p = 0; p < n; ++p) all_ok &= (h->h_info[p].status == B200QP_ACADOS_SUCCESS);
+  if (all_ok) {
+    memcpy(forces, h->h_forces, f_b);
+    memcpy(xpred, h->h_xpred, x_b);
+  } else {
+    for (int p = 0; p < n; ++p)
+      if (h->h_info[p].status == B200QP_ACADOS_SUCCESS) {
+        memcpy(forces + p * f1, h->h_forces + p * f1, f1 * sizeof(double));
+        memcpy(xpred + p * x1, h->h_xpred + p * x1, x1 * sizeof(double));
+      }
+  }
+  memcpy(info, h->h_info, (size_t)n * sizeof(b200qp_solver_info));
+  return B200QP_OK;
+}
+
+int32_t b200qp_mpc_get_duals(b200qp_mpc *h, int32_t n, double *lam_box, double *lam_g) {
+  if (!h || n < 0 || n > h->last_n || !lam_box || !lam_g || !h->last_in) return B200QP_ERR_ARG;
+  CK(cudaSetDevice(h->cfg.device));
+  // re-run the last batch with dual output enabled (diagnostic path, not timed)
+  const int N = h->cfg.horizon;
+  h->want_duals = true;
+  double *tf = nullptr, *tx = nullptr;
+  b200qp_solver_info *ti = nullptr;
+  CK(cudaMalloc(&tf, (size_t)n * N * 12 * sizeof(double)));
+  CK(cudaMalloc(&tx, (size_t)n * (N + 1) * 13 * sizeof(double)));
+  CK(cudaMalloc(&ti, (size_t)n * sizeof(b200qp_solver_info)));
+  CK(cudaMemsetAsync(h->d_lam_box, 0, (size_t)n * N * 12 * sizeof(double), h->stream));
+  CK(cudaMemsetAsync(h->d_lam_g, 0, (size_t)n * N * 16 * sizeof(double), h->stream));
+  int32_t rc = solve_device_impl(h, n, h->last_in, h->last_contact, tf, tx, ti, -1, nullptr, nullptr);
+  h->want_duals = false;
+  if (rc == B200QP_OK) {
+    cudaMemcpyAsync(lam_box, h->d_lam_box, (size_t)n * N * 12 * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+    cudaMemcpyAsync(lam_g, h->d_lam_g, (size_t)n * N * 16 * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+  }
+  cudaError_t e = cudaStreamSynchronize(h->stream);
+  cudaFree(tf);
+  cudaFree(tx);
+  cudaFree(ti);
+  if (e != cudaSuccess) {
+    set_err("b200qp_mpc_get_duals", e);
+    return B200QP_ERR_CUDA;
+  }
+  return rc;
+}
+
+int32_t b200qp_mpc_get_condensed(b200qp_mpc *h, int32_t index, double *H, int32_t ldh, double *g) {
+  if (!h || !H || !g || index < 0 || index >= h->last_n || !h->last_in) return B200QP_ERR_ARG;
+  if (h->cfg.solver != B200QP_SOLVER_CONDENSED_ADMM) return B200QP_ERR_UNSUPPORTED;
+  CK(cudaSetDevice(h->cfg.device));
+  const int N = h->cfg.horizon;
+  const size_t in_d = (size_t)b200qp_mpc_in_doubles(N);
+  double *dH = nullptr, *dg = nullptr, *tf = nullptr, *tx = nullptr;
+  b200qp_solver_info *ti = nullptr;
+  const int nmax = 12 * N;
+  CK(cudaMalloc(&dH, (size_t)nmax * nmax * sizeof(double)));
+  CK(cudaMalloc(&dg, (size_t)nmax * sizeof(double)));
+  CK(cudaMalloc(&tf, (size_t)N * 12 * sizeof(double)));
+  CK(cudaMalloc(&tx, (size_t)(N + 1) * 13 * sizeof(double)));
+  CK(cudaMalloc(&ti, sizeof(b200qp_solver_info)));
+  const double *sv_in = h->last_in;
+  const uint8_t *sv_ct = h->last_contact;
+  const int sv_n = h->last_n;
+  int32_t rc = solve_device_impl(h, 1, sv_in + (size_t)index * in_d, sv_ct + (size_t)index * N * 4, tf, tx, ti, 0, dH, dg);
+  h->last_in = sv_in;
+  h->last_contact = sv_ct;
+  h->last_n = sv_n;
+  b200qp_solver_info inf;
+  memset(&inf, 0, sizeof(inf));
+  int nfree = -1;
+  if (rc == B200QP_OK && cudaMemcpyAsync(&inf, ti, sizeof(inf), cudaMemcpyDeviceToHost, h->stream) == cudaSuccess &&
+      cudaStreamSynchronize(h->stream) == cudaSuccess) {
+    nfree = inf.n_free;
+    if (nfree > 0 && nfree <= nmax && ldh >= nfree) {
+      cudaMemcpy2D(H, (size_t)ldh * sizeof(double), dH, (size_t)nfree * sizeof(double), (size_t)nfree * sizeof(double),
+                   nfree, cudaMemcpyDeviceToHost);
+      cudaMemcpy(g, dg, (size_t)nfree * sizeof(double), cudaMemcpyDeviceToHost);
+    } else if (nfree > 0) {
+      nfree = B200QP_ERR_ARG;
+    }
+  }
+  cudaFree(dH);
+  cudaFree(dg);
+  cudaFree(tf);
+  cudaFree(tx);
+  cudaFree(ti);
+  return nfree;
+}
+
+int32_t b200qp_mpc_last_timing(b200qp_mpc *h, float *kernel_ms, int32_t *kernel_launches) {
+  if (!h) return B200QP_ERR_ARG;
+  CK(cudaSetDevice(h->cfg.device));
+  CK(cudaEventSynchronize(h->ev1));
+  float ms = 0.f;
+  CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+  if (kernel_ms) *kernel_ms = ms;
+  if (kernel_launches) *kernel_launches = h->last_launches;
+  return B200QP_OK;
+}
+
+void *b200qp_mpc_stream(b200qp_mpc *h) { return h ? (void *)h->stream : nullptr; }
+
+int32_t b200qp_gait_schedule_device(int32_t n, int32_t steps, double dt, const double *d_period, const double *d_duty,
+                                    const double *d_offset, const double *d_phase, const uint8_t *d_measured_contact,
+                                    double fmin, double fmax, uint8_t *d_contact, double *d_swing_time, double *d_lbu,
+                                    double *d_ubu, void *stream) {
+  if (n < 0 || steps < 1 || steps > B200QP_GAIT_SEQUENCE_SIZE || !d_period || !d_duty || !d_offset || !d_phase ||
+      !d_contact || ((d_lbu == nullptr) != (d_ubu == nullptr)))
+    return B200QP_ERR_ARG;
+  CK(launch_gait_schedule(n, steps, dt, d_period, d_duty, d_offset, d_phase, d_measured_contact, fmin, fmax, d_contact,
+                          d_swing_time, d_lbu, d_ubu, (cudaStream_t)stream));
+  return B200QP_OK;
+}
+
+int32_t b200qp_gait_schedule(int32_t device, int32_t n, int32_t steps, double dt, const double *period,
+                             const double *duty, const double *offset, const double *phase,
+                             const uint8_t *measured_contact, double fmin, double fmax, uint8_t *contact,
+                             double *swing_time, double *lbu, double *ubu) {
+  if (n < 0 || steps < 1 || steps > B200QP_GAIT_SEQUENCE_SIZE || !period || !duty || !offset || !phase || !contact ||
+      ((lbu == nullptr) != (ubu == nullptr)))
+    return B200QP_ERR_ARG;
+  if (n == 0) return B200QP_OK;
+  int ndev = 0;
+  CK(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) {
+    g_err = "b200qp_gait_schedule: no such CUDA device (there is no CPU fallback)";
+    return B200QP_ERR_CUDA;
+  }
+  CK(cudaSetDevice(device));
+  const size_t nn = (size_t)n;
+  double *d_per = nullptr, *d_duty = nullptr, *d_off = nullptr, *d_ph = nullptr, *d_sw = nullptr, *d_lb = nullptr,
+         *d_ub = nullptr;
+  uint8_t *d_meas = nullptr, *d_ct = nullptr;
+  int32_t rc = B200QP_OK;
+  cudaError_t e = cudaSuccess;
+#define TRY(x)                                   \
+  if (e == cudaSuccess) {                        \
+    e = (x);                                     \
+    if (e != cudaSuccess) set_err(#x, e);        \
+  }
+  TRY(cudaMalloc(&d_per, nn * 8));
+  TRY(cudaMalloc(&d_duty, nn * 32));
+  TRY(cudaMalloc(&d_off, nn * 32));
+  TRY(cudaMalloc(&d_ph, nn * 8));
+  TRY(cudaMalloc(&d_ct, nn * steps * 4));
+  if (measured_contact) TRY(cudaMalloc(&d_meas, nn * 4));
+  if (swing_time) TRY(cudaMalloc(&d_sw, nn * steps * 32));
+  if (lbu) {
+    TRY(cudaMalloc(&d_lb, nn * steps * 96));
+    TRY(cudaMalloc(&d_ub, nn * steps * 96));
+  }
+  TRY(cudaMemcpy(d_per, period, nn * 8, cudaMemcpyHostToDevice));
+  TRY(cudaMemcpy(d_duty, duty, nn * 32, cudaMemcpyHostToDevice));
+  TRY(cudaMemcpy(d_off, offset, nn * 32, cudaMemcpyHostToDevice));
+  TRY(cudaMemcpy(d_ph, phase, nn * 8, cudaMemcpyHostToDevice));
+  if (measured_contact) TRY(cudaMemcpy(d_meas, measured_contact, nn * 4, cudaMemcpyHostToDevice));
+  TRY(launch_gait_schedule(n, steps, dt, d_per, d_duty, d_off, d_ph, d_meas, fmin, fmax, d_ct, d_sw, d_lb, d_ub, 0));
+  TRY(cudaMemcpy(contact, d_ct, nn * steps * 4, cudaMemcpyDeviceToHost));
+  if (swing_time) TRY(cudaMemcpy(swing_time, d_sw, nn * steps * 32, cudaMemcpyDeviceToHost));
+  if (lbu) {
+    TRY(cudaMemcpy(lbu, d_lb, nn * steps * 96, cudaMemcpyDeviceToHost));
+    TRY(cudaMemcpy(ubu, d_ub, nn * steps * 96, cudaMemcpyDeviceToHost));
+  }
+#undef TRY
+  if (e != cudaSuccess) rc = B200QP_ERR_CUDA;
+  cudaFree(d_per);
+  cudaFree(d_duty);
+  cudaFree(d_off);
+  cudaFree(d_ph);
+  cudaFree(d_ct);
+  cudaFree(d_meas);
+  cudaFree(d_sw);
+  cudaFree(d_lb);
+  cudaFree(d_ub);
+  return rc;
+}
+
+}  // extern "C"

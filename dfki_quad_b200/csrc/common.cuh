@@ -1,0 +1,108 @@
+// Shared device helpers for the b200qp kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/b200qp.h"
+
+namespace b200qp {
+
+constexpr int NX = B200QP_NX;
+constexpr int NU = B200QP_NU;
+constexpr int MAXH = B200QP_MAX_HORIZON;
+constexpr double GRAVITY_CONSTANT = 9.8067;  // MPC::GRAVITY_CONSTANT, mpc.hpp:22
+
+// Kernel-side copy of b200qp_mpc_config (passed by value in the launch).
+struct MpcParams {
+  int N;
+  int in_stride;  // doubles per input record
+  double dt, alpha, w[12], mu, fmin, fmax;
+  double rho0, sigma, relax, eps, kkt_tol;
+  int max_iter, check_every, polish_rounds, ipm_max_iter;
+};
+
+struct MpcBuffers {
+  const double *in;        // [n][in_stride]
+  const uint8_t *contact;  // [n][N][4]
+  double *forces;          // [n][N][12]
+  double *xpred;           // [n][N+1][13]
+  b200qp_solver_info *info;
+  double *lam_box;  // [n][N][12] or nullptr
+  double *lam_g;    // [n][N][16] or nullptr
+  // work distribution
+  const int *bin_list;  // problem indices of this bin
+  const int *bin_count;
+  int *bin_next;     // atomic work counter
+  double *hscratch;  // [gridDim.x][BS*BS] condensed Hessian per resident block
+  // debug (parity hook)
+  int dbg_index;
+  double *dbg_H;
+  double *dbg_g;
+};
+
+// Eigen::Quaternion::toRotationMatrix for q = (x, y, z, w); R is row-major [3][3].
+__device__ __forceinline__ void quat_to_rot(const double *q, double R[3][3]) {
+  const double x = q[0], y = q[1], z = q[2], w = q[3];
+  const double tx = 2.0 * x, ty = 2.0 * y, tz = 2.0 * z;
+  const double twx = tx * w, twy = ty * w, twz = tz * w;
+  const double txx = tx * x, txy = ty * x, txz = tz * x;
+  const double tyy = ty * y, tyz = tz * y, tzz = tz * z;
+  R[0][0] = 1.0 - (tyy + tzz);
+  R[0][1] = txy - twz;
+  R[0][2] = txz + twy;
+  R[1][0] = txy + twz;
+  R[1][1] = 1.0 - (txx + tzz);
+  R[1][2] = tyz - twx;
+  R[2][0] = txz - twy;
+  R[2][1] = tyz + twx;
+  R[2][2] = 1.0 - (txx + tyy);
+}
+
+// matrix_to_euler, quaternion_operations.hpp:106-124 (same gimbal branches), returns roll, pitch, yaw.
+__device__ __forceinline__ void rot_to_euler(const double R[3][3], double e[3]) {
+  const double eps = 2.220446049250313e-16;
+  const double m20 = R[2][0];
+  const double pitch = -asin(m20);
+  double yaw, roll;
+  if ((1.0 - eps <= m20) && (m20 <= 1.0 + eps)) {
+    yaw = 0.0;
+    roll = atan2(-R[0][1], -R[0][2]);
+  } else if (m20 <= -1.0 + eps) {
+    yaw = 0.0;
+    roll = atan2(R[0][1], R[0][2]);
+  } else {
+    yaw = atan2(R[1][0], R[0][0]);
+    roll = atan2(R[2][1], R[2][2]);
+  }
+  e[0] = roll;
+  e[1] = pitch;
+  e[2] = yaw;
+}
+
+// max over the block of V values per thread; result valid in all threads. red must hold V * 32 doubles.
+template <int V>
+__device__ __forceinline__ void block_max(double (&v)[V], double *red) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+  for (int k = 0; k < V; ++k) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v[k] = fmax(v[k], __shfl_xor_sync(0xffffffffu, v[k], o));
+  }
+  __syncthreads();  // protect red from a previous use
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < V; ++k) red[k * 32 + warp] = v[k];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < V; ++k) {
+    double m = red[k * 32];
+    for (int wv = 1; wv < nw; ++wv) m = fmax(m, red[k * 32 + wv]);
+    v[k] = m;
+  }
+}
+
+// NaN-propagating abs-max helper: fmax drops NaNs, so NaN detection is done separately.
+__device__ __forceinline__ double absmax(double a, double b) { return fmax(fabs(a), fabs(b)); }
+
+}  // namespace b200qp

@@ -1,0 +1,1010 @@
+// Kernels K1 + K2a, fused: SRBD discretisation, condensed (stance-only) Hessian/gradient assembly, OSQP-style ADMM
+// with an explicit K^-1 in shared memory, null-space active-set polish, roll-out of the predicted states.
+// One thread block per problem, one thread per free force variable (FP64 throughout).
+//
+// Replaces, per problem: MPC::GetWrenchSequence (ws/src/controllers/src/mit_controller/mpc.cpp:329-470) =
+//   GetA/GetB/GetIWorld/GetUBounds (mpc.cpp:11-115) + acados condensing + OSQP behind ocp_qp_solve (mpc.cpp:410)
+//   + unpack of u_k / x_k (mpc.cpp:457-467).
+//
+// Math.  With M = A - I nilpotent the condensed Hessian has the closed form
+//   H[(j,f),(l,f')] = Bw_jf^T (cnt Qw + S2 dt^2 Rt^T Qth Rt) Bw_lf' + (dt/m)^2 diag(cnt Qv + S2 dt^2 Qp) + alpha I
+//   cnt = N - max(j,l),  S2 = sum_{t=max(j,l)}^{N-1} (t-j)(t-l),  Bw_kf = dt Iw_k^-1 skew(r_kf)
+// and g = B^T lambda with lambda the adjoint of the free response; swing-leg forces (pinned to 0 by
+// lbu = ubu = 0, mpc.cpp:110-113) are eliminated, which leaves the optimum unchanged.
+#include "common.cuh"
+
+namespace b200qp {
+
+// ---------------------------------------------------------------------------------------------------------------
+// per-foot constraint rows (reduced problem), in the order
+//   0: fx in [-fmax, fmax]   1: fy in [-fmax, fmax]   2: fz in [fmin, fmax]            (mpc.cpp:103-109)
+//   3: fx - mu fz <= 0       4: fx + mu fz >= 0       5: fy - mu fz <= 0   6: fy + mu fz >= 0   (mpc.cpp:66-92)
+// rows 3..6 are the reference's D rows 0..3 of that foot.
+constexpr double BIG = 1.0e300;
+
+__device__ __forceinline__ void foot_rows_eval(double fx, double fy, double fz, double mu, double (&ax)[7]) {
+  ax[0] = fx;
+  ax[1] = fy;
+  ax[2] = fz;
+  ax[3] = fx - mu * fz;
+  ax[4] = fx + mu * fz;
+  ax[5] = fy - mu * fz;
+  ax[6] = fy + mu * fz;
+}
+__device__ __forceinline__ void foot_row_vec(int r, double mu, double (&a)[3]) {
+  a[0] = (r == 0 || r == 3 || r == 4) ? 1.0 : 0.0;
+  a[1] = (r == 1 || r == 5 || r == 6) ? 1.0 : 0.0;
+  a[2] = (r == 2) ? 1.0 : ((r == 3 || r == 5) ? -mu : ((r == 4 || r == 6) ? mu : 0.0));
+}
+__device__ __forceinline__ void foot_bounds(double fmin, double fmax, double (&lo)[7], double (&hi)[7]) {
+  lo[0] = -fmax; hi[0] = fmax;
+  lo[1] = -fmax; hi[1] = fmax;
+  lo[2] = fmin;  hi[2] = fmax;
+  lo[3] = -BIG;  hi[3] = 0.0;
+  lo[4] = 0.0;   hi[4] = BIG;
+  lo[5] = -BIG;  hi[5] = 0.0;
+  lo[6] = 0.0;   hi[6] = BIG;
+}
+// (A^T w)_c for the variable with component c of a foot
+__device__ __forceinline__ double foot_at(int c, const double (&w)[7], double mu) {
+  return (c == 0) ? (w[0] + w[3] + w[4]) : (c == 1) ? (w[1] + w[5] + w[6]) : (w[2] + mu * ((w[4] - w[3]) + (w[6] - w[5])));
+}
+
+// Reduced row echelon form of the active rows of one foot: returns nz = 3 - rank, particular solution cf and
+// null-space basis Z (column q at Z[3q..3q+2]).
+__device__ int foot_nullspace(unsigned actl, unsigned actu, double mu, const double (&lo)[7], const double (&hi)[7],
+                              double (&cf)[3], double (&Z)[9]) {
+  double M[7][4];
+  int m = 0;
+  for (int r = 0; r < 7; ++r) {
+    const bool l = (actl >> r) & 1u, u = (actu >> r) & 1u;
+    if (l || u) {
+      double a[3];
+      foot_row_vec(r, mu, a);
+      M[m][0] = a[0];
+      M[m][1] = a[1];
+      M[m][2] = a[2];
+      M[m][3] = l ? lo[r] : hi[r];
+      ++m;
+    }
+  }
+  int piv[3];
+  int np = 0;
+  for (int col = 0; col < 3 && np < m; ++col) {
+    int p = np;
+    double best = fabs(M[np][col]);
+    for (int q = np + 1; q < m; ++q)
+      if (fabs(M[q][col]) > best) {
+        best = fabs(M[q][col]);
+        p = q;
+      }
+    if (best < 1e-12) continue;
+    for (int t = 0; t < 4; ++t) {
+      const double tmp = M[np][t];
+      M[np][t] = M[p][t];
+      M[p][t] = tmp;
+    }
+    const double inv = 1.0 / M[np][col];
+    for (int t = 0; t < 4; ++t) M[np][t] *= inv;
+    for (int q = 0; q < m; ++q)
+      if (q != np) {
+        const double f = M[q][col];
+        if (f != 0.0)
+          for (int t = 0; t < 4; ++t) M[q][t] -= f * M[np][t];
+      }
+    piv[np++] = col;
+  }
+  cf[0] = cf[1] = cf[2] = 0.0;
+  for (int i = 0; i < np; ++i) cf[piv[i]] = M[i][3];
+  int nz = 0;
+  for (int col = 0; col < 3; ++col) {
+    bool isp = false;
+    for (int i = 0; i < np; ++i) isp |= (piv[i] == col);
+    if (isp) continue;
+    double v[3] = {0.0, 0.0, 0.0};
+    v[col] = 1.0;
+    for (int i = 0; i < np; ++i) v[piv[i]] = -M[i][col];
+    Z[3 * nz + 0] = v[0];
+    Z[3 * nz + 1] = v[1];
+    Z[3 * nz + 2] = v[2];
+    ++nz;
+  }
+  return nz;
+}
+
+// Least squares on <= 3 columns (normal equations, Gaussian elimination with partial pivoting).
+__device__ bool ls_small(const double (*M)[3], const int *idx, int k, const double (&b)[3], double *s) {
+  double G[3][4];
+  for (int i = 0; i < k; ++i) {
+    for (int j = 0; j < k; ++j)
+      G[i][j] = M[idx[i]][0] * M[idx[j]][0] + M[idx[i]][1] * M[idx[j]][1] + M[idx[i]][2] * M[idx[j]][2];
+    G[i][3] = M[idx[i]][0] * b[0] + M[idx[i]][1] * b[1] + M[idx[i]][2] * b[2];
+  }
+  for (int col = 0; col < k; ++col) {
+    int p = col;
+    for (int q = col + 1; q < k; ++q)
+      if (fabs(G[q][col]) > fabs(G[p][col])) p = q;
+    if (fabs(G[p][col]) < 1e-14) return false;
+    if (p != col)
+      for (int t = 0; t < 4; ++t) {
+        const double tmp = G[col][t];
+        G[col][t] = G[p][t];
+        G[p][t] = tmp;
+      }
+    const double inv = 1.0 / G[col][col];
+    for (int q = 0; q < k; ++q)
+      if (q != col) {
+        const double f = G[q][col] * inv;
+        for (int t = col; t < 4; ++t) G[q][t] -= f * G[col][t];
+      }
+  }
+  for (int i = 0; i < k; ++i) s[i] = G[i][3] / G[i][i];
+  return true;
+}
+
+// Lawson-Hanson NNLS for min || M c - b ||, c >= 0, M = [3 x m] given as m columns.  Returns residual b - M c.
+__device__ void nnls3(const double (*M)[3], int m, const double (&b)[3], double *coef, double (&res)[3]) {
+  bool P[14], excl[14];
+  for (int j = 0; j < m; ++j) {
+    coef[j] = 0.0;
+    P[j] = false;
+    excl[j] = false;
+  }
+  const double bn = fmax(fmax(fabs(b[0]), fabs(b[1])), fabs(b[2]));
+  for (int outer = 0; outer < 3 * m + 6; ++outer) {
+    res[0] = b[0]; res[1] = b[1]; res[2] = b[2];
+    for (int j = 0; j < m; ++j)
+      if (coef[j] != 0.0) {
+        res[0] -= coef[j] * M[j][0];
+        res[1] -= coef[j] * M[j][1];
+        res[2] -= coef[j] * M[j][2];
+      }
+    int js = -1;
+    double wbest = 1e-13 * (bn + 1e-300);
+    int np = 0;
+    for (int j = 0; j < m; ++j) {
+      if (P[j]) {
+        ++np;
+        continue;
+      }
+      if (excl[j]) continue;
+      const double w = M[j][0] * res[0] + M[j][1] * res[1] + M[j][2] * res[2];
+      if (w > wbest) {
+        wbest = w;
+        js = j;
+      }
+    }
+    if (js < 0 || np >= 3) break;
+    P[js] = true;
+    for (int inner = 0; inner < 8; ++inner) {
+      int idx[3];
+      int k = 0;
+      for (int j = 0; j < m && k < 3; ++j)
+        if (P[j]) idx[k++] = j;
+      double s[3];
+      if (k == 0) break;
+      if (!ls_small(M, idx, k, b, s)) {  // dependent column: drop the newest one and stop
+        P[js] = false;
+        excl[js] = true;
+        break;
+      }
+      bool allpos = true;
+      for (int i = 0; i < k; ++i) allpos &= (s[i] > 0.0);
+      if (allpos) {
+        for (int i = 0; i < k; ++i) coef[idx[i]] = s[i];
+        break;
+      }
+      double al = 1.0;
+      for (int i = 0; i < k; ++i)
+        if (s[i] <= 0.0) {
+          const double d = coef[idx[i]] - s[i];
+          if (d > 0.0) al = fmin(al, coef[idx[i]] / d);
+          else al = 0.0;
+        }
+      for (int i = 0; i < k; ++i) {
+        coef[idx[i]] += al * (s[i] - coef[idx[i]]);
+        if (coef[idx[i]] <= 1e-300 || (s[i] <= 0.0 && coef[idx[i]] <= 1e-14 * (bn + 1.0))) {
+          coef[idx[i]] = 0.0;
+          P[idx[i]] = false;
+        }
+      }
+    }
+  }
+  res[0] = b[0]; res[1] = b[1]; res[2] = b[2];
+  for (int j = 0; j < m; ++j)
+    if (coef[j] != 0.0) {
+      res[0] -= coef[j] * M[j][0];
+      res[1] -= coef[j] * M[j][1];
+      res[2] -= coef[j] * M[j][2];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// dense helpers on the shared-memory matrix K (column-major, odd leading dimension LD => row and column
+// accesses across a warp are both bank-conflict free for 8-byte words)
+
+// in-place Gauss-Jordan inverse of an SPD matrix (no pivoting), thread i owns row i.
+template <int LD>
+__device__ __forceinline__ void gj_invert(double *K, int n, double *prow) {
+  const int i = threadIdx.x;
+  for (int p = 0; p < n; ++p) {
+    if (i < n) prow[i] = K[i * LD + p];  // pivot row element (p, i)
+    __syncthreads();
+    if (i < n) {
+      const double d = 1.0 / prow[p];
+      if (i == p) {
+        for (int j = 0; j < n; ++j) K[j * LD + p] = prow[j] * d;
+        K[p * LD + p] = d;
+      } else {
+        const double f = K[p * LD + i] * d;
+        int j = 0;
+        for (; j + 1 < n; j += 2) {
+          const double2 pr = *reinterpret_cast<const double2 *>(prow + j);
+          K[j * LD + i] = fma(-f, pr.x, K[j * LD + i]);
+          K[(j + 1) * LD + i] = fma(-f, pr.y, K[(j + 1) * LD + i]);
+        }
+        if (j < n) K[j * LD + i] = fma(-f, prow[j], K[j * LD + i]);
+        K[p * LD + i] = -f;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+template <int LD>
+__device__ __forceinline__ double matvec_smem(const double *K, int n, const double *v) {
+  const int i = threadIdx.x;
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+  int j = 0;
+  for (; j + 3 < n; j += 4) {
+    const double2 v01 = *reinterpret_cast<const double2 *>(v + j);
+    const double2 v23 = *reinterpret_cast<const double2 *>(v + j + 2);
+    a0 = fma(K[j * LD + i], v01.x, a0);
+    a1 = fma(K[(j + 1) * LD + i], v01.y, a1);
+    a2 = fma(K[(j + 2) * LD + i], v23.x, a2);
+    a3 = fma(K[(j + 3) * LD + i], v23.y, a3);
+  }
+  for (; j < n; ++j) a0 = fma(K[j * LD + i], v[j], a0);
+  return (a0 + a1) + (a2 + a3);
+}
+
+// y_i = sum_j Hs(i,j) v_j with Hs in global memory (column-major, leading dimension BS; coalesced over i)
+template <int BS>
+__device__ __forceinline__ double matvec_glob(const double *__restrict__ Hs, int n, const double *v) {
+  const int i = threadIdx.x;
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+  int j = 0;
+  for (; j + 3 < n; j += 4) {
+    const double h0 = Hs[j * BS + i], h1 = Hs[(j + 1) * BS + i], h2 = Hs[(j + 2) * BS + i], h3 = Hs[(j + 3) * BS + i];
+    a0 = fma(h0, v[j], a0);
+    a1 = fma(h1, v[j + 1], a1);
+    a2 = fma(h2, v[j + 2], a2);
+    a3 = fma(h3, v[j + 3], a3);
+  }
+  for (; j < n; ++j) a0 = fma(Hs[j * BS + i], v[j], a0);
+  return (a0 + a1) + (a2 + a3);
+}
+
+// S2(j,l) = sum_{t=m}^{N-1} (t-j)(t-l), m = max(j,l); cnt = N - m
+__device__ __forceinline__ void horizon_sums(int N, int j, int l, double &cnt, double &S2) {
+  const int m = j > l ? j : l;
+  const int c = N - m;
+  // sum t, sum t^2 for t = m..N-1
+  const long long a = m, b = N - 1;
+  const long long st = (b * (b + 1) - (a - 1) * a) / 2;
+  const long long st2 = (b * (b + 1) * (2 * b + 1) - (a - 1) * a * (2 * a - 1)) / 6;
+  cnt = (double)c;
+  S2 = (double)(st2 - (long long)(j + l) * st + (long long)j * l * c);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// BS = threads per block (multiple of 32), NV = largest reduced problem the instantiation accepts (even, <= BS)
+template <int BS, int NV>
+__global__ void __launch_bounds__(BS) mpc_admm_kernel(const MpcParams P, const MpcBuffers B) {
+  constexpr int LD = NV + 1;
+  constexpr int MAXF = NV / 3 + 1;
+  extern __shared__ __align__(16) double smem[];
+  double *K = smem;                 // [NV * LD]
+  double *s_g = K + NV * LD;        // [BS] gradient
+  double *s_v = s_g + BS;           // [BS] rhs / x broadcast buffer
+  double *s_xt = s_v + BS;          // [BS]
+  double *s_r = s_xt + BS;          // [BS] H x + g
+  double *s_c = s_r + BS;           // [BS] particular solution of the polish
+  double *s_w = s_c + BS;           // [BS] reduced solution
+  double *prow = s_w + BS;          // [BS] pivot row
+  double *red = prow + BS;          // [4 * 32]
+  __shared__ double s_Bw[MAXH * 36];       // Bw_kf, row-major 3x3 per (k,f); zero for swing feet
+  __shared__ double s_lw[(MAXH + 2) * 3];  // adjoint, angular-velocity part, per stage
+  __shared__ double s_lv[(MAXH + 2) * 3];  // adjoint, linear-velocity part
+  __shared__ double s_qe[(MAXH + 1) * 12]; // Q e_k (free-response error), later reused for suffix sums
+  __shared__ double s_yawd[MAXH + 1];
+  __shared__ double s_x0[13];
+  __shared__ double s_Rt[9];   // Rt(psi0) row-major
+  __shared__ double s_G2[9];   // dt^2 Rt^T Qth Rt
+  __shared__ double s_fZ[MAXF * 9];
+  __shared__ double s_fc[MAXF * 3];
+  __shared__ double s_bw[MAXH * 6];  // per-stage input effect on (omega, v) for the roll-out
+  __shared__ double s_X[(MAXH + 1) * 13];
+  __shared__ short s_fidx[MAXH * 4];  // (k,f) -> free foot index or -1
+  __shared__ unsigned char s_fk[MAXF], s_ff[MAXF], s_fnz[MAXF];
+  __shared__ short s_foff[MAXF + 1];
+  __shared__ short s_rfoot[BS];
+  __shared__ unsigned char s_rk[BS];
+  __shared__ unsigned short s_actl[MAXF], s_actu[MAXF];
+  __shared__ int s_slot, s_nf, s_changed;
+  __shared__ double s_psi0;
+
+  const int tid = threadIdx.x;
+  const int N = P.N;
+  const double dt = P.dt, mu = P.mu;
+  double *Hs = B.hscratch + (size_t)blockIdx.x * BS * BS;
+  double lo[7], hi[7];
+  foot_bounds(P.fmin, P.fmax, lo, hi);
+
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) s_slot = atomicAdd(B.bin_next, 1);
+    __syncthreads();
+    const int slot = s_slot;
+    if (slot >= *B.bin_count) break;
+    const int prob = B.bin_list[slot];
+    const double *rec = B.in + (size_t)prob * P.in_stride;
+    const uint8_t *ct = B.contact + (size_t)prob * N * 4;
+    const double mass = rec[13];
+
+    // ---- phase 0: per-stage quantities -------------------------------------------------------------------
+    if (tid <= N) {
+      double R[3][3];
+      quat_to_rot(rec + 26 + 13 * tid, R);
+      s_yawd[tid] = atan2(R[1][0], R[0][0]);  // yaw_from_quaternion (quaternion_operations.hpp:136-141)
+    }
+    if (tid == 32) {
+      double R[3][3], e[3];
+      quat_to_rot(rec, R);
+      rot_to_euler(R, e);
+      s_x0[0] = e[0]; s_x0[1] = e[1]; s_x0[2] = e[2];
+      for (int c = 0; c < 3; ++c) {
+        s_x0[3 + c] = rec[4 + c] + rec[23 + c];
+        s_x0[6 + c] = rec[7 + c];
+        s_x0[9 + c] = rec[10 + c];
+      }
+      s_x0[12] = GRAVITY_CONSTANT;
+      const double psi0 = atan2(R[1][0], R[0][0]);
+      const double cs = cos(psi0), sn = sin(psi0);
+      // MPC::GetR (mpc.cpp:46-58)
+      s_Rt[0] = cs; s_Rt[1] = sn; s_Rt[2] = 0.0;
+      s_Rt[3] = -sn; s_Rt[4] = cs; s_Rt[5] = 0.0;
+      s_Rt[6] = 0.0; s_Rt[7] = 0.0; s_Rt[8] = 1.0;
+      // G2 = dt^2 Rt^T diag(qth) Rt
+      for (int a = 0; a < 3; ++a)
+        for (int b = 0; b < 3; ++b) {
+          double s = 0.0;
+          for (int d = 0; d < 3; ++d) s += s_Rt[3 * d + a] * P.w[d] * s_Rt[3 * d + b];
+          s_G2[3 * a + b] = dt * dt * s;
+        }
+      s_psi0 = psi0;
+    }
+    // free-variable list (warp 0): ordered by (stage, leg)
+    if (tid < 32) {
+      int base = 0;
+      for (int e0 = 0; e0 < 4 * N; e0 += 32) {
+        const int e = e0 + tid;
+        const bool on = (e < 4 * N) && (ct[e] != 0);
+        const unsigned bal = __ballot_sync(0xffffffffu, on);
+        const int pos = base + __popc(bal & ((1u << tid) - 1u));
+        if (e < 4 * N) s_fidx[e] = on ? (short)pos : (short)-1;
+        if (on && pos < MAXF) {
+          s_fk[pos] = (unsigned char)(e >> 2);
+          s_ff[pos] = (unsigned char)(e & 3);
+        }
+        base += __popc(bal);
+      }
+      if (tid == 0) s_nf = base;
+    }
+    __syncthreads();
+    const int nf = s_nf;
+    const int n = 3 * nf;
+    if (tid == 0) {  // sequential yaw unwrap (mpc.cpp:334-344)
+      double before = s_psi0;
+      for (int k = 0; k <= N; ++k) {
+        double y = s_yawd[k];
+        const double diff = y - before;
+        if (diff < -M_PI) y += 2 * M_PI;
+        else if (diff > M_PI) y -= 2 * M_PI;
+        before = y;
+        s_yawd[k] = y;
+      }
+    }
+    __syncthreads();
+    if (n > NV) {  // cannot happen after binning; defensive
+      if (tid == 0) {
+        b200qp_solver_info inf = {B200QP_ACADOS_QP_FAILURE, 0, 0, n, {0, 0, 0, 0}};
+        B.info[prob] = inf;
+      }
+      continue;
+    }
+    if (tid < N) {
+      // MPC::GetB rotational block (mpc.cpp:33-43): Bw = Iw^-1 skew(r) dt, Iw = Rt I Rt^T (mpc.cpp:60-64)
+      const int k = tid;
+      const double psi = s_yawd[k];
+      const double cs = cos(psi), sn = sin(psi);
+      const double Rt[3][3] = {{cs, sn, 0.0}, {-sn, cs, 0.0}, {0.0, 0.0, 1.0}};
+      double Ib[3][3], T[3][3], Iw[3][3];
+      for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) Ib[r][c] = rec[14 + 3 * c + r];
+      for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) T[r][c] = Rt[r][0] * Ib[0][c] + Rt[r][1] * Ib[1][c] + Rt[r][2] * Ib[2][c];
+      for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) Iw[r][c] = T[r][0] * Rt[c][0] + T[r][1] * Rt[c][1] + T[r][2] * Rt[c][2];
+      const double c00 = Iw[1][1] * Iw[2][2] - Iw[1][2] * Iw[2][1];
+      const double c01 = Iw[1][2] * Iw[2][0] - Iw[1][0] * Iw[2][2];
+      const double c02 = Iw[1][0] * Iw[2][1] - Iw[1][1] * Iw[2][0];
+      const double det = Iw[0][0] * c00 + Iw[0][1] * c01 + Iw[0][2] * c02;
+      const double id = 1.0 / det;
+      double Ii[3][3];
+      Ii[0][0] = c00 * id;
+      Ii[0][1] = (Iw[0][2] * Iw[2][1] - Iw[0][1] * Iw[2][2]) * id;
+      Ii[0][2] = (Iw[0][1] * Iw[1][2] - Iw[0][2] * Iw[1][1]) * id;
+      Ii[1][0] = c01 * id;
+      Ii[1][1] = (Iw[0][0] * Iw[2][2] - Iw[0][2] * Iw[2][0]) * id;
+      Ii[1][2] = (Iw[0][2] * Iw[1][0] - Iw[0][0] * Iw[1][2]) * id;
+      Ii[2][0] = c02 * id;
+      Ii[2][1] = (Iw[0][1] * Iw[2][0] - Iw[0][0] * Iw[2][1]) * id;
+      Ii[2][2] = (Iw[0][0] * Iw[1][1] - Iw[0][1] * Iw[1][0]) * id;
+      const double *dp = rec + 26 + 13 * k + 4;  // desired position
+      const double *fp = rec + 26 + 13 * (N + 1) + 12 * k;
+      for (int f = 0; f < 4; ++f) {
+        double *Bw = s_Bw + (k * 4 + f) * 9;
+        if (ct[k * 4 + f]) {
+          const double rx = fp[3 * f + 0] - (dp[0] + rec[23]);
+          const double ry = fp[3 * f + 1] - (dp[1] + rec[24]);
+          const double rz = fp[3 * f + 2] - (dp[2] + rec[25]);
+          const double S[3][3] = {{0.0, -rz, ry}, {rz, 0.0, -rx}, {-ry, rx, 0.0}};
+          for (int r = 0; r < 3; ++r)
+            for (int c = 0; c < 3; ++c)
+              Bw[3 * r + c] = (Ii[r][0] * S[0][c] + Ii[r][1] * S[1][c] + Ii[r][2] * S[2][c]) * dt;
+        } else {
+          for (int t = 0; t < 9; ++t) Bw[t] = 0.0;
+        }
+      }
+    }
+    // free-response error e_k = A^k x0 - xref_k (closed form), k = 1..N, times Q  (mpc.cpp:372-381)
+    if (tid >= 32 && tid - 32 < N) {
+      const int k = tid - 32 + 1;
+      double R[3][3], e[3];
+      quat_to_rot(rec + 26 + 13 * k, R);
+      rot_to_euler(R, e);
+      e[2] = s_yawd[k];
+      const double *st = rec + 26 + 13 * k;
+      const double kd = (double)k;
+      const double w0 = s_x0[6], w1 = s_x0[7], w2 = s_x0[8];
+      double *qe = s_qe + 12 * k;
+      for (int c = 0; c < 3; ++c) {
+        const double th = s_x0[c] + kd * dt * (s_Rt[3 * c] * w0 + s_Rt[3 * c + 1] * w1 + s_Rt[3 * c + 2] * w2);
+        qe[c] = P.w[c] * (th - e[c]);
+        double pp = s_x0[3 + c] + kd * dt * s_x0[9 + c];
+        double vv = s_x0[9 + c];
+        if (c == 2) {
+          pp -= 0.5 * kd * (kd - 1.0) * dt * dt * s_x0[12];
+          vv -= kd * dt * s_x0[12];
+        }
+        qe[3 + c] = P.w[3 + c] * (pp - (st[4 + c] + rec[23 + c]));
+        qe[6 + c] = P.w[6 + c] * (s_x0[6 + c] - st[7 + c]);
+        qe[9 + c] = P.w[9 + c] * (vv - st[10 + c]);
+      }
+    }
+    __syncthreads();
+    // adjoint recursion (component-wise suffix sums), lambda_k for k = 1..N
+    if (tid < 6) {
+      // tid 0..2: theta/omega chain component, 3..5: p/v chain component
+      const int c = tid % 3;
+      const bool lin = tid >= 3;
+      double sA = 0.0;  // suffix sum of Q e^theta (or Q e^p)
+      double ssA = 0.0; // sum_{i>k} sA_i
+      double sB = 0.0;  // suffix sum of Q e^omega (or Q e^v)
+      for (int k = N; k >= 1; --k) {
+        ssA += sA;  // now sum over i > k of sA_i
+        sA += s_qe[12 * k + (lin ? 3 : 0) + c];
+        sB += s_qe[12 * k + (lin ? 9 : 6) + c];
+        if (lin) {
+          s_lv[3 * k + c] = sB + dt * ssA;
+        } else {
+          s_lw[3 * k + c] = sB;       // Rt^T (dt ssTheta) added below
+          s_qe[12 * k + c] = ssA;      // reuse slot: ssTheta_k[c]
+        }
+      }
+    }
+    __syncthreads();
+    if (tid < N) {
+      const int k = tid + 1;
+      const double a0 = s_qe[12 * k], a1 = s_qe[12 * k + 1], a2 = s_qe[12 * k + 2];
+      for (int c = 0; c < 3; ++c) s_lw[3 * k + c] += dt * (s_Rt[c] * a0 + s_Rt[3 + c] * a1 + s_Rt[6 + c] * a2);
+    }
+    __syncthreads();
+
+    // ---- phase 1: condensed reduced Hessian and gradient (K1) ------------------------------------------------
+    const bool act = tid < n;
+    const int fa = act ? tid / 3 : 0;
+    const int ca = tid - 3 * fa;
+    double gi = 0.0;
+    if (act) {
+      const int j = s_fk[fa], f = s_ff[fa];
+      const double *Bwa = s_Bw + (j * 4 + f) * 9;
+      double pa[3], pb[3];
+      for (int e = 0; e < 3; ++e) {
+        pa[e] = Bwa[3 * e + ca] * P.w[6 + e];
+        pb[e] = Bwa[ca] * s_G2[e] + Bwa[3 + ca] * s_G2[3 + e] + Bwa[6 + ca] * s_G2[6 + e];
+      }
+      const double dm = dt / mass;
+      const double lv = dm * dm * P.w[9 + ca], lp = dm * dm * dt * dt * P.w[3 + ca];
+      for (int b = 0; b < nf; ++b) {
+        const int l = s_fk[b], f2 = s_ff[b];
+        double cnt, S2;
+        horizon_sums(N, j, l, cnt, S2);
+        const double v0 = cnt * pa[0] + S2 * pb[0], v1 = cnt * pa[1] + S2 * pb[1], v2 = cnt * pa[2] + S2 * pb[2];
+        const double *Bwb = s_Bw + (l * 4 + f2) * 9;
+        double h[3];
+        for (int cc = 0; cc < 3; ++cc) h[cc] = v0 * Bwb[cc] + v1 * Bwb[3 + cc] + v2 * Bwb[6 + cc];
+        h[ca] += cnt * lv + S2 * lp;
+        if (b == fa) h[ca] += P.alpha;
+        for (int cc = 0; cc < 3; ++cc) {
+          K[(3 * b + cc) * LD + tid] = h[cc];
+          Hs[(3 * b + cc) * BS + tid] = h[cc];
+        }
+      }
+      gi = Bwa[ca] * s_lw[3 * (j + 1)] + Bwa[3 + ca] * s_lw[3 * (j + 1) + 1] + Bwa[6 + ca] * s_lw[3 * (j + 1) + 2] +
+           dm * s_lv[3 * (j + 1) + ca];
+      s_g[tid] = gi;
+    }
+    __syncthreads();
+    if (prob == B.dbg_index && B.dbg_H != nullptr) {
+      if (act) {
+        for (int jx = 0; jx < n; ++jx) B.dbg_H[(size_t)jx * n + tid] = K[jx * LD + tid];
+        B.dbg_g[tid] = gi;
+      }
+    }
+
+    // ---- phase 2: ADMM (K2a) -------------------------------------------------------------------------------------
+    const double Ei = (ca == 2) ? (1.0 + 4.0 * mu * mu) : 3.0;  // diag(A^T A)
+    double rho = P.rho0;
+    const double sigma = P.sigma, relax = P.relax;
+    double x = 0.0;
+    double z[7], y[7];
+#pragma unroll
+    for (int r = 0; r < 7; ++r) {
+      z[r] = fmin(fmax(0.0, lo[r]), hi[r]);
+      y[r] = 0.0;
+    }
+    int iters = 0, rounds_total = 0, status = B200QP_ACADOS_MAXITER;
+    double eps = P.eps;
+    double kkt_stat = 0.0, kkt_ineq = 0.0, kkt_comp = 0.0;
+    double ysol[7] = {0, 0, 0, 0, 0, 0, 0};
+    double xsol = 0.0;
+    bool need_factor = true;
+
+    if (n == 0) status = B200QP_ACADOS_SUCCESS;
+    for (int attempt = 0; attempt < 5 && status != B200QP_ACADOS_SUCCESS && n > 0; ++attempt) {
+      // (re)build K^-1 from the Hessian scratch when needed
+      bool admm_done = false;
+      while (!admm_done) {
+        if (need_factor) {
+          __syncthreads();
+          if (act)
+            for (int jx = 0; jx < n; ++jx) {
+              double h = Hs[jx * BS + tid];
+              if (jx == tid) h += sigma + rho * Ei;
+              K[jx * LD + tid] = h;
+            }
+          __syncthreads();
+          gj_invert<LD>(K, n, prow);
+          need_factor = false;
+        }
+        const double rinv = 1.0 / rho;
+        int it_block = 0;
+        for (; it_block < P.check_every && iters < P.max_iter; ++it_block, ++iters) {
+          if (act) {
+            double w[7];
+#pragma unroll
+            for (int r = 0; r < 7; ++r) w[r] = rho * z[r] - y[r];
+            s_v[tid] = sigma * x - gi + foot_at(ca, w, mu);
+          }
+          __syncthreads();
+          double xt = 0.0;
+          if (act) {
+            xt = matvec_smem<LD>(K, n, s_v);
+            s_xt[tid] = xt;
+          }
+          __syncthreads();
+          if (act) {
+            double zt[7];
+            foot_rows_eval(s_xt[3 * fa], s_xt[3 * fa + 1], s_xt[3 * fa + 2], mu, zt);
+            x = relax * xt + (1.0 - relax) * x;
+#pragma unroll
+            for (int r = 0; r < 7; ++r) {
+              const double zr = relax * zt[r] + (1.0 - relax) * z[r];
+              const double zn = fmin(fmax(zr + y[r] * rinv, lo[r]), hi[r]);
+              y[r] += rho * (zr - zn);
+              z[r] = zn;
+            }
+          }
+        }
+        // residuals (OSQP termination test) on the true H
+        __syncthreads();
+        if (act) s_v[tid] = x;
+        __syncthreads();
+        double nrm[4] = {0.0, 0.0, 0.0, 0.0};
+        bool bad = false;
+        if (act) {
+          double ax[7];
+          foot_rows_eval(s_v[3 * fa], s_v[3 * fa + 1], s_v[3 * fa + 2], mu, ax);
+          const double hx = matvec_glob<BS>(Hs, n, s_v);
+          const double aty = foot_at(ca, y, mu);
+#pragma unroll
+          for (int r = 0; r < 7; ++r) {
+            nrm[0] = fmax(nrm[0], fabs(ax[r] - z[r]));
+            nrm[2] = fmax(nrm[2], absmax(ax[r], z[r]));
+          }
+          const double rd = hx + gi + aty;
+          nrm[1] = fabs(rd);
+          nrm[3] = fmax(absmax(hx, aty), fabs(gi));
+          bad = !(fabs(rd) < BIG) || !(fabs(x) < BIG);
+        }
+        const int anybad = __syncthreads_or(bad ? 1 : 0);
+        block_max<4>(nrm, red);
+        if (anybad) {
+          status = B200QP_ACADOS_NAN_DETECTED;
+          admm_done = true;
+          break;
+        }
+        const bool conv = (nrm[0] <= eps * (1.0 + nrm[2])) && (nrm[1] <= eps * (1.0 + nrm[3]));
+        if (conv || iters >= P.max_iter) {
+          admm_done = true;
+        } else {
+          // residual-balancing rho update (OSQP adaptive rho), refactor only on a factor-5 change
+          const double num = nrm[0] / fmax(nrm[2], 1e-30), den = nrm[1] / fmax(nrm[3], 1e-30);
+          double nr = rho * sqrt(num / fmax(den, 1e-30));
+          nr = fmin(fmax(nr, 1e-6), 1e6);
+          if (nr > 5.0 * rho || nr < 0.2 * rho) {
+            rho = nr;
+            need_factor = true;
+          }
+        }
+      }
+      if (status == B200QP_ACADOS_NAN_DETECTED) break;
+
+      // ---- phase 3: polish = primal-dual active-set sweeps in the null space of the active rows --------------
+      if (act && ca == 2) {
+        unsigned al = 0, au = 0;
+#pragma unroll
+        for (int r = 0; r < 7; ++r) {  // OSQP polish rule: lower-active if z - l < -y, upper-active if u - z < y
+          if (lo[r] > -BIG && (z[r] - lo[r]) < -y[r]) al |= 1u << r;
+          else if (hi[r] < BIG && (hi[r] - z[r]) < y[r]) au |= 1u << r;
+        }
+        s_actl[fa] = (unsigned short)al;
+        s_actu[fa] = (unsigned short)au;
+      }
+      bool accepted = false;
+      for (int round = 0; round < P.polish_rounds && !accepted; ++round) {
+        ++rounds_total;
+        __syncthreads();
+        if (act && ca == 2) {
+          double cf[3], Z[9];
+          const int nz = foot_nullspace(s_actl[fa], s_actu[fa], mu, lo, hi, cf, Z);
+          s_fnz[fa] = (unsigned char)nz;
+          for (int t = 0; t < 3; ++t) s_fc[3 * fa + t] = cf[t];
+          for (int t = 0; t < 3 * nz; ++t) s_fZ[9 * fa + t] = Z[t];
+        }
+        __syncthreads();
+        if (tid == 0) {
+          int off = 0;
+          for (int f = 0; f < nf; ++f) {
+            s_foff[f] = (short)off;
+            for (int q = 0; q < s_fnz[f]; ++q) {
+              s_rfoot[off + q] = (short)f;
+              s_rk[off + q] = (unsigned char)q;
+            }
+            off += s_fnz[f];
+          }
+          s_foff[nf] = (short)off;
+          s_changed = 0;
+        }
+        if (act) s_c[tid] = s_fc[tid];
+        __syncthreads();
+        const int nr = s_foff[nf];
+        // hc = H c + g
+        if (act) s_r[tid] = matvec_glob<BS>(Hs, n, s_c) + gi;
+        // reduced Hessian Hr = Z^T H Z into K
+        double vp[3] = {0, 0, 0};
+        int ap = 0;
+        if (tid < nr) {
+          ap = s_rfoot[tid];
+          const int kq = s_rk[tid];
+          vp[0] = s_fZ[9 * ap + 3 * kq];
+          vp[1] = s_fZ[9 * ap + 3 * kq + 1];
+          vp[2] = s_fZ[9 * ap + 3 * kq + 2];
+          for (int q = 0; q < nr; ++q) {
+            const int bq = s_rfoot[q];
+            const double *vq = s_fZ + 9 * bq + 3 * s_rk[q];
+            double acc = 0.0;
+#pragma unroll
+            for (int c2 = 0; c2 < 3; ++c2) {
+              const double *col = Hs + (size_t)(3 * bq + c2) * BS + 3 * ap;
+              acc += vq[c2] * (vp[0] * col[0] + vp[1] * col[1] + vp[2] * col[2]);
+            }
+            K[q * LD + tid] = acc;
+          }
+        }
+        __syncthreads();
+        double grp = 0.0;
+        if (tid < nr) grp = vp[0] * s_r[3 * ap] + vp[1] * s_r[3 * ap + 1] + vp[2] * s_r[3 * ap + 2];
+        gj_invert<LD>(K, nr, prow);
+        if (tid < nr) s_v[tid] = -grp;
+        __syncthreads();
+        double wred = 0.0;
+        if (tid < nr) wred = matvec_smem<LD>(K, nr, s_v);
+        double xn = 0.0;
+        for (int refine = 0; refine < 2; ++refine) {
+          __syncthreads();
+          if (tid < nr) s_w[tid] = wred;
+          __syncthreads();
+          if (act) {
+            xn = s_c[tid];
+            const int o = s_foff[fa];
+            for (int q = 0; q < s_fnz[fa]; ++q) xn += s_fZ[9 * fa + 3 * q + ca] * s_w[o + q];
+            s_xt[tid] = xn;
+          }
+          __syncthreads();
+          if (act) s_r[tid] = matvec_glob<BS>(Hs, n, s_xt) + gi;  // r = H x + g
+          __syncthreads();
+          if (refine == 0) {  // one step of iterative refinement on the reduced system
+            if (tid < nr) s_v[tid] = -(vp[0] * s_r[3 * ap] + vp[1] * s_r[3 * ap + 1] + vp[2] * s_r[3 * ap + 2]);
+            __syncthreads();
+            if (tid < nr) wred += matvec_smem<LD>(K, nr, s_v);
+          }
+        }
+        // per-foot optimality check: feasibility, NNLS duals over the geometrically tight rows, new active set
+        double chk[3] = {0.0, 0.0, 0.0};  // stat, viol, comp
+        bool bad = false;
+        double ynew[7] = {0, 0, 0, 0, 0, 0, 0};
+        if (act && ca == 2) {
+          const double fx = s_xt[3 * fa], fy = s_xt[3 * fa + 1], fz = s_xt[3 * fa + 2];
+          double ax[7];
+          foot_rows_eval(fx, fy, fz, mu, ax);
+          const double sc = fmax(1.0, fmax(fabs(fx), fmax(fabs(fy), fabs(fz))));
+          const double ttol = 1e-9 * sc;
+          double Mc[14][3];
+          int tagr[14];
+          int m = 0;
+          unsigned nl = 0, nu = 0;
+          for (int r = 0; r < 7; ++r) {
+            double a[3];
+            foot_row_vec(r, mu, a);
+            if (lo[r] > -BIG) {
+              const double s = ax[r] - lo[r];
+              if (s < -ttol) nl |= 1u << r;
+              chk[1] = fmax(chk[1], -s);
+              if (fabs(s) <= ttol) {
+                Mc[m][0] = -a[0]; Mc[m][1] = -a[1]; Mc[m][2] = -a[2];
+                tagr[m++] = -(r + 1);
+              }
+            }
+            if (hi[r] < BIG) {
+              const double s = hi[r] - ax[r];
+              if (s < -ttol) nu |= 1u << r;
+              chk[1] = fmax(chk[1], -s);
+              if (fabs(s) <= ttol) {
+                Mc[m][0] = a[0]; Mc[m][1] = a[1]; Mc[m][2] = a[2];
+                tagr[m++] = (r + 1);
+              }
+            }
+          }
+          const double b3[3] = {-s_r[3 * fa], -s_r[3 * fa + 1], -s_r[3 * fa + 2]};
+          double coef[14], res[3] = {b3[0], b3[1], b3[2]};
+          if (m > 0) nnls3(Mc, m, b3, coef, res);
+          chk[0] = fmax(fabs(res[0]), fmax(fabs(res[1]), fabs(res[2])));
+          bad = !(chk[0] < BIG) || !(sc < BIG);
+          for (int q = 0; q < m; ++q)
+            if (coef[q] > 0.0) {
+              const int r = (tagr[q] > 0 ? tagr[q] : -tagr[q]) - 1;
+              if (tagr[q] > 0) {
+                nu |= 1u << r;
+                ynew[r] += coef[q];
+                chk[2] = fmax(chk[2], coef[q] * fabs(hi[r] - ax[r]));
+              } else {
+                nl |= 1u << r;
+                ynew[r] -= coef[q];
+                chk[2] = fmax(chk[2], coef[q] * fabs(ax[r] - lo[r]));
+              }
+            }
+          if (nl != s_actl[fa] || nu != s_actu[fa]) s_changed = 1;
+          s_actl[fa] = (unsigned short)nl;
+          s_actu[fa] = (unsigned short)nu;
+        }
+        const int anybad = __syncthreads_or(bad ? 1 : 0);
+        block_max<3>(chk, red);
+        if (anybad) break;
+        if (chk[0] <= P.kkt_tol && chk[1] <= P.kkt_tol && chk[2] <= P.kkt_tol) {
+          accepted = true;
+          kkt_stat = chk[0];
+          kkt_ineq = chk[1];
+          kkt_comp = chk[2];
+          xsol = xn;
+#pragma unroll
+          for (int r = 0; r < 7; ++r) ysol[r] = ynew[r];
+        } else if (!s_changed) {
+          break;  // active set is a fixed point but not optimal to tolerance: go back to ADMM
+        }
+      }
+      if (accepted) {
+        status = B200QP_ACADOS_SUCCESS;
+      } else {
+        if (iters >= P.max_iter) break;
+        eps *= 0.1;
+        need_factor = true;  // K was overwritten by the polish
+      }
+    }
+
+    // ---- phase 4: outputs -------------------------------------------------------------------------------------
+    __syncthreads();
+    if (status == B200QP_ACADOS_SUCCESS) {
+      if (act) s_xt[tid] = xsol;
+      __syncthreads();
+      double *fo = B.forces + (size_t)prob * N * 12;
+      for (int e = tid; e < N * 12; e += BS) {
+        const int kf = e / 3, c = e - 3 * kf;
+        const int fi = s_fidx[kf];
+        fo[e] = (fi >= 0) ? s_xt[3 * fi + c] : 0.0;
+      }
+      if (B.lam_box != nullptr) {
+        double *lb = B.lam_box + (size_t)prob * N * 12;
+        double *lg = B.lam_g + (size_t)prob * N * 16;
+        for (int e = tid; e < N * 12; e += BS)
+          if (s_fidx[e / 3] < 0) lb[e] = 0.0;
+        for (int e = tid; e < N * 16; e += BS)
+          if (s_fidx[e / 4] < 0) lg[e] = 0.0;
+        if (act && ca == 2) {
+          const int kf = s_fk[fa] * 4 + s_ff[fa];
+          lb[kf * 3 + 0] = ysol[0];
+          lb[kf * 3 + 1] = ysol[1];
+          lb[kf * 3 + 2] = ysol[2];
+          lg[kf * 4 + 0] = ysol[3];
+          lg[kf * 4 + 1] = ysol[4];
+          lg[kf * 4 + 2] = ysol[5];
+          lg[kf * 4 + 3] = ysol[6];
+        }
+      }
+      // per-stage input effect: d omega = sum_f Bw f, d v = dt/m sum_f f
+      if (tid < N) {
+        double dw[3] = {0, 0, 0}, dv[3] = {0, 0, 0};
+        for (int f = 0; f < 4; ++f) {
+          const int fi = s_fidx[tid * 4 + f];
+          if (fi < 0) continue;
+          const double *Bw = s_Bw + (tid * 4 + f) * 9;
+          const double u0 = s_xt[3 * fi], u1 = s_xt[3 * fi + 1], u2 = s_xt[3 * fi + 2];
+          for (int r = 0; r < 3; ++r) dw[r] += Bw[3 * r] * u0 + Bw[3 * r + 1] * u1 + Bw[3 * r + 2] * u2;
+          dv[0] += u0; dv[1] += u1; dv[2] += u2;
+        }
+        for (int r = 0; r < 3; ++r) {
+          s_bw[6 * tid + r] = dw[r];
+          s_bw[6 * tid + 3 + r] = dv[r] * (dt / mass);
+        }
+      }
+      __syncthreads();
+      if (tid == 0) {  // x_{k+1} = A x_k + B_k u_k (mpc.cpp:11-44 structure), N short steps
+        double xs[13];
+        for (int c = 0; c < 13; ++c) {
+          xs[c] = s_x0[c];
+          s_X[c] = xs[c];
+        }
+        for (int k = 0; k < N; ++k) {
+          double nx[13];
+          for (int c = 0; c < 3; ++c) {
+            nx[c] = xs[c] + dt * (s_Rt[3 * c] * xs[6] + s_Rt[3 * c + 1] * xs[7] + s_Rt[3 * c + 2] * xs[8]);
+            nx[3 + c] = xs[3 + c] + dt * xs[9 + c];
+            nx[6 + c] = xs[6 + c] + s_bw[6 * k + c];
+            nx[9 + c] = xs[9 + c] + s_bw[6 * k + 3 + c];
+          }
+          nx[11] -= dt * xs[12];
+          nx[12] = xs[12];
+          for (int c = 0; c < 13; ++c) {
+            xs[c] = nx[c];
+            s_X[13 * (k + 1) + c] = nx[c];
+          }
+        }
+      }
+      __syncthreads();
+      double *xo = B.xpred + (size_t)prob * (N + 1) * 13;
+      bool nanout = false;
+      for (int e = tid; e < (N + 1) * 13; e += BS) {
+        const double v = s_X[e];
+        nanout |= !(fabs(v) < BIG);
+      }
+      if (act) nanout |= !(fabs(xsol) < BIG);
+      if (__syncthreads_or(nanout ? 1 : 0)) {
+        status = B200QP_NAN_AFTER_SUCCESS;  // mpc.cpp:447-455
+      } else {
+        for (int e = tid; e < (N + 1) * 13; e += BS) xo[e] = s_X[e];
+      }
+    }
+    if (tid == 0) {
+      b200qp_solver_info inf;
+      inf.status = status;
+      inf.iterations = iters;
+      inf.polish_rounds = rounds_total;
+      inf.n_free = n;
+      inf.kkt[0] = kkt_stat;
+      inf.kkt[1] = 0.0;  // dynamics hold by construction of the roll-out
+      inf.kkt[2] = kkt_ineq;
+      inf.kkt[3] = kkt_comp;
+      B.info[prob] = inf;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// binning by reduced problem size
+__global__ void mpc_bin_kernel(int n, int N, const uint8_t *__restrict__ contact, int *bin_count, int *bin_lists,
+                               b200qp_solver_info *info) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  const uint8_t *ct = contact + (size_t)p * N * 4;
+  int cnt = 0;
+  for (int e = 0; e < 4 * N; ++e) cnt += ct[e] != 0;
+  const int nv = 3 * cnt;
+  int bin;
+  if (nv <= 64) bin = 0;
+  else if (nv <= 128) bin = 1;
+  else if (nv <= 156) bin = 2;
+  else bin = 3;
+  if (bin == 3) {
+    b200qp_solver_info inf = {B200QP_ACADOS_QP_FAILURE, 0, 0, nv, {0, 0, 0, 0}};
+    info[p] = inf;
+    return;
+  }
+  const int pos = atomicAdd(bin_count + bin, 1);
+  bin_lists[(size_t)bin * n + pos] = p;
+}
+
+template <int BS, int NV>
+static size_t admm_smem_bytes() {
+  return sizeof(double) * ((size_t)NV * (NV + 1) + 7 * BS + 4 * 32);
+}
+
+template <int BS, int NV>
+static cudaError_t launch_one(const MpcParams &P, MpcBuffers B, int grid, cudaStream_t st) {
+  const size_t sm = admm_smem_bytes<BS, NV>();
+  cudaError_t e = cudaFuncSetAttribute(mpc_admm_kernel<BS, NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+  if (e != cudaSuccess) return e;
+  mpc_admm_kernel<BS, NV><<<grid, BS, sm, st>>>(P, B);
+  return cudaGetLastError();
+}
+
+template <int BS, int NV>
+static int occupancy_one() {
+  const size_t sm = admm_smem_bytes<BS, NV>();
+  int occ = 0;
+  if (cudaFuncSetAttribute(mpc_admm_kernel<BS, NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm) != cudaSuccess ||
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, mpc_admm_kernel<BS, NV>, BS, sm) != cudaSuccess) {
+    cudaGetLastError();  // clear
+    return 1;
+  }
+  return occ < 1 ? 1 : occ;
+}
+int admm_occupancy(int bin) {
+  return bin == 0 ? occupancy_one<64, 64>() : bin == 1 ? occupancy_one<128, 128>() : occupancy_one<160, 156>();
+}
+int admm_block_size(int bin) { return bin == 0 ? 64 : bin == 1 ? 128 : 160; }
+
+cudaError_t launch_mpc_bin(int n, int N, const uint8_t *contact, int *bin_count, int *bin_lists,
+                           b200qp_solver_info *info, cudaStream_t st) {
+  mpc_bin_kernel<<<(n + 127) / 128, 128, 0, st>>>(n, N, contact, bin_count, bin_lists, info);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_mpc_admm(int bin, const MpcParams &P, const MpcBuffers &B, int grid, cudaStream_t st) {
+  if (bin == 0) return launch_one<64, 64>(P, B, grid, st);
+  if (bin == 1) return launch_one<128, 128>(P, B, grid, st);
+  return launch_one<160, 156>(P, B, grid, st);
+}
+
+}  // namespace b200qp

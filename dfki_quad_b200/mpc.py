@@ -1,0 +1,228 @@
+"""Host-side mirror of the reference's MPC solver plugin for a *batch* of robots.
+
+`BatchedMPC` keeps the method set of `class MPC : MPCInterface`
+(ws/src/controllers/include/mit_controller/mpc.hpp:117-141, mpc_interface.hpp:22-33):
+UpdateState / UpdateModel / UpdateGaitSequence / GetWrenchSequence + SetStateWeights / SetInputWeights / SetFmax /
+SetMu, with every argument gaining a leading batch dimension.  All arithmetic runs in libb200qp.so (CUDA, sm_100a)
+through the C ABI of include/b200qp.h; nothing here computes a QP on the CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _lib
+
+NX, NU, NLEGS = 13, 12, 4
+
+
+def in_doubles(N: int) -> int:
+    return 26 + 13 * (N + 1) + 12 * N
+
+
+@dataclass
+class SolverInformation:
+    """Batched analogue of SolverInformation (mpc_interface.hpp:10-20)."""
+
+    success: np.ndarray  # bool [n]
+    return_code: np.ndarray  # int32 [n]
+    acados_num_iter: np.ndarray  # int32 [n]
+    polish_rounds: np.ndarray  # int32 [n]
+    n_free: np.ndarray  # int32 [n]
+    kkt: np.ndarray  # float64 [n, 4]  (stationarity, dynamics, inequality, complementarity)
+    total_solver_time: float  # seconds, device time of the kernels of this call (all problems)
+    kernel_launches: int
+
+
+@dataclass
+class MPCPrediction:
+    """Batched analogue of MPCPrediction (mpc_prediction.hpp:7-13)."""
+
+    orientation: np.ndarray  # [n, N+1, 4] quaternion (x, y, z, w)
+    position: np.ndarray  # [n, N+1, 3]
+    angular_velocity: np.ndarray
+    linear_velocity: np.ndarray
+    raw_data: np.ndarray  # [n, N+1, 13]
+
+
+def pack_records(N, quat, pos, omega, vel, mass, inertia, com, des_quat, des_pos, ref_twist, ref_vel, foot_pos):
+    """Pack batched inputs into the flat record layout of include/b200qp.h.  inertia is [n,3,3] (row-major numpy)."""
+    n = quat.shape[0]
+    rec = np.empty((n, in_doubles(N)))
+    rec[:, 0:4] = quat
+    rec[:, 4:7] = pos
+    rec[:, 7:10] = omega
+    rec[:, 10:13] = vel
+    rec[:, 13] = mass
+    rec[:, 14:23] = np.transpose(np.broadcast_to(inertia, (n, 3, 3)), (0, 2, 1)).reshape(n, 9)
+    rec[:, 23:26] = com
+    st = rec[:, 26 : 26 + 13 * (N + 1)].reshape(n, N + 1, 13)
+    st[:, :, 0:4] = des_quat[:, : N + 1]
+    st[:, :, 4:7] = des_pos[:, : N + 1]
+    st[:, :, 7:10] = ref_twist[:, : N + 1]
+    st[:, :, 10:13] = ref_vel[:, : N + 1]
+    rec[:, 26 + 13 * (N + 1) :] = foot_pos[:, :N].reshape(n, 12 * N)
+    return rec
+
+
+def euler_to_quaternion(e):
+    """euler_to_quaternion (quaternion_operations.hpp:19-25), vectorised; e[..., (roll, pitch, yaw)] -> (x,y,z,w)."""
+    r, p, y = e[..., 0] * 0.5, e[..., 1] * 0.5, e[..., 2] * 0.5
+    cr, sr, cp, sp, cy, sy = np.cos(r), np.sin(r), np.cos(p), np.sin(p), np.cos(y), np.sin(y)
+    # qz * qy * qx
+    w = cy * cp * cr + sy * sp * sr
+    x = cy * cp * sr - sy * sp * cr
+    yy = cy * sp * cr + sy * cp * sr
+    z = sy * cp * cr - cy * sp * sr
+    return np.stack([x, yy, z, w], axis=-1)
+
+
+class BatchedMPC:
+    """Drop-in for `MPC` over a batch.  Constructor arguments follow mpc.hpp:117-127; `solver` accepts the reference's
+    acados plan names ("PARTIAL_CONDENSING_HPIPM", "PARTIAL_CONDENSING_OSQP", ...) or the kernel names
+    "CONDENSED_ADMM" / "SPARSE_RICCATI"; `condensing_N`, `hpipm_mode`, `warm_start` are accepted for signature
+    compatibility (the GPU kernels always solve to `kkt_tol`)."""
+
+    def __init__(self, alpha, state_weights, mu, fmin, fmax, solver="CONDENSED_ADMM", condensing_N=None,
+                 hpipm_mode="BALANCE", warm_start=0, *, horizon=10, dt=0.05, max_batch=4096, device=0, **opts):
+        self._lib = _lib.load()
+        if solver not in _lib.SOLVERS:
+            raise ValueError(f"unknown solver {solver!r}")
+        cfg = _lib.MpcConfig()
+        cfg.horizon, cfg.solver, cfg.max_batch, cfg.device = int(horizon), _lib.SOLVERS[solver], int(max_batch), int(device)
+        cfg.dt, cfg.alpha, cfg.mu, cfg.fmin, cfg.fmax = float(dt), float(alpha), float(mu), float(fmin), float(fmax)
+        sw = np.asarray(state_weights, dtype=np.float64).reshape(12)
+        for i in range(12):
+            cfg.state_weights[i] = sw[i]
+        for k, v in opts.items():
+            if not hasattr(cfg, k):
+                raise TypeError(f"unknown solver option {k!r}")
+            setattr(cfg, k, v)
+        self.cfg = cfg
+        self.N = int(horizon)
+        self.max_batch = int(max_batch)
+        self._h = C.c_void_p()
+        _lib.check(self._lib.b200qp_mpc_create(C.byref(cfg), C.byref(self._h)), "b200qp_mpc_create")
+        self._state = None
+        self._model = None
+        self._gs = None
+
+    # -- lifetime ---------------------------------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._lib.b200qp_mpc_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- MPCInterface -------------------------------------------------------------------------------------------------
+    def UpdateState(self, orientation, position, angular_vel_world, linear_vel_world):
+        """StateInterface getters used at mpc.cpp:332,392-395; arrays [n,4] (x,y,z,w), [n,3], [n,3], [n,3]."""
+        self._state = tuple(np.ascontiguousarray(a, dtype=np.float64) for a in
+                            (orientation, position, angular_vel_world, linear_vel_world))
+
+    def UpdateModel(self, mass, inertia, body_to_com):
+        """ModelInterface getters used at mpc.cpp:335,357-358; scalars/arrays broadcast over the batch."""
+        self._model = (mass, np.asarray(inertia, dtype=np.float64), np.asarray(body_to_com, dtype=np.float64))
+
+    def UpdateGaitSequence(self, gait_sequence: dict):
+        """GaitSequence fields read by the MPC (gait_sequence.hpp:21-29): contact_sequence [n,>=N,4],
+        foot_position_sequence [n,>=N,4,3], desired_reference_trajectory_orientation [n,>=N+1,4],
+        desired_reference_trajectory_position [n,>=N+1,3], reference_trajectory_twist, reference_trajectory_velocity."""
+        self._gs = gait_sequence
+
+    def GetWrenchSequence(self):
+        """-> (forces [n,N,4,3], MPCPrediction, SolverInformation); failed problems keep zeros (fresh buffers)."""
+        if self._state is None or self._model is None or self._gs is None:
+            raise RuntimeError("UpdateState / UpdateModel / UpdateGaitSequence must be called first")
+        q, p, w, v = self._state
+        n = q.shape[0]
+        gs = self._gs
+        mass, inertia, com = self._model
+        rec = pack_records(self.N, q, p, w, v, np.broadcast_to(mass, (n,)), inertia, np.broadcast_to(com, (n, 3)),
+                           gs["desired_reference_trajectory_orientation"], gs["desired_reference_trajectory_position"],
+                           gs["reference_trajectory_twist"], gs["reference_trajectory_velocity"],
+                           gs["foot_position_sequence"])
+        contact = np.ascontiguousarray(np.asarray(gs["contact_sequence"])[:, : self.N], dtype=np.uint8)
+        forces, xpred, info = self.solve_records(rec, contact)
+        com_b = np.broadcast_to(com, (n, 3))[:, None, :]
+        pred = MPCPrediction(
+            orientation=euler_to_quaternion(xpred[:, :, 0:3]),  # mpc.cpp:463
+            position=xpred[:, :, 3:6] - com_b,  # mpc.cpp:464
+            angular_velocity=xpred[:, :, 6:9].copy(), linear_velocity=xpred[:, :, 9:12].copy(), raw_data=xpred)
+        return forces.reshape(n, self.N, 4, 3), pred, info
+
+    # -- setters (mpc.hpp:138-141) ---------------------------------------------------------------------------------------
+    def SetStateWeights(self, weights):
+        w = np.ascontiguousarray(weights, dtype=np.float64).reshape(12)
+        _lib.check(self._lib.b200qp_mpc_set_state_weights(self._h, w.ctypes.data_as(C.POINTER(C.c_double))), "set_state_weights")
+
+    def SetInputWeights(self, alpha):
+        _lib.check(self._lib.b200qp_mpc_set_input_weights(self._h, float(alpha)), "set_input_weights")
+
+    def SetFmax(self, fmax):
+        _lib.check(self._lib.b200qp_mpc_set_fmax(self._h, float(fmax)), "set_fmax")
+
+    def SetMu(self, mu):
+        _lib.check(self._lib.b200qp_mpc_set_mu(self._h, float(mu)), "set_mu")
+
+    # -- record-level entry points -------------------------------------------------------------------------------------
+    def solve_records(self, rec, contact, forces=None, xpred=None):
+        """b200qp_mpc_solve_batch on host arrays: rec [n, in_doubles(N)] float64, contact [n, N, 4] uint8."""
+        rec = np.ascontiguousarray(rec, dtype=np.float64)
+        contact = np.ascontiguousarray(contact, dtype=np.uint8)
+        n = rec.shape[0]
+        if rec.shape != (n, in_doubles(self.N)) or contact.shape != (n, self.N, 4):
+            raise ValueError("record / contact shape mismatch")
+        if forces is None:
+            forces = np.zeros((n, self.N, 12))
+        if xpred is None:
+            xpred = np.zeros((n, self.N + 1, 13))
+        info = (_lib.SolverInfo * max(n, 1))()
+        rc = self._lib.b200qp_mpc_solve_batch(self._h, n, rec.ctypes.data, contact.ctypes.data, forces.ctypes.data,
+                                              xpred.ctypes.data, C.addressof(info))
+        _lib.check(rc, "b200qp_mpc_solve_batch")
+        return forces, xpred, self._info(info, n)
+
+    def solve_device(self, n, d_in, d_contact, d_forces, d_xpred, d_info, sync=True):
+        """b200qp_mpc_solve_batch_device on raw device pointers (ints)."""
+        rc = self._lib.b200qp_mpc_solve_batch_device(self._h, n, d_in, d_contact, d_forces, d_xpred, d_info, 1 if sync else 0)
+        _lib.check(rc, "b200qp_mpc_solve_batch_device")
+
+    def last_timing(self):
+        ms, nl = C.c_float(), C.c_int32()
+        _lib.check(self._lib.b200qp_mpc_last_timing(self._h, C.byref(ms), C.byref(nl)), "last_timing")
+        return ms.value, nl.value
+
+    def stream(self) -> int:
+        return int(self._lib.b200qp_mpc_stream(self._h) or 0)
+
+    def get_duals(self, n):
+        lam_box = np.zeros((n, self.N, 12))
+        lam_g = np.zeros((n, self.N, 16))
+        _lib.check(self._lib.b200qp_mpc_get_duals(self._h, n, lam_box.ctypes.data, lam_g.ctypes.data), "get_duals")
+        return lam_box, lam_g
+
+    def get_condensed(self, index):
+        nmax = 12 * self.N
+        H = np.zeros((nmax, nmax), order="F")
+        g = np.zeros(nmax)
+        nf = self._lib.b200qp_mpc_get_condensed(self._h, int(index), H.ctypes.data, nmax, g.ctypes.data)
+        if nf < 0:
+            raise _lib.B200QPError(f"b200qp_mpc_get_condensed failed with code {nf}: {_lib.last_error()}")
+        return np.array(H[:nf, :nf]), g[:nf].copy()
+
+    def _info(self, info, n):
+        arr = np.frombuffer(info, dtype=np.dtype([("status", "i4"), ("iterations", "i4"), ("polish_rounds", "i4"),
+                                                  ("n_free", "i4"), ("kkt", "f8", (4,))]), count=n)
+        ms, nl = self.last_timing()
+        return SolverInformation(success=arr["status"] == 0, return_code=arr["status"].copy(),
+                                 acados_num_iter=arr["iterations"].copy(), polish_rounds=arr["polish_rounds"].copy(),
+                                 n_free=arr["n_free"].copy(), kkt=arr["kkt"].copy(), total_solver_time=ms * 1e-3,
+                                 kernel_launches=nl)

@@ -1,0 +1,166 @@
+/*
+ * b200qp.h - C ABI of the B200-native batched MPC / WBC QP engine.
+ *
+ * Drop-in boundary for ONE hot path of dfki-ric-underactuated-lab/dfki-quad: the MPC solver plugin
+ *   class MPCInterface { UpdateState; UpdateModel; UpdateGaitSequence; GetWrenchSequence }
+ *   (ws/src/controllers/include/mit_controller/mpc_interface.hpp:22-33), implemented there by class MPC
+ *   (ws/src/controllers/include/mit_controller/mpc.hpp:13-144, src/mit_controller/mpc.cpp) on top of acados.
+ * The reference has no FFI of its own; these are the entry points a cgo/JNI/ctypes/C++ adapter for that class
+ * binds (INTEGRATION.md shows the C++ adapter).  Plain pointers and sizes only; no torch / Eigen / ROS types.
+ *
+ * Batch semantics: every call processes `n` independent problems (robots / sampled states).  All matrices that
+ * cross the ABI are column-major like the reference's acados pointers (mpc.hpp:37-47).
+ * Quaternions are (x, y, z, w) = Eigen::Quaterniond::coeffs() order.
+ * There is NO CPU fallback: every solve entry point fails with B200QP_ERR_CUDA if no sm_100 device is usable.
+ */
+#ifndef B200QP_H_
+#define B200QP_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200QP_NX 13            /* MPC::STATE_SIZE            mpc.hpp:15 */
+#define B200QP_NU 12            /* MPC::INPUT_SIZE            mpc.hpp:17 */
+#define B200QP_NLEGS 4          /* N_LEGS                     mit_controller_params.hpp:3 */
+#define B200QP_MAX_HORIZON 20   /* MPC_PREDICTION_HORIZON of the checkout, mit_controller_params.hpp:6 */
+#define B200QP_GAIT_SEQUENCE_SIZE 100 /* GAIT_SEQUENCE_SIZE   mit_controller_params.hpp:5 */
+
+/* function return codes (argument / CUDA errors only; per-problem solver results are in b200qp_solver_info) */
+#define B200QP_OK 0
+#define B200QP_ERR_ARG (-1)
+#define B200QP_ERR_CUDA (-2)
+#define B200QP_ERR_UNSUPPORTED (-3)
+
+/* per-problem status = acados `return_values` as named at mpc.cpp:413-425 (numeric order per upstream
+ * acados/utils/types.h), plus the reference's own -7777 for NaN-after-success (mpc.cpp:452). */
+#define B200QP_ACADOS_SUCCESS 0
+#define B200QP_ACADOS_NAN_DETECTED 1
+#define B200QP_ACADOS_MAXITER 2
+#define B200QP_ACADOS_MINSTEP 3
+#define B200QP_ACADOS_QP_FAILURE 4
+#define B200QP_ACADOS_READY 5
+#define B200QP_NAN_AFTER_SUCCESS (-7777)
+
+/* solver selection, named after the reference's acados plans (mit_controller_node.cpp:502-519) */
+#define B200QP_SOLVER_CONDENSED_ADMM 0 /* replaces PARTIAL_CONDENSING_OSQP with small cond_N / FULL_CONDENSING_* */
+#define B200QP_SOLVER_SPARSE_RICCATI 1 /* replaces PARTIAL_CONDENSING_HPIPM with cond_N == N                     */
+
+/* Replaces the MPC constructor arguments (mpc.hpp:117-127) + compile-time constants (mit_controller_params.hpp). */
+typedef struct b200qp_mpc_config {
+  int32_t horizon;            /* N, 1..B200QP_MAX_HORIZON (reference: compile-time MPC_PREDICTION_HORIZON)        */
+  int32_t solver;             /* B200QP_SOLVER_*                                                                 */
+  int32_t max_batch;          /* device buffers are sized for this many problems at create                      */
+  int32_t device;             /* CUDA device ordinal                                                            */
+  double dt;                  /* MPC_DT                                                                         */
+  double alpha;               /* input weight, R = alpha I        (mpc.cpp:166)                                  */
+  double state_weights[12];   /* Q = diag(w, 0)                   (mpc.cpp:161-165)                              */
+  double mu;                  /* friction coefficient             (mpc.cpp:66-71)                                */
+  double fmin;                /* (mpc.cpp:94-115)                                                                */
+  double fmax;
+  /* solver options (0 => library default) */
+  double admm_rho;            /* initial ADMM penalty                                     default 1e-3          */
+  double admm_sigma;          /* ADMM proximal weight                                     default 1e-6          */
+  double admm_alpha;          /* ADMM over-relaxation                                     default 1.6           */
+  double admm_eps;            /* relative tolerance at which ADMM hands over to polish    default 1e-3          */
+  double kkt_tol;             /* accept when all four KKT inf-norms <= kkt_tol            default 1e-7          */
+  int32_t admm_max_iter;      /* total ADMM iteration cap per problem                     default 2000          */
+  int32_t admm_check_every;   /* residual check / rho adaptation interval                 default 10            */
+  int32_t polish_max_rounds;  /* active-set repair sweeps per polish                      default 8             */
+  int32_t ipm_max_iter;       /* Riccati IPM iteration cap                                default 40            */
+} b200qp_mpc_config;
+
+/* Input record of one problem = the subset of {StateInterface, ModelInterface, GaitSequence} that
+ * MPC::GetWrenchSequence reads (mpc.cpp:332-396), as a flat FP64 array of b200qp_mpc_in_doubles(N) values:
+ *   [0:4)    body orientation quaternion (x,y,z,w)          StateInterface::GetOrientationInWorld
+ *   [4:7)    body position                                  GetPositionInWorld
+ *   [7:10)   angular velocity, world frame                  GetAngularVelInWorld
+ *   [10:13)  linear velocity, world frame                   GetLinearVelInWorld
+ *   [13]     mass                                           ModelInterface::GetMass
+ *   [14:23)  body inertia 3x3, column-major                 GetInertia
+ *   [23:26)  body -> COM translation                        GetBodyToCOM().translation()
+ *   then for k = 0..N (13 doubles each):
+ *            desired_reference_trajectory_orientation[k] (4), desired_reference_trajectory_position[k] (3),
+ *            reference_trajectory_twist[k] (3), reference_trajectory_velocity[k] (3)      gait_sequence.hpp:22-29
+ *   then for k = 0..N-1 (12 doubles each): foot_position_sequence[k][leg 0..3] (3 each)   gait_sequence.hpp:22
+ * plus a separate uint8 array contact[n][N][4] = contact_sequence rows 0..N-1             gait_sequence.hpp:21 */
+static inline int32_t b200qp_mpc_in_doubles(int32_t horizon) { return 26 + 13 * (horizon + 1) + 12 * horizon; }
+
+/* Per-problem result record; replaces SolverInformation (mpc_interface.hpp:10-20). */
+typedef struct b200qp_solver_info {
+  int32_t status;     /* B200QP_ACADOS_* / B200QP_NAN_AFTER_SUCCESS; success <=> status == 0 (mpc.cpp:445)      */
+  int32_t iterations; /* ADMM or IPM iterations (acados_num_iter, mpc.cpp:442)                                  */
+  int32_t polish_rounds; /* active-set solves done by the polish (0 for the IPM)                                */
+  int32_t n_free;     /* number of free (stance) force variables of the reduced QP                              */
+  double kkt[4];      /* inf-norms: stationarity, dynamics, inequality, complementarity (the 4-tuple of the
+                         commented-out ocp_qp_inf_norm_residuals call, mpc.cpp:430-433)                         */
+} b200qp_solver_info;
+
+typedef struct b200qp_mpc b200qp_mpc; /* opaque handle: one per host thread / per GPU; not thread-safe           */
+
+/* MPC::MPC(...)  mpc.cpp:117-272 */
+int32_t b200qp_mpc_create(const b200qp_mpc_config *cfg, b200qp_mpc **out);
+/* MPC::~MPC()    mpc.cpp:274-282 */
+void b200qp_mpc_destroy(b200qp_mpc *h);
+/* MPC::SetStateWeights / SetInputWeights / SetFmax / SetMu   mpc.cpp:294-326, mpc.hpp:138-141 */
+int32_t b200qp_mpc_set_state_weights(b200qp_mpc *h, const double weights[12]);
+int32_t b200qp_mpc_set_input_weights(b200qp_mpc *h, double alpha);
+int32_t b200qp_mpc_set_fmax(b200qp_mpc *h, double fmax);
+int32_t b200qp_mpc_set_mu(b200qp_mpc *h, double mu);
+
+/* MPC::GetWrenchSequence for `n` problems, HOST buffers (mpc.cpp:329-470).
+ *   in       [n][b200qp_mpc_in_doubles(N)]   input records (see above)
+ *   contact  [n][N][4]                        uint8 0/1
+ *   forces   [n][N][4][3]                     WrenchSequence::forces (wrench_sequence.hpp:9); world-frame GRFs
+ *   xpred    [n][N+1][13]                     MPCPrediction::raw_data (mpc_prediction.hpp:12)
+ *   info     [n]
+ * Problems whose status != 0 leave their forces/xpred slots untouched (mpc.cpp:447-455).
+ * Copies H2D, runs the kernels, copies D2H, synchronises. */
+int32_t b200qp_mpc_solve_batch(b200qp_mpc *h, int32_t n, const double *in, const uint8_t *contact, double *forces,
+                               double *xpred, b200qp_solver_info *info);
+/* Same with DEVICE pointers (inputs already resident in HBM); asynchronous on the handle's stream unless sync != 0. */
+int32_t b200qp_mpc_solve_batch_device(b200qp_mpc *h, int32_t n, const double *d_in, const uint8_t *d_contact,
+                                      double *d_forces, double *d_xpred, b200qp_solver_info *d_info, int32_t sync);
+/* Optional diagnostics of the last device solve: duals in the reference's row order, per problem
+ *   lam_box [n][N][12]  multipliers of lbu/ubu rows (>0 at upper, <0 at lower),  lam_g [n][N][16] of lg/ug rows.
+ * Host buffers. Valid for problems with status == 0. */
+int32_t b200qp_mpc_get_duals(b200qp_mpc *h, int32_t n, double *lam_box, double *lam_g);
+/* Debug/parity hook: condensed reduced Hessian and gradient of problem `index` of the last solve
+ * (SURVEY.md section 7 step 5).  H is [n_free x n_free] column-major, g is [n_free]; free variables are ordered by
+ * (stage, leg, xyz) over stance feet.  Returns n_free or a negative error. Requires the handle to have been
+ * created with max_batch problems of scratch (always true). */
+int32_t b200qp_mpc_get_condensed(b200qp_mpc *h, int32_t index, double *H, int32_t ldh, double *g);
+/* Device time (ms, CUDA events on the handle's stream) of the kernels of the last solve call, and launch count. */
+int32_t b200qp_mpc_last_timing(b200qp_mpc *h, float *kernel_ms, int32_t *kernel_launches);
+/* CUDA stream of the handle as a void* (cudaStream_t), for callers that time with their own events. */
+void *b200qp_mpc_stream(b200qp_mpc *h);
+
+/* ---- gait schedule -> contact mask -> bound indexing (kernel K4, bit-exact) -------------------------------------
+ * Gait::update_sequence (gait.cpp:67-112) for n robots with per-robot gait parameters and phase, followed by
+ * MPC::GetUBounds (mpc.cpp:94-115).
+ *   period[n], duty[n][4], offset[n][4], phase[n]         Gait members / SimpleGaitSequencer::phase_
+ *   measured_contact[n][4] or NULL                        StateInterface::GetFeetContacts (early-contact rule)
+ *   steps                                                 rows to produce (<= B200QP_GAIT_SEQUENCE_SIZE)
+ *   contact[n][steps][4] uint8, swing_time[n][steps][4] (may be NULL), lbu/ubu[n][steps][12] (may be NULL)
+ * HOST buffers. */
+int32_t b200qp_gait_schedule(int32_t device, int32_t n, int32_t steps, double dt, const double *period,
+                             const double *duty, const double *offset, const double *phase,
+                             const uint8_t *measured_contact, double fmin, double fmax, uint8_t *contact,
+                             double *swing_time, double *lbu, double *ubu);
+/* Same with DEVICE pointers on `stream` (cudaStream_t as void*, may be NULL). */
+int32_t b200qp_gait_schedule_device(int32_t n, int32_t steps, double dt, const double *d_period, const double *d_duty,
+                                    const double *d_offset, const double *d_phase, const uint8_t *d_measured_contact,
+                                    double fmin, double fmax, uint8_t *d_contact, double *d_swing_time, double *d_lbu,
+                                    double *d_ubu, void *stream);
+
+/* library / device info */
+const char *b200qp_version(void);
+int32_t b200qp_device_count(void);
+const char *b200qp_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200QP_H_ */

@@ -396,7 +396,16 @@ def solve_ipm_dense(H, g, A, l, u, tol=1e-11, max_iter=100):
             break
         W = z / s
         K = Hf + G.T @ (W[:, None] * G)
-        Lc = np.linalg.cholesky(K)
+        Lc = None
+        reg = 0.0
+        for _try in range(6):  # degenerate vertices (cone apex) make K numerically indefinite late in the solve
+            try:
+                Lc = np.linalg.cholesky(K + reg * np.eye(nf))
+                break
+            except np.linalg.LinAlgError:
+                reg = max(10.0 * reg, 1e-12 * np.abs(np.diag(K)).max())
+        if Lc is None or not np.all(np.isfinite(Lc)):
+            break
 
         def kkt(rc):
             # eliminate ds = -rp - G dx ; dz = (-rc - z ds)/s

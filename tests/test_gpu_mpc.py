@@ -1,0 +1,240 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu).  Everything goes through the C ABI (libb200qp.so via
+ctypes); the oracle (oracle/) is the checker only."""
+import math
+
+import numpy as np
+import pytest
+
+from oracle import mpc_oracle as mo
+
+pytestmark = pytest.mark.gpu
+
+
+def _mpc(N, max_batch, solver="CONDENSED_ADMM", weights="state_weights_move", **opts):
+    from dfki_quad_b200 import BatchedMPC, sequencer
+
+    cfg = sequencer.GO2_MPC
+    return BatchedMPC(cfg["alpha"], cfg[weights], cfg["mu"], cfg["fmin"], cfg["fmax"], solver, horizon=N, dt=cfg["dt"],
+                      max_batch=max_batch, **opts)
+
+
+# ---------------------------------------------------------------------------------------------------- K4 gait masks
+def test_gait_schedule_bit_exact_random():
+    from dfki_quad_b200 import gait
+
+    rng = np.random.default_rng(20261019)
+    n, steps, dt = 1500, 21, 0.05
+    ids = rng.integers(0, len(gait.GAIT_NAMES), n)
+    per, duty, off = gait.gait_arrays(ids)
+    phase = rng.uniform(0, 1, n)
+    # exact-boundary phases: multiples of dt/T and of the offsets
+    phase[:200] = rng.integers(0, 20, 200) * 0.05
+    phase[200:300] = 0.0
+    meas = rng.integers(0, 2, (n, 4)).astype(np.uint8)
+    contact, swing, lbu, ubu = gait.contact_schedule(per, duty, off, phase, steps, dt, measured_contact=meas, fmin=0.0,
+                                                     fmax=400.0, want_bounds=True)
+    for p in range(n):
+        c_ref, s_ref = mo.gait_update_sequence(per[p], duty[p], off[p], dt, float(phase[p]), steps, meas[p])
+        assert np.array_equal(contact[p], c_ref), (p, gait.GAIT_NAMES[ids[p]], phase[p])
+        assert np.array_equal(swing[p].view(np.uint64), s_ref.view(np.uint64)), (p, "swing time not bit exact")
+        for k in range(0, steps, 5):
+            lb, ub = mo.get_u_bounds(c_ref[k], 0.0, 400.0)
+            assert np.array_equal(lbu[p, k], lb) and np.array_equal(ubu[p, k], ub)
+
+
+def test_gait_schedule_known_answer_trot_phase0():
+    """TROT at phase 0, dt = 0.05: rows 0-4 [1,0,0,1], rows 5-9 [0,1,1,0], row 10 [1,0,0,1]
+    (the 0.5 < 0.5 comparison at i = 5 must come out false)."""
+    from dfki_quad_b200 import gait
+
+    per, duty, off = gait.gait_arrays(np.array([gait.GAIT_NAMES.index("TROT")]))
+    contact, _ = gait.contact_schedule(per, duty, off, np.array([0.0]), 11, 0.05)
+    exp = np.array([[1, 0, 0, 1]] * 5 + [[0, 1, 1, 0]] * 5 + [[1, 0, 0, 1]], dtype=np.uint8)
+    assert np.array_equal(contact[0], exp)
+
+
+def test_gait_schedule_no_measured_contacts_and_empty():
+    from dfki_quad_b200 import gait
+
+    per, duty, off = gait.gait_arrays(np.arange(len(gait.GAIT_NAMES)))
+    phase = np.linspace(0, 0.95, len(per))
+    contact, swing = gait.contact_schedule(per, duty, off, phase, 100, 0.05)
+    for p in range(len(per)):
+        c_ref, s_ref = mo.gait_update_sequence(per[p], duty[p], off[p], 0.05, float(phase[p]), 100, None)
+        assert np.array_equal(contact[p], c_ref) and np.array_equal(swing[p], s_ref)
+    c0, s0 = gait.contact_schedule(np.zeros(0), np.zeros((0, 4)), np.zeros((0, 4)), np.zeros(0), 10, 0.05)
+    assert c0.shape == (0, 10, 4)
+
+
+# ---------------------------------------------------------------------------------------------------- K1 assembly
+@pytest.mark.parametrize("N,gaits", [(10, ("TROT",)), (10, ("STAND", "PACE", "STATIC_WALK")), (16, ("TROT", "BOUND"))])
+def test_condensed_hessian_gradient_parity(N, gaits, go2_params):
+    from dfki_quad_b200 import sequencer
+
+    n = 6
+    batch = sequencer.random_batch(n, N, seed=11 + N, gaits=gaits)
+    mpc = _mpc(N, n)
+    _, _, info = mpc.solve_records(batch["rec"], batch["contact"])
+    for p in range(n):
+        if info.n_free[p] > 156:
+            continue
+        H, g = mpc.get_condensed(p)
+        qp = mo.build_ocp_qp(N, batch["rec"][p], batch["contact"][p], go2_params)
+        dq = mo.condense(qp)
+        idx = np.array([12 * k + 3 * f + c for k in range(N) for f in range(4) if batch["contact"][p, k, f] for c in range(3)],
+                       dtype=int)
+        assert H.shape[0] == len(idx) == info.n_free[p]
+        Href, gref = dq["H"][np.ix_(idx, idx)], dq["g"][idx]
+        assert np.abs(H - Href).max() <= 1e-12 * np.abs(Href).max()
+        assert np.abs(g - gref).max() <= 1e-12 * max(np.abs(gref).max(), 1.0)
+
+
+# ---------------------------------------------------------------------------------------------------- K2a ADMM solve
+def _check_against_oracle(N, batch, forces, xpred, info, params, idx, grf_tol=1e-5, kkt_tol=1e-6):
+    for p in idx:
+        assert info.return_code[p] == 0, (p, info.return_code[p])
+        U, X, qp, dq = mo.solve_reference_qp(N, batch["rec"][p], batch["contact"][p], params)
+        Ug = forces[p].reshape(N, 12)
+        # oracle IPM is an interior solution: polish it on the active set it identified, for a 1e-10 reference
+        x2, y2, ok = mo.polish_active_set(dq["H"], dq["g"], dq["A"], np.where(dq["l"] <= -mo.INF_THRESHOLD, -np.inf, dq["l"]),
+                                          np.where(dq["u"] >= mo.INF_THRESHOLD, np.inf, dq["u"]), U.reshape(-1),
+                                          _ipm_duals(dq, U.reshape(-1)))
+        Uref = x2.reshape(N, 12) if ok else U
+        scale = max(1.0, np.abs(Uref).max())
+        assert np.abs(Ug - Uref).max() / scale <= grf_tol, (p, np.abs(Ug - Uref).max() / scale)
+        kkt = mo.kkt_residuals(qp, Ug)  # FP64 KKT 4-tuple by the independent checker
+        assert max(kkt) <= kkt_tol, (p, kkt)
+        Xr = mo.rollout(qp, Ug)
+        assert np.abs(xpred[p] - Xr).max() <= 1e-9 * max(1.0, np.abs(Xr).max())
+        # swing legs are exactly zero (constraint indexing bit-exact)
+        mask = np.repeat(batch["contact"][p].reshape(N, 4), 3, axis=1) == 0
+        assert np.all(Ug[mask] == 0.0)
+
+
+def _ipm_duals(dq, u):
+    """Sign pattern of the duals at the IPM solution from the gradient (for the oracle-side polish)."""
+    r = dq["H"] @ u + dq["g"]
+    A, l, uu = dq["A"], dq["l"], dq["u"]
+    Ax = A @ u
+    y = np.zeros(len(l))
+    tol = 1e-6 * max(1.0, np.abs(u).max())
+    y[(np.abs(Ax - uu) <= tol) & (uu < mo.INF_THRESHOLD)] = 1.0
+    y[(np.abs(Ax - l) <= tol) & (l > -mo.INF_THRESHOLD)] = -1.0
+    return y
+
+
+@pytest.mark.parametrize("gaits,N", [(("TROT",), 10), (("STAND", "PACE", "BOUND", "WALKING_TROT", "PRONK"), 10),
+                                      (("TROT", "PACE"), 16)])
+def test_admm_parity_small(gaits, N, go2_params):
+    from dfki_quad_b200 import sequencer
+
+    n = 24
+    batch = sequencer.random_batch(n, N, seed=100 + N + len(gaits), gaits=gaits)
+    mpc = _mpc(N, n)
+    forces, xpred, info = mpc.solve_records(batch["rec"], batch["contact"])
+    ok = [p for p in range(n) if info.n_free[p] <= 156]
+    assert len(ok) > 0
+    _check_against_oracle(N, batch, forces, xpred, info, go2_params, ok)
+    assert np.all(info.kkt[ok].max(axis=1) <= 1e-6)
+
+
+def test_config2_full_batch_converges(go2_params):
+    """BASELINE.json configs[1]: 4096 randomised trot problems, N = 10, condensed ADMM."""
+    from dfki_quad_b200 import sequencer
+
+    N, n = 10, 4096
+    batch = sequencer.random_batch(n, N, seed=20261019 + 2, gaits=("TROT",))
+    mpc = _mpc(N, n)
+    forces, xpred, info = mpc.solve_records(batch["rec"], batch["contact"])
+    assert info.success.mean() >= 0.999, (info.success.mean(), np.bincount(info.return_code[info.return_code >= 0]))
+    assert np.all(info.kkt[info.success].max(axis=1) <= 1e-6)
+    rng = np.random.default_rng(3)
+    idx = rng.choice(np.nonzero(info.success)[0], 24, replace=False)
+    _check_against_oracle(N, batch, forces, xpred, info, go2_params, idx)
+    # size-independent properties on the whole batch: friction pyramid, boxes, swing legs zero
+    F = forces.reshape(n, N, 4, 3)[info.success]
+    C = batch["contact"][info.success]
+    assert np.all(F[C == 0] == 0.0)
+    mu, fmax = 0.6, 400.0
+    assert np.all(np.abs(F[..., 0]) <= mu * F[..., 2] + 1e-7) and np.all(np.abs(F[..., 1]) <= mu * F[..., 2] + 1e-7)
+    assert np.all(F[..., 2] >= -1e-7) and np.all(F[..., 2] <= fmax + 1e-7)
+
+
+def test_known_answer_standing(go2_params):
+    """level stand, 4 symmetric stance feet, zero velocity, reference = current state =>
+    sum f_z = m g at every stage (up to the alpha regularisation), f_xy ~ 0."""
+    from dfki_quad_b200 import pack_records
+
+    N = 10
+    quat = np.array([[0.0, 0.0, 0.0, 1.0]])
+    pos = np.array([[0.0, 0.0, 0.3]])
+    z3 = np.zeros((1, 3))
+    feet = np.array([[[0.18, 0.13, 0.0], [0.18, -0.13, 0.0], [-0.18, 0.13, 0.0], [-0.18, -0.13, 0.0]]])
+    rec = pack_records(N, quat, pos, z3, z3, np.array([mo.GO2_MASS]), mo.GO2_INERTIA, z3,
+                       np.repeat(quat[:, None], N + 1, 1), np.repeat(pos[:, None], N + 1, 1), np.zeros((1, N + 1, 3)),
+                       np.zeros((1, N + 1, 3)), np.repeat(feet[:, None], N, 1))
+    contact = np.ones((1, N, 4), dtype=np.uint8)
+    mpc = _mpc(N, 1, weights="state_weights_stand")
+    forces, xpred, info = mpc.solve_records(rec, contact)
+    assert info.success[0] and info.n_free[0] == 120
+    F = forces.reshape(N, 4, 3)
+    mg = mo.GO2_MASS * mo.GRAVITY_CONSTANT
+    assert np.allclose(F[:, :, 2].sum(axis=1), mg, rtol=2e-3)
+    assert np.abs(F[:, :, :2]).max() < 1e-6 * mg
+    assert np.allclose(F[:, :, 2], mg / 4, rtol=2e-3)
+
+
+def test_all_swing_is_ballistic(go2_params):
+    """Appendix A (ii): no stance foot at any stage => U = 0 and X is the free roll-out."""
+    from dfki_quad_b200 import sequencer
+
+    N, n = 10, 3
+    batch = sequencer.random_batch(n, N, seed=5)
+    contact = np.zeros((n, N, 4), dtype=np.uint8)
+    mpc = _mpc(N, n)
+    forces, xpred, info = mpc.solve_records(batch["rec"], contact)
+    assert info.success.all() and np.all(forces == 0.0) and np.all(info.n_free == 0)
+    for p in range(n):
+        qp = mo.build_ocp_qp(N, batch["rec"][p], contact[p], go2_params)
+        assert np.abs(xpred[p] - mo.rollout(qp, np.zeros((N, 12)))).max() <= 1e-12
+
+
+def test_setters_and_failure_semantics(go2_params):
+    from dfki_quad_b200 import sequencer
+
+    N, n = 10, 8
+    batch = sequencer.random_batch(n, N, seed=9)
+    mpc = _mpc(N, n)
+    f0, _, _ = mpc.solve_records(batch["rec"], batch["contact"])
+    mpc.SetMu(0.3)
+    mpc.SetFmax(150.0)
+    f1, _, info = mpc.solve_records(batch["rec"], batch["contact"])
+    assert info.success.all()
+    F = f1.reshape(n, N, 4, 3)
+    assert np.all(np.abs(F[..., 0]) <= 0.3 * F[..., 2] + 1e-7) and np.all(F[..., 2] <= 150.0 + 1e-7)
+    p2 = dict(go2_params, mu=0.3, fmax=150.0)
+    _check_against_oracle(N, batch, f1, mpc.solve_records(batch["rec"], batch["contact"])[1], info, p2, range(3))
+    # NaN input => that problem fails and leaves its output slot untouched; the others are unaffected
+    rec = batch["rec"].copy()
+    rec[2, 5] = np.nan
+    forces = np.full((n, N, 12), 123.0)
+    xpred = np.full((n, N + 1, 13), 321.0)
+    _, _, info = mpc.solve_records(rec, batch["contact"], forces, xpred)
+    assert not info.success[2] and info.return_code[2] in (1, -7777)
+    assert np.all(forces[2] == 123.0) and np.all(xpred[2] == 321.0)
+    assert info.success[[0, 1, 3, 4, 5, 6, 7]].all()
+    assert np.array_equal(forces[0], f1[0])
+
+
+def test_duals_reported_in_reference_row_order(go2_params):
+    from dfki_quad_b200 import sequencer
+
+    N, n = 10, 6
+    batch = sequencer.random_batch(n, N, seed=21, gaits=("TROT", "STAND"))
+    mpc = _mpc(N, n)
+    forces, _, info = mpc.solve_records(batch["rec"], batch["contact"])
+    lam_box, lam_g = mpc.get_duals(n)
+    for p in range(n):
+        qp = mo.build_ocp_qp(N, batch["rec"][p], batch["contact"][p], go2_params)
+        kkt = mo.kkt_residuals(qp, forces[p].reshape(N, 12), lam_box[p], lam_g[p])
+        assert max(kkt) <= 1e-6, (p, kkt)

@@ -1,0 +1,153 @@
+"""CPU-side tests: C-ABI surface, host logic (sequencer, sharding), failure without a GPU.  No compute calls."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _oracle_schedule(period, duty, offset, phase, steps, dt):
+    from oracle import mpc_oracle as mo
+
+    n = len(period)
+    c = np.zeros((n, steps, 4), dtype=np.uint8)
+    s = np.zeros((n, steps, 4))
+    for p in range(n):
+        c[p], s[p] = mo.gait_update_sequence(period[p], duty[p], offset[p], dt, float(phase[p]), steps, None)
+    return c, s
+
+
+def test_library_builds_and_exports_every_declared_symbol():
+    import __graft_entry__ as ge
+
+    ge.build()
+    from dfki_quad_b200 import _lib
+
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    header = open(os.path.join(ROOT, "include", "b200qp.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b(b200qp_[a-z_0-9]+)\s*\(", header)) - {"b200qp_mpc_in_doubles"}
+    assert len(declared) >= 15
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/b200qp.h but not exported"
+    assert set(_lib.EXPORTS) == declared
+    assert b"sm_100a" in _lib.load().b200qp_version()
+
+
+def test_struct_layout_matches_header():
+    from dfki_quad_b200 import _lib
+
+    assert ctypes.sizeof(_lib.SolverInfo) == 48
+    assert ctypes.sizeof(_lib.MpcConfig) == 16 + 8 * (2 + 12 + 3 + 5) + 16
+
+
+def test_no_gpu_fails_loudly():
+    from dfki_quad_b200 import BatchedMPC, _lib, sequencer
+
+    lib = _lib.load()
+    if lib.b200qp_device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    cfg = sequencer.GO2_MPC
+    with pytest.raises(_lib.B200QPError):
+        BatchedMPC(cfg["alpha"], cfg["state_weights_move"], cfg["mu"], cfg["fmin"], cfg["fmax"], horizon=10, max_batch=4)
+    with pytest.raises(_lib.B200QPError):
+        from dfki_quad_b200 import gait
+
+        gait.contact_schedule(np.array([0.5]), np.full((1, 4), 0.5), np.zeros((1, 4)), np.array([0.0]), 5, 0.05)
+
+
+def test_bad_arguments_rejected():
+    from dfki_quad_b200 import _lib
+
+    lib = _lib.load()
+    cfg = _lib.MpcConfig()
+    h = ctypes.c_void_p()
+    cfg.horizon = 99
+    assert lib.b200qp_mpc_create(ctypes.byref(cfg), ctypes.byref(h)) == _lib.ERR_ARG
+    assert lib.b200qp_mpc_create(None, ctypes.byref(h)) == _lib.ERR_ARG
+    assert lib.b200qp_gait_schedule(0, 1, 0, 0.05, None, None, None, None, None, 0.0, 1.0, None, None, None, None) == _lib.ERR_ARG
+
+
+def test_product_never_imports_oracle():
+    """The shipped path must not route through the CPU oracle (or /root/reference)."""
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "dfki_quad_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src.replace("no CPU oracle", ""), f"{f} mentions the oracle"
+                assert "/root/reference" not in src
+
+
+def test_batched_sequencer_matches_scalar_oracle():
+    from dfki_quad_b200 import sequencer
+    from oracle import mpc_oracle as mo
+    from oracle import sequencer_oracle as so
+
+    N, n = 10, 12
+    batch = sequencer.random_batch(n, N, seed=3, gaits=("TROT", "PACE", "BOUND", "STATIC_WALK"), schedule_fn=_oracle_schedule)
+    params = dict(mo.GO2_PARAMS)
+    for p in range(n):
+        from dfki_quad_b200.gait import GAIT_NAMES
+
+        tgt = {k: float(v[p]) for k, v in batch["target"].items()}
+        state = dict(quat=batch["quat"][p], pos=batch["pos"][p], omega=batch["omega"][p], vel=batch["vel"][p])
+        rec, contact = so.make_problem(N, GAIT_NAMES[batch["gait_ids"][p]], float(batch["phase"][p]), state, tgt,
+                                       batch["feet"][p], params)
+        assert np.array_equal(contact, batch["contact"][p])
+        assert np.allclose(rec, batch["rec"][p], rtol=0, atol=1e-12), np.abs(rec - batch["rec"][p]).max()
+
+
+def test_pack_records_layout_matches_oracle():
+    from dfki_quad_b200 import pack_records
+    from oracle import mpc_oracle as mo
+
+    rng = np.random.default_rng(0)
+    N = 7
+    a = lambda *s: rng.normal(size=s)  # noqa: E731
+    I = a(3, 3)
+    rec = pack_records(N, a(1, 4), a(1, 3), a(1, 3), a(1, 3), np.array([2.0]), I, a(1, 3), a(1, N + 1, 4), a(1, N + 1, 3),
+                       a(1, N + 1, 3), a(1, N + 1, 3), a(1, N, 4, 3))
+    d = mo.unpack_problem(N, rec[0])
+    assert np.array_equal(d["inertia"], I)
+    rec2 = mo.pack_problem(N, d["quat"], d["pos"], d["omega"], d["vel"], d["mass"], d["inertia"], d["com"], d["des_quat"],
+                           d["des_pos"], d["ref_twist"], d["ref_vel"], d["foot_pos"])
+    assert np.array_equal(rec[0], rec2)
+    assert rec.shape[1] == mo.in_doubles(N) == 26 + 13 * (N + 1) + 12 * N
+
+
+def test_shard_range_partitions():
+    from dfki_quad_b200.shard import shard_range
+
+    for n in (0, 1, 7, 4096, 1048576 + 3):
+        for w in (1, 2, 4, 8):
+            spans = [shard_range(n, r, w) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
+    with pytest.raises(ValueError):
+        shard_range(4, 2, 2)
+
+
+def test_sharding_two_ranks_gloo(tmp_path):
+    """world_size-2 gloo run of the N>1 host path: each rank takes its slice, statistics are reduced off the clock."""
+    script = tmp_path / "w.py"
+    script.write_text(
+        "import os, sys\n"
+        f"sys.path.insert(0, {ROOT!r})\n"
+        "import torch.distributed as dist\n"
+        "from dfki_quad_b200.shard import shard_range, gather_stats\n"
+        "dist.init_process_group('gloo')\n"
+        "r, w = dist.get_rank(), dist.get_world_size()\n"
+        "lo, hi = shard_range(1001, r, w)\n"
+        "s = gather_stats({'solved': hi - lo, 'iters_max': 10 + r})\n"
+        "assert s['solved'] == 1001 and s['iters_max'] == 11, s\n"
+        "dist.destroy_process_group()\n")
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29611", str(script)], env=env,
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
