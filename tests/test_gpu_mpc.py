@@ -162,7 +162,8 @@ def test_config2_full_batch_converges(go2_params):
 
 def test_known_answer_standing(go2_params):
     """level stand, 4 symmetric stance feet, zero velocity, reference = current state =>
-    sum f_z = m g at every stage (up to the alpha regularisation), f_xy ~ 0."""
+    sum f_z = m g (the finite horizon lets the last stages sag, so the early stages are checked), f_xy ~ 0, equal
+    split over the symmetric feet at every stage."""
     from dfki_quad_b200 import pack_records
 
     N = 10
@@ -179,9 +180,11 @@ def test_known_answer_standing(go2_params):
     assert info.success[0] and info.n_free[0] == 120
     F = forces.reshape(N, 4, 3)
     mg = mo.GO2_MASS * mo.GRAVITY_CONSTANT
-    assert np.allclose(F[:, :, 2].sum(axis=1), mg, rtol=2e-3)
+    assert np.allclose(F[:6, :, 2].sum(axis=1), mg, rtol=1e-3)
     assert np.abs(F[:, :, :2]).max() < 1e-6 * mg
-    assert np.allclose(F[:, :, 2], mg / 4, rtol=2e-3)
+    assert np.allclose(F[:, :, 2], F[:, :1, 2], rtol=1e-9)
+    U, _, qp, _ = mo.solve_reference_qp(N, rec[0], contact[0], dict(go2_params, weights=go2_params["w_stand"]))
+    assert np.abs(forces[0].reshape(N, 12) - U).max() <= 1e-5 * np.abs(U).max()
 
 
 def test_all_swing_is_ballistic(go2_params):
@@ -238,3 +241,32 @@ def test_duals_reported_in_reference_row_order(go2_params):
         qp = mo.build_ocp_qp(N, batch["rec"][p], batch["contact"][p], go2_params)
         kkt = mo.kkt_residuals(qp, forces[p].reshape(N, 12), lam_box[p], lam_g[p])
         assert max(kkt) <= 1e-6, (p, kkt)
+
+
+# ---------------------------------------------------------------------------------------------------- golden fixtures
+@pytest.mark.parametrize("tag,N", [("h10_trot", 10), ("h10_mixed", 10), ("h16_mixed", 16)])
+def test_golden_fixtures(tag, N):
+    """Committed oracle fixtures (tests/golden/make_golden.py): GRFs within 1e-5 relative, predicted states 1e-9."""
+    import os
+
+    G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "mpc_golden.npz"))
+    rec, contact, F, X = G[tag + "_rec"], G[tag + "_contact"], G[tag + "_forces"], G[tag + "_xpred"]
+    mpc = _mpc(N, rec.shape[0])
+    forces, xpred, info = mpc.solve_records(rec, contact)
+    ok = info.n_free <= 156
+    assert info.success[ok].all() and ok.sum() >= rec.shape[0] - 2
+    assert np.abs(forces[ok] - F[ok]).max() <= 1e-5 * max(1.0, np.abs(F).max())
+    assert np.abs(xpred[ok] - X[ok]).max() <= 1e-8
+    assert (info.return_code[~ok] == 4).all()  # too large for the condensed kernel -> ACADOS_QP_FAILURE, outputs untouched
+    assert not forces[~ok].any()
+
+
+def test_gait_golden_bit_exact():
+    import os
+
+    from dfki_quad_b200 import gait
+
+    G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "mpc_golden.npz"))
+    per, duty, off = gait.gait_arrays(G["gait_ids"])
+    c, s = gait.contact_schedule(per, duty, off, G["gait_phase"], 100, 0.05, measured_contact=G["gait_meas"])
+    assert np.array_equal(c, G["gait_contact"]) and np.array_equal(s.view(np.uint64), G["gait_swing"].view(np.uint64))
