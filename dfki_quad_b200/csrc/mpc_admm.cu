@@ -223,29 +223,38 @@ __device__ void nnls3(const double (*M)[3], int m, const double (&b)[3], double 
 // dense helpers on the shared-memory matrix K (column-major, odd leading dimension LD => row and column
 // accesses across a warp are both bank-conflict free for 8-byte words)
 
-// in-place Gauss-Jordan inverse of an SPD matrix (no pivoting), thread i owns row i.
+// in-place Gauss-Jordan inverse of an SPD matrix (no pivoting), thread i owns row i.  Per pivot p: the pivot row is
+// staged in prow[], every other row does a rank-1 update against it, and the pivot row itself is rescaled with one
+// element per thread (no single-thread tail, no divergent long branch).
 template <int LD>
 __device__ __forceinline__ void gj_invert(double *K, int n, double *prow) {
   const int i = threadIdx.x;
+  double *Ki = K + i;
   for (int p = 0; p < n; ++p) {
-    if (i < n) prow[i] = K[i * LD + p];  // pivot row element (p, i)
+    double pi = 0.0;
+    if (i < n) {
+      pi = K[i * LD + p];  // pivot row element (p, i)
+      prow[i] = pi;
+    }
     __syncthreads();
     if (i < n) {
       const double d = 1.0 / prow[p];
-      if (i == p) {
-        for (int j = 0; j < n; ++j) K[j * LD + p] = prow[j] * d;
-        K[p * LD + p] = d;
-      } else {
-        const double f = K[p * LD + i] * d;
+      if (i != p) {
+        const double f = Ki[p * LD] * d;
         int j = 0;
-        for (; j + 1 < n; j += 2) {
-          const double2 pr = *reinterpret_cast<const double2 *>(prow + j);
-          K[j * LD + i] = fma(-f, pr.x, K[j * LD + i]);
-          K[(j + 1) * LD + i] = fma(-f, pr.y, K[(j + 1) * LD + i]);
+        for (; j + 3 < n; j += 4) {
+          const double2 p01 = *reinterpret_cast<const double2 *>(prow + j);
+          const double2 p23 = *reinterpret_cast<const double2 *>(prow + j + 2);
+          const double k0 = Ki[j * LD], k1 = Ki[(j + 1) * LD], k2 = Ki[(j + 2) * LD], k3 = Ki[(j + 3) * LD];
+          Ki[j * LD] = fma(-f, p01.x, k0);
+          Ki[(j + 1) * LD] = fma(-f, p01.y, k1);
+          Ki[(j + 2) * LD] = fma(-f, p23.x, k2);
+          Ki[(j + 3) * LD] = fma(-f, p23.y, k3);
         }
-        if (j < n) K[j * LD + i] = fma(-f, prow[j], K[j * LD + i]);
-        K[p * LD + i] = -f;
+        for (; j < n; ++j) Ki[j * LD] = fma(-f, prow[j], Ki[j * LD]);
+        Ki[p * LD] = -f;
       }
+      K[i * LD + p] = (i == p) ? d : pi * d;  // rescaled pivot row, element (p, i)
     }
     __syncthreads();
   }
