@@ -17,8 +17,9 @@ cudaError_t launch_mpc_admm(int bin, const MpcParams &P, const MpcBuffers &B, in
 int admm_block_size(int bin);
 int admm_occupancy(int bin);
 cudaError_t launch_mpc_riccati(const MpcParams &P, int n, const double *in, const uint8_t *contact, double *forces,
-                               double *xpred, b200qp_solver_info *info, double *lam_box, double *lam_g,
-                               cudaStream_t st);
+                               double *xpred, b200qp_solver_info *info, double *lam_box, double *lam_g, double *scratch,
+                               int *next, int grid, cudaStream_t st);
+int riccati_grid(int num_sms);
 }  // namespace b200qp
 
 using namespace b200qp;
@@ -50,6 +51,8 @@ struct b200qp_mpc {
   int *d_bin_lists = nullptr;  // [3][max_batch]
   double *d_hscratch[3] = {nullptr, nullptr, nullptr};
   int grid[3] = {0, 0, 0};
+  double *d_ric_scratch = nullptr;
+  int ric_grid = 0;
   // pinned staging
   double *h_in = nullptr, *h_forces = nullptr, *h_xpred = nullptr;
   uint8_t *h_contact = nullptr;
@@ -146,6 +149,12 @@ int32_t b200qp_mpc_create(const b200qp_mpc_config *cfg, b200qp_mpc **out) {
       CK(cudaMalloc(&h->d_hscratch[b], (size_t)g * bs * bs * sizeof(double)));
     }
   }
+  if (cfg->solver == B200QP_SOLVER_SPARSE_RICCATI) {
+    int g = riccati_grid(h->num_sms);
+    if ((size_t)g > nb) g = (int)nb;
+    h->ric_grid = g;
+    CK(cudaMalloc(&h->d_ric_scratch, (size_t)g * B200QP_MAX_HORIZON * 288 * sizeof(double)));
+  }
   CK(cudaMallocHost(&h->h_in, nb * in_d * sizeof(double)));
   CK(cudaMallocHost(&h->h_contact, nb * N * 4));
   CK(cudaMallocHost(&h->h_forces, nb * N * 12 * sizeof(double)));
@@ -168,6 +177,7 @@ void b200qp_mpc_destroy(b200qp_mpc *h) {
   cudaFree(h->d_bin_count);
   cudaFree(h->d_bin_lists);
   for (int b = 0; b < 3; ++b) cudaFree(h->d_hscratch[b]);
+  cudaFree(h->d_ric_scratch);
   cudaFreeHost(h->h_in);
   cudaFreeHost(h->h_contact);
   cudaFreeHost(h->h_forces);
@@ -236,8 +246,10 @@ static int32_t solve_device_impl(b200qp_mpc *h, int32_t n, const double *d_in, c
       ++launches;
     }
   } else {
+    CK(cudaMemsetAsync(h->d_bin_count, 0, 8 * sizeof(int), h->stream));
     CK(launch_mpc_riccati(h->P, n, d_in, d_contact, d_forces, d_xpred, d_info,
-                          h->want_duals ? h->d_lam_box : nullptr, h->want_duals ? h->d_lam_g : nullptr, h->stream));
+                          h->want_duals ? h->d_lam_box : nullptr, h->want_duals ? h->d_lam_g : nullptr,
+                          h->d_ric_scratch, h->d_bin_count + 7, h->ric_grid, h->stream));
     ++launches;
   }
   CK(cudaEventRecord(h->ev1, h->stream));

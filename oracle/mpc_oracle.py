@@ -649,3 +649,112 @@ def solve_reference_qp(N, rec, contacts, params, method="ipm"):
     U = u.reshape(N, NU)
     X = rollout(qp, U)
     return U, X, qp, dq
+
+
+# ------------------------------------------------------------------ solver 3: sparse OCP-QP, Riccati-based Mehrotra IPM
+def _foot_G(mu):
+    return np.array([[1, 0, 0], [-1, 0, 0], [0, 1, 0], [0, -1, 0], [0, 0, 1], [0, 0, -1], [1, 0, -mu], [-1, 0, -mu],
+                     [0, 1, -mu], [0, -1, -mu]], float)
+
+
+def _chol_solve(L, b):
+    import scipy.linalg as sla
+
+    return sla.solve_triangular(L.T, sla.solve_triangular(L, b, lower=True), lower=False)
+
+
+def solve_riccati_ipm(qp, params, tol=1e-10, max_iter=60, return_info=False):
+    """HPIPM-style solve of the stage-wise QP of build_ocp_qp: Mehrotra predictor-corrector, every Newton system solved
+    by a Riccati recursion on (A, B_k, Q, R~_k = alpha I + G'WG).  States are the full 13-vector (the g state included),
+    so this is independent of the structure exploitation in the CUDA kernel."""
+    N, A, Q = qp["N"], qp["A"], np.diag(qp["Q"])
+    mu_f, fmin, fmax, alpha = params["mu"], params["fmin"], params["fmax"], qp["R"]
+    Gf = _foot_G(mu_f)
+    hf = np.array([fmax, fmax, fmax, fmax, fmax, -fmin, 0, 0, 0, 0], float)
+    on = np.asarray(qp["contacts"]).astype(bool)
+    G = np.zeros((N, 40, 12))
+    for f in range(4):
+        G[:, 10 * f:10 * f + 10, 3 * f:3 * f + 3] = Gf
+    act = np.repeat(on, 10, axis=1)  # [N,40] rows that exist
+    h = np.tile(hf, 4)
+    U = np.zeros((N, 12))
+    s = np.where(act, np.maximum(h, 1.0), 1.0)
+    z = np.where(act, 1.0, 0.0)
+    m = max(int(act.sum()), 1)
+    pin = ~np.repeat(on, 3, axis=1)  # swing inputs pinned to zero
+    it = 0
+    for it in range(max_iter + 1):
+        X = rollout(qp, U)
+        lam = np.zeros((N + 2, NX))
+        for k in range(N, 0, -1):
+            lam[k] = qp["Q"] * X[k] + qp["q"][k] + (A.T @ lam[k + 1] if k < N else 0.0)
+        rd = np.array([alpha * U[k] + qp["B"][k].T @ lam[k + 1] + G[k].T @ z[k] for k in range(N)])
+        rd[pin] = 0.0
+        rp = np.where(act, np.einsum("kij,kj->ki", G, U) + s - h, 0.0)
+        mu_c = float((s * z)[act].sum()) / m
+        res = max(np.abs(rd).max(), np.abs(rp).max(), float((s * z)[act].max(initial=0.0)))
+        if res <= tol or not act.any():
+            break
+        W = np.where(act, z / s, 0.0)
+        # backward Riccati (matrices)
+        Pm = Q.copy()
+        Ks, Hinv = [None] * N, [None] * N
+        for k in range(N - 1, -1, -1):
+            B = qp["B"][k]
+            Rt = alpha * np.eye(12) + G[k].T @ (W[k][:, None] * G[k])
+            Huu = Rt + B.T @ Pm @ B
+            Hux = B.T @ Pm @ A
+            p_ = pin[k]
+            Huu[p_, :] = 0.0
+            Huu[:, p_] = 0.0
+            Huu[p_, p_] = 1.0
+            Hux[p_, :] = 0.0
+            Hinv[k] = np.linalg.cholesky(Huu)  # Cholesky factor; explicit inverses lose the endgame accuracy
+            Ks[k] = -_chol_solve(Hinv[k], Hux)
+            Pm = Q + A.T @ Pm @ A + Hux.T @ Ks[k]
+            Pm = 0.5 * (Pm + Pm.T)
+
+        def solve(rc):
+            t = np.where(act, (z * rp - rc) / s, 0.0)
+            rt = rd + np.einsum("kij,ki->kj", G, t)
+            rt[pin] = 0.0
+            p = np.zeros(NX)
+            kk = np.zeros((N, 12))
+            for k in range(N - 1, -1, -1):
+                hu = rt[k] + qp["B"][k].T @ p
+                hu[pin[k]] = 0.0
+                kk[k] = -_chol_solve(Hinv[k], hu)
+                p = A.T @ p + Ks[k].T @ hu
+            dx = np.zeros(NX)
+            dU = np.zeros((N, 12))
+            for k in range(N):
+                dU[k] = Ks[k] @ dx + kk[k]
+                dU[k][pin[k]] = 0.0
+                dx = A @ dx + qp["B"][k] @ dU[k]
+            ds = np.where(act, -rp - np.einsum("kij,kj->ki", G, dU), 0.0)
+            dz = np.where(act, (-rc - z * ds) / s, 0.0)
+            return dU, ds, dz
+
+        def maxstep(ds, dz):
+            a = 1.0
+            msk = act & (ds < 0)
+            if msk.any():
+                a = min(a, float(np.min(-s[msk] / ds[msk])))
+            msk = act & (dz < 0)
+            if msk.any():
+                a = min(a, float(np.min(-z[msk] / dz[msk])))
+            return a
+
+        dU, ds, dz = solve(s * z)
+        a = maxstep(ds, dz)
+        mu_aff = float(((s + a * ds) * (z + a * dz))[act].sum()) / m
+        sig = (mu_aff / max(mu_c, 1e-300)) ** 3
+        dU, ds, dz = solve(s * z + ds * dz - sig * mu_c)
+        a = min(1.0, 0.995 * maxstep(ds, dz))
+        U = U + a * dU
+        s = np.where(act, s + a * ds, s)
+        z = np.where(act, z + a * dz, z)
+    U[pin] = 0.0
+    if return_info:
+        return U, dict(iters=it, res=res, z=z)
+    return U

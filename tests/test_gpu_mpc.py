@@ -270,3 +270,81 @@ def test_gait_golden_bit_exact():
     per, duty, off = gait.gait_arrays(G["gait_ids"])
     c, s = gait.contact_schedule(per, duty, off, G["gait_phase"], 100, 0.05, measured_contact=G["gait_meas"])
     assert np.array_equal(c, G["gait_contact"]) and np.array_equal(s.view(np.uint64), G["gait_swing"].view(np.uint64))
+
+
+# ---------------------------------------------------------------------------------------------------- K2b Riccati IPM
+def _check_riccati(N, batch, mpc, forces, xpred, info, params, idx, grf_tol=1e-5):
+    lam_box, lam_g = mpc.get_duals(len(batch["rec"]))
+    for p in idx:
+        assert info.return_code[p] == 0, (p, info.return_code[p], info.kkt[p])
+        U, X, qp, dq = mo.solve_reference_qp(N, batch["rec"][p], batch["contact"][p], params)
+        x2, _, ok = mo.polish_active_set(dq["H"], dq["g"], dq["A"], np.where(dq["l"] <= -mo.INF_THRESHOLD, -np.inf, dq["l"]),
+                                         np.where(dq["u"] >= mo.INF_THRESHOLD, np.inf, dq["u"]), U.reshape(-1),
+                                         _ipm_duals(dq, U.reshape(-1)))
+        Uref = x2.reshape(N, 12) if ok else U
+        Ug = forces[p].reshape(N, 12)
+        scale = max(1.0, np.abs(Uref).max())
+        assert np.abs(Ug - Uref).max() / scale <= grf_tol, (p, np.abs(Ug - Uref).max() / scale)
+        kkt = mo.kkt_residuals(qp, Ug, lam_box[p], lam_g[p])  # interior point: check with the solver's own duals
+        assert max(kkt) <= 1e-6, (p, kkt)
+        assert np.abs(xpred[p] - mo.rollout(qp, Ug)).max() <= 1e-9 * max(1.0, np.abs(xpred[p]).max())
+        mask = np.repeat(batch["contact"][p].reshape(N, 4), 3, axis=1) == 0
+        assert np.all(Ug[mask] == 0.0)
+
+
+@pytest.mark.parametrize("gaits,N", [(("TROT", "PACE", "BOUND"), 16), (("STAND", "WALKING_TROT", "STATIC_WALK"), 10),
+                                      (("TROT", "STAND"), 20)])
+def test_riccati_parity_small(gaits, N, go2_params):
+    from dfki_quad_b200 import sequencer
+
+    n = 16
+    batch = sequencer.random_batch(n, N, seed=300 + N, gaits=gaits)
+    mpc = _mpc(N, n, solver="SPARSE_RICCATI")
+    forces, xpred, info = mpc.solve_records(batch["rec"], batch["contact"])
+    assert info.success.all(), (info.return_code, info.kkt)
+    _check_riccati(N, batch, mpc, forces, xpred, info, go2_params, range(n))
+
+
+def test_riccati_golden_h16():
+    import os
+
+    G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "mpc_golden.npz"))
+    for tag, N in (("h16_mixed", 16), ("h10_mixed", 10)):
+        rec, contact, F, X = G[tag + "_rec"], G[tag + "_contact"], G[tag + "_forces"], G[tag + "_xpred"]
+        mpc = _mpc(N, rec.shape[0], solver="PARTIAL_CONDENSING_HPIPM")
+        forces, xpred, info = mpc.solve_records(rec, contact)
+        assert info.success.all()
+        assert np.abs(forces - F).max() <= 1e-5 * max(1.0, np.abs(F).max())
+        assert np.abs(xpred - X).max() <= 1e-5  # interior-point solution vs polished vertex
+
+
+def test_riccati_matches_admm(go2_params):
+    """The two kernels solve the same QP: their GRFs agree to 1e-5 relative on a mixed-gait batch."""
+    from dfki_quad_b200 import sequencer
+
+    N, n = 10, 256
+    batch = sequencer.random_batch(n, N, seed=77, gaits=("TROT", "PACE", "BOUND", "STAND"))
+    fa, xa, ia = _mpc(N, n).solve_records(batch["rec"], batch["contact"])
+    fr, xr, ir = _mpc(N, n, solver="SPARSE_RICCATI").solve_records(batch["rec"], batch["contact"])
+    assert ia.success.all() and ir.success.all()
+    scale = np.maximum(1.0, np.abs(fa).reshape(n, -1).max(axis=1))
+    assert (np.abs(fa - fr).reshape(n, -1).max(axis=1) / scale).max() <= 1e-5
+    assert np.abs(xa - xr).max() <= 1e-5
+
+
+def test_config3_full_batch_riccati(go2_params):
+    """BASELINE.json configs[2]: 16384 mixed trot/pace/bound problems, N = 16, sparse Riccati kernel."""
+    from dfki_quad_b200 import sequencer
+
+    N, n = 16, 16384
+    batch = sequencer.random_batch(n, N, seed=20261019 + 3, gaits=("TROT", "PACE", "BOUND"))
+    mpc = _mpc(N, n, solver="SPARSE_RICCATI")
+    forces, xpred, info = mpc.solve_records(batch["rec"], batch["contact"])
+    assert info.success.mean() >= 0.999, (info.success.mean(), np.unique(info.return_code, return_counts=True))
+    assert np.all(info.kkt[info.success].max(axis=1) <= 1e-6)
+    rng = np.random.default_rng(4)
+    idx = rng.choice(np.nonzero(info.success)[0], 12, replace=False)
+    _check_riccati(N, batch, mpc, forces, xpred, info, go2_params, idx)
+    F = forces.reshape(n, N, 4, 3)[info.success]
+    assert np.all(F[batch["contact"][info.success] == 0] == 0.0)
+    assert np.all(np.abs(F[..., 0]) <= 0.6 * F[..., 2] + 1e-6) and np.all(F[..., 2] >= -1e-6)
