@@ -23,7 +23,13 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 KKT_TOL = 1e-6
-WORKLOAD = "go2_trot_condensed_mpc_h10_admm"
+# BASELINE.json configs: [1] is the configuration the metric is quoted on (default); [2] is the Riccati config.
+WORKLOADS = {
+    "config2": dict(name="go2_trot_condensed_mpc_h10_admm", horizon=10, batch=4096, gaits=("TROT",), solver="CONDENSED_ADMM",
+                    seed=20261019 + 2, kernel="mpc_admm_kernel<64,64>"),
+    "config3": dict(name="go2_mixed_sparse_mpc_h16_riccati", horizon=16, batch=16384, gaits=("TROT", "PACE", "BOUND"),
+                    solver="SPARSE_RICCATI", seed=20261019 + 3, kernel="mpc_riccati_kernel<64>"),
+}
 
 
 def algorithmic_bytes(N):
@@ -115,8 +121,9 @@ def run_reference(args):
     from oracle import mpc_oracle as mo
     from oracle import cpu_baseline as cb
 
-    N, B = args.horizon, args.batch
-    batch = cb.make_batch_cpu(B, N, seed=20261019 + 2)
+    wl = WORKLOADS[args.workload]
+    N, B = args.horizon or wl["horizon"], args.batch or wl["batch"]
+    batch = cb.make_batch_cpu(B, N, seed=wl["seed"], gaits=wl["gaits"])
     per_step_budget = 8.0
     total_solved, total_t = 0, 0.0
     res = None
@@ -130,7 +137,7 @@ def run_reference(args):
         "impl": "reference", "metric": "MPC QP solves/sec (Go2, horizon 10, batch N)", "value": value, "unit": "solves/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total_t / max(args.steps, 1),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "horizon": N, "batch_per_gpu": B, "gait": "TROT", "solver": res["solver"]},
+        "config": {"workload": wl["name"], "horizon": N, "batch_per_gpu": B, "gait": "/".join(wl["gaits"]), "solver": res["solver"]},
         "cpu_baseline": {"value": value, "unit": "solves/s", "cores": res["cores"], "kind": res["kind"], "sample": res["sample"]},
         "e2e": {"value": value, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -155,11 +162,12 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = local
     torch.cuda.set_device(dev)
-    N, B = args.horizon, args.batch
+    wl = WORKLOADS[args.workload]
+    N, B = args.horizon or wl["horizon"], args.batch or wl["batch"]
     cfg = sequencer.GO2_MPC
     # every rank gets its own batch (weak scaling): seed offset by rank
-    batch = sequencer.random_batch(B, N, seed=20261019 + 2 + 1000 * rank, gaits=("TROT",), device=dev)
-    mpc = BatchedMPC(cfg["alpha"], cfg["state_weights_move"], cfg["mu"], cfg["fmin"], cfg["fmax"], "CONDENSED_ADMM",
+    batch = sequencer.random_batch(B, N, seed=wl["seed"] + 1000 * rank, gaits=wl["gaits"], device=dev)
+    mpc = BatchedMPC(cfg["alpha"], cfg["state_weights_move"], cfg["mu"], cfg["fmin"], cfg["fmax"], wl["solver"],
                      horizon=N, dt=cfg["dt"], max_batch=B, device=dev)
     ext = torch.cuda.ExternalStream(mpc.stream(), device=dev)
     rec_h = torch.from_numpy(batch["rec"]).pin_memory()
@@ -239,7 +247,10 @@ def run_b200(args):
         # also contains the bin kernel and two empty-bin launches (a few microseconds)
         kern_s = (total_ms / args.steps) * 1e-3
         achieved = ab * B / kern_s / 1e9
-        fl = float(sum(algorithmic_flops(N, r["n_free"], r["iterations"], r["polish_rounds"]) for r in info))
+        if wl["solver"] == "CONDENSED_ADMM":
+            fl = float(sum(algorithmic_flops(N, r["n_free"], r["iterations"], r["polish_rounds"]) for r in info))
+        else:  # Riccati IPM: per iteration N stages x ~9.6 kFLOP structured matrix sweep + 2 vector sweeps (~1.2 kFLOP each)
+            fl = float(info["iterations"].sum()) * N * (9600.0 + 2 * 1200.0)
         cpu = None
         if not args.no_cpu_baseline:
             try:
@@ -250,7 +261,7 @@ def run_b200(args):
             "metric": "MPC QP solves/sec (Go2, horizon 10, batch N)", "value": value, "unit": "solves/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms_max / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "horizon": N, "batch_per_gpu": B, "gait": "TROT", "solver": "CONDENSED_ADMM",
+            "config": {"workload": wl["name"], "horizon": N, "batch_per_gpu": B, "gait": "/".join(wl["gaits"]), "solver": wl["solver"],
                        "l2": "256 MiB flush between timed iterations", "converged_fraction": conv_all / issued_all,
                        "mean_iterations": float(info["iterations"].mean()), "mean_polish_rounds": float(info["polish_rounds"].mean()),
                        "kkt_max": float(info["kkt"][conv].max()) if n_conv else None, "parallelism": f"shard{world}"},
@@ -259,7 +270,7 @@ def run_b200(args):
             "gpu_launches": int(launches_per_step * args.steps),
             "clocks": clocks.summary(),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "kernel": "mpc_admm_kernel<64,64>",
+                         "traffic": None, "peak_source": peak_src, "kernel": wl["kernel"],
                          "algorithmic_bytes_per_solve": ab,
                          "note": "latency/FP64-bound on-chip solve: HBM fraction is tiny by design (SURVEY.md 8d)"},
             "fp64": {"flops_per_step": fl, "achieved_tflops": fl / kern_s / 1e12, "nominal_peak_tflops": 37.0},
@@ -281,8 +292,9 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=4096)
-    ap.add_argument("--horizon", type=int, default=10)
+    ap.add_argument("--workload", default="config2", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0, help="problems per GPU (0 = the workload's own)")
+    ap.add_argument("--horizon", type=int, default=0)
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

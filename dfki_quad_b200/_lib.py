@@ -35,11 +35,17 @@ class SolverInfo(C.Structure):
                 ("kkt", C.c_double * 4)]
 
 
+class WbcConfig(C.Structure):
+    _fields_ = [("nq", C.c_int32), ("neq", C.c_int32), ("nin", C.c_int32), ("max_batch", C.c_int32), ("device", C.c_int32),
+                ("max_iter", C.c_int32), ("kkt_tol", C.c_double)]
+
+
 EXPORTS = [
     "b200qp_version", "b200qp_device_count", "b200qp_last_error", "b200qp_mpc_create", "b200qp_mpc_destroy",
     "b200qp_mpc_set_state_weights", "b200qp_mpc_set_input_weights", "b200qp_mpc_set_fmax", "b200qp_mpc_set_mu",
     "b200qp_mpc_solve_batch", "b200qp_mpc_solve_batch_device", "b200qp_mpc_get_duals", "b200qp_mpc_get_condensed",
     "b200qp_mpc_last_timing", "b200qp_mpc_stream", "b200qp_gait_schedule", "b200qp_gait_schedule_device",
+    "b200qp_wbc_create", "b200qp_wbc_destroy", "b200qp_wbc_solve_batch", "b200qp_wbc_solve_batch_device", "b200qp_wbc_stream",
 ]
 
 _lib = None
@@ -75,6 +81,13 @@ def load() -> C.CDLL:
     lib.b200qp_mpc_stream.restype = vp
     lib.b200qp_gait_schedule.argtypes = [i32, i32, i32, dbl, vp, vp, vp, vp, vp, dbl, dbl, vp, vp, vp, vp]
     lib.b200qp_gait_schedule_device.argtypes = [i32, i32, dbl, vp, vp, vp, vp, vp, dbl, dbl, vp, vp, vp, vp, vp]
+    lib.b200qp_wbc_create.argtypes = [p(WbcConfig), p(vp)]
+    lib.b200qp_wbc_destroy.argtypes = [vp]
+    lib.b200qp_wbc_destroy.restype = None
+    lib.b200qp_wbc_solve_batch.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, vp]
+    lib.b200qp_wbc_solve_batch_device.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, vp, i32]
+    lib.b200qp_wbc_stream.argtypes = [vp]
+    lib.b200qp_wbc_stream.restype = vp
     for name in EXPORTS:
         fn = getattr(lib, name)
         if fn.restype is C.c_int:  # default restype

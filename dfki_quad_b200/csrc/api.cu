@@ -20,6 +20,15 @@ cudaError_t launch_mpc_riccati(const MpcParams &P, int n, const double *in, cons
                                double *xpred, b200qp_solver_info *info, double *lam_box, double *lam_g, double *scratch,
                                int *next, int grid, cudaStream_t st);
 int riccati_grid(int num_sms);
+struct WbcParams {
+  int nq, neq, nin;
+  double kkt_tol;
+  int max_iter;
+};
+size_t wbc_smem_bytes(const WbcParams &P);
+int wbc_grid(const WbcParams &P, int num_sms);
+cudaError_t launch_wbc_qp(const WbcParams &P, int n, const double *H, const double *g, const double *A, const double *lo,
+                          const double *hi, double *x, b200qp_solver_info *info, int *next, int grid, cudaStream_t st);
 }  // namespace b200qp
 
 using namespace b200qp;
@@ -474,5 +483,116 @@ int32_t b200qp_gait_schedule(int32_t device, int32_t n, int32_t steps, double dt
   cudaFree(d_ub);
   return rc;
 }
+
+
+// ---- WBC QP (kernel K3) ---------------------------------------------------------------------------------------------
+}  // extern "C"
+
+struct b200qp_wbc {
+  b200qp_wbc_config cfg;
+  WbcParams P;
+  cudaStream_t stream = nullptr;
+  int grid = 0;
+  double *d_H = nullptr, *d_g = nullptr, *d_A = nullptr, *d_lo = nullptr, *d_hi = nullptr, *d_x = nullptr;
+  b200qp_solver_info *d_info = nullptr;
+  int *d_next = nullptr;
+};
+
+extern "C" {
+
+int32_t b200qp_wbc_create(const b200qp_wbc_config *cfg, b200qp_wbc **out) {
+  if (!cfg || !out) return B200QP_ERR_ARG;
+  *out = nullptr;
+  if (cfg->nq < 1 || cfg->nq > 48 || cfg->neq < 0 || cfg->neq > 32 || cfg->nin < 0 || cfg->nin > 64 || cfg->max_batch < 1) {
+    g_err = "b200qp_wbc_create: invalid configuration";
+    return B200QP_ERR_ARG;
+  }
+  int ndev = 0;
+  CK(cudaGetDeviceCount(&ndev));
+  if (cfg->device < 0 || cfg->device >= ndev) {
+    g_err = "b200qp_wbc_create: no such CUDA device (there is no CPU fallback)";
+    return B200QP_ERR_CUDA;
+  }
+  CK(cudaSetDevice(cfg->device));
+  b200qp_wbc *h = new (std::nothrow) b200qp_wbc();
+  if (!h) return B200QP_ERR_ARG;
+  h->cfg = *cfg;
+  h->P.nq = cfg->nq;
+  h->P.neq = cfg->neq;
+  h->P.nin = cfg->nin;
+  h->P.kkt_tol = cfg->kkt_tol > 0 ? cfg->kkt_tol : 1e-6;
+  h->P.max_iter = cfg->max_iter > 0 ? cfg->max_iter : 40;
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, cfg->device));
+  h->grid = wbc_grid(h->P, prop.multiProcessorCount);
+  if (h->grid <= 0) {
+    g_err = "b200qp_wbc_create: problem dimensions do not fit shared memory";
+    delete h;
+    return B200QP_ERR_UNSUPPORTED;
+  }
+  const size_t nb = cfg->max_batch, nq = cfg->nq, nc = cfg->neq + cfg->nin;
+  CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  CK(cudaMalloc(&h->d_H, nb * nq * nq * sizeof(double)));
+  CK(cudaMalloc(&h->d_g, nb * nq * sizeof(double)));
+  CK(cudaMalloc(&h->d_A, nb * nc * nq * sizeof(double)));
+  CK(cudaMalloc(&h->d_lo, nb * nc * sizeof(double)));
+  CK(cudaMalloc(&h->d_hi, nb * nc * sizeof(double)));
+  CK(cudaMalloc(&h->d_x, nb * nq * sizeof(double)));
+  CK(cudaMalloc(&h->d_info, nb * sizeof(b200qp_solver_info)));
+  CK(cudaMalloc(&h->d_next, sizeof(int)));
+  *out = h;
+  return B200QP_OK;
+}
+
+void b200qp_wbc_destroy(b200qp_wbc *h) {
+  if (!h) return;
+  cudaSetDevice(h->cfg.device);
+  cudaFree(h->d_H);
+  cudaFree(h->d_g);
+  cudaFree(h->d_A);
+  cudaFree(h->d_lo);
+  cudaFree(h->d_hi);
+  cudaFree(h->d_x);
+  cudaFree(h->d_info);
+  cudaFree(h->d_next);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+int32_t b200qp_wbc_solve_batch_device(b200qp_wbc *h, int32_t n, const double *d_H, const double *d_g, const double *d_A,
+                                      const double *d_lower_y, const double *d_upper_y, double *d_x,
+                                      b200qp_solver_info *d_info, int32_t sync) {
+  if (!h || n < 0 || n > h->cfg.max_batch || (n > 0 && (!d_H || !d_g || !d_A || !d_lower_y || !d_upper_y || !d_x || !d_info)))
+    return B200QP_ERR_ARG;
+  if (n == 0) return B200QP_OK;
+  CK(cudaSetDevice(h->cfg.device));
+  CK(cudaMemsetAsync(h->d_next, 0, sizeof(int), h->stream));
+  CK(launch_wbc_qp(h->P, n, d_H, d_g, d_A, d_lower_y, d_upper_y, d_x, d_info, h->d_next, h->grid, h->stream));
+  if (sync) CK(cudaStreamSynchronize(h->stream));
+  return B200QP_OK;
+}
+
+int32_t b200qp_wbc_solve_batch(b200qp_wbc *h, int32_t n, const double *H, const double *g, const double *A,
+                               const double *lower_y, const double *upper_y, double *x, b200qp_solver_info *info) {
+  if (!h || n < 0 || n > h->cfg.max_batch || (n > 0 && (!H || !g || !A || !lower_y || !upper_y || !x || !info)))
+    return B200QP_ERR_ARG;
+  if (n == 0) return B200QP_OK;
+  CK(cudaSetDevice(h->cfg.device));
+  const size_t nn = n, nq = h->cfg.nq, nc = h->cfg.neq + h->cfg.nin;
+  CK(cudaMemcpyAsync(h->d_H, H, nn * nq * nq * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->d_g, g, nn * nq * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->d_A, A, nn * nc * nq * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->d_lo, lower_y, nn * nc * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->d_hi, upper_y, nn * nc * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->d_x, x, nn * nq * sizeof(double), cudaMemcpyHostToDevice, h->stream));  // keep caller's x on failure
+  int32_t rc = b200qp_wbc_solve_batch_device(h, n, h->d_H, h->d_g, h->d_A, h->d_lo, h->d_hi, h->d_x, h->d_info, 0);
+  if (rc != B200QP_OK) return rc;
+  CK(cudaMemcpyAsync(x, h->d_x, nn * nq * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(info, h->d_info, nn * sizeof(b200qp_solver_info), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return B200QP_OK;
+}
+
+void *b200qp_wbc_stream(b200qp_wbc *h) { return h ? (void *)h->stream : nullptr; }
 
 }  // extern "C"

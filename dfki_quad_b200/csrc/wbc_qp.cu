@@ -1,0 +1,438 @@
+// Kernel K3: batched dense QP for the whole-body-control task-space problem, one thread block per QP, FP64.
+//     min 1/2 x'Hx + g'x   s.t.   Aeq x = beq,   lo <= Ain x <= hi          (nq <= 48, neq <= 32, nin <= 64)
+// Replaces the `wbc::QPSolver` plugin call inside `wbc_scene_->solve(qp)`
+// (ws/src/controllers/src/mit_controller/wbc_arc_opt.cpp:51-74,297): Eiquadprog / ProxQP / qpOASES / OSQP / qpSWIFT /
+// HPIPM behind ARC-OPT.  Same Mehrotra predictor-corrector machinery as the MPC Riccati kernel (K2b), with the Newton
+// system reduced by block elimination instead of a Riccati sweep:
+//     Phi = H + Ain' W Ain = L L',   Y = L^-1 Aeq',   S = Y'Y = Ls Ls'
+//     dnu = S^-1 (re + Y'u1),  dx = L^-T (u1 - Y dnu),   u1 = -L^-1 r~
+// Cholesky factors and explicit triangular inverses (not Phi^-1: see K2b) live in shared memory; thread r owns the
+// (s, z) pairs of inequality row r (lower and upper side) in registers.
+#include "common.cuh"
+
+namespace b200qp {
+
+struct WbcParams {
+  int nq, neq, nin;
+  double kkt_tol;
+  int max_iter;
+};
+
+namespace {
+constexpr double WBIG = 1.0e300;
+constexpr double WINF = 1.0e19;  // |bound| >= this: side absent
+
+template <class Op>
+__device__ __forceinline__ double wblock_reduce(double v, double *red, Op op) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = op(v, __shfl_xor_sync(0xffffffffu, v, o));
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  double m = red[0];
+  for (int w = 1; w < nw; ++w) m = op(m, red[w]);
+  return m;
+}
+struct WMax { __device__ double operator()(double a, double b) const { return fmax(a, b); } };
+struct WMin { __device__ double operator()(double a, double b) const { return fmin(a, b); } };
+struct WSum { __device__ double operator()(double a, double b) const { return a + b; } };
+
+// In-place lower Cholesky of the n x n row-major matrix A (ld = n) by the whole block, then Li = L^-1 (row-major).
+__device__ void chol_and_inverse(double *A, double *Li, int n, double *diag0) {
+  const int tid = threadIdx.x, BS = blockDim.x;
+  if (tid < n) diag0[tid] = A[tid * n + tid];
+  __syncthreads();
+  for (int p = 0; p < n; ++p) {
+    const double flo = 1e-13 * diag0[p];
+    const double piv = A[p * n + p];
+    const double d = sqrt(piv > flo ? piv : flo);
+    __syncthreads();
+    for (int i = p + tid; i < n; i += BS) A[i * n + p] = (i == p) ? d : A[i * n + p] / d;
+    __syncthreads();
+    const int rem = n - p - 1;
+    for (int e = tid; e < rem * rem; e += BS) {
+      const int i = p + 1 + e / rem, j = p + 1 + e % rem;
+      if (j <= i) A[i * n + j] -= A[i * n + p] * A[j * n + p];
+    }
+    __syncthreads();
+  }
+  // L^-1: thread j computes column j by forward substitution
+  for (int j = tid; j < n; j += BS) {
+    for (int i = 0; i < j; ++i) Li[i * n + j] = 0.0;
+    for (int i = j; i < n; ++i) {
+      double acc = (i == j) ? 1.0 : 0.0;
+      for (int k = j; k < i; ++k) acc -= A[i * n + k] * Li[k * n + j];
+      Li[i * n + j] = acc / A[i * n + i];
+    }
+  }
+  __syncthreads();
+}
+
+// dx, dnu from r~ (srt) and re (sre):  u1 = -L^-1 r~,  dnu = S^-1 (re + Y'u1),  dx = L^-T (u1 - Y dnu)
+__device__ void kkt_solve(int nq, int me, const double *sLi, const double *sY, const double *sSi, const double *srt,
+                          const double *sre, double *su1, double *sv, double *sdx, double *sdnu) {
+  const int tid = threadIdx.x, BS = blockDim.x;
+  for (int i = tid; i < nq; i += BS) {
+    double a = 0.0;
+    for (int k = 0; k <= i; ++k) a = fma(sLi[i * nq + k], srt[k], a);
+    su1[i] = -a;
+  }
+  __syncthreads();
+  for (int r = tid; r < me; r += BS) {
+    double a = sre[r];
+    for (int i = 0; i < nq; ++i) a = fma(sY[i * me + r], su1[i], a);
+    sv[r] = a;
+  }
+  __syncthreads();
+  for (int r = tid; r < me; r += BS) {
+    double a = 0.0;
+    for (int k = 0; k <= r; ++k) a = fma(sSi[r * me + k], sv[k], a);
+    sdnu[r] = a;
+  }
+  __syncthreads();
+  double dn = 0.0;
+  if (tid < me)
+    for (int k = tid; k < me; ++k) dn = fma(sSi[k * me + tid], sdnu[k], dn);
+  __syncthreads();
+  if (tid < me) sdnu[tid] = dn;
+  __syncthreads();
+  for (int i = tid; i < nq; i += BS) {
+    double a = su1[i];
+    for (int r = 0; r < me; ++r) a = fma(-sY[i * me + r], sdnu[r], a);
+    sv[i] = a;
+  }
+  __syncthreads();
+  for (int i = tid; i < nq; i += BS) {
+    double a = 0.0;
+    for (int k = i; k < nq; ++k) a = fma(sLi[k * nq + i], sv[k], a);
+    sdx[i] = a;
+  }
+  __syncthreads();
+}
+}  // namespace
+
+__global__ void __launch_bounds__(64) wbc_qp_kernel(const WbcParams P, int nprob, const double *__restrict__ Hg,
+                                                    const double *__restrict__ gg, const double *__restrict__ Ag,
+                                                    const double *__restrict__ log, const double *__restrict__ hig,
+                                                    double *__restrict__ xout, b200qp_solver_info *__restrict__ info,
+                                                    int *next) {
+  extern __shared__ __align__(16) double sm[];
+  const int nq = P.nq, me = P.neq, mi = P.nin, nc = me + mi;
+  double *sH = sm;                  // [nq*nq] row-major (symmetric)
+  double *sAe = sH + nq * nq;       // [me*nq] row-major
+  double *sAi = sAe + me * nq;      // [mi*nq]
+  double *sPhi = sAi + mi * nq;     // [nq*nq] Phi -> L
+  double *sLi = sPhi + nq * nq;     // [nq*nq] L^-1
+  double *sY = sLi + nq * nq;       // [nq*me]  Y = L^-1 Aeq'
+  double *sS = sY + nq * me;        // [me*me]  S -> Ls
+  double *sSi = sS + me * me;       // [me*me]  Ls^-1
+  double *sx = sSi + me * me;       // [nq]
+  double *sg = sx + nq;             // [nq]
+  double *snu = sg + nq;            // [me]
+  double *sbe = snu + me;           // [me]
+  double *srd = sbe + me;           // [nq]
+  double *sre = srd + nq;           // [me]
+  double *srt = sre + me;           // [nq]  r~
+  double *su1 = srt + nq;           // [nq]
+  double *sv = su1 + nq;            // [max(nq,me)] scratch
+  double *sdx = sv + (nq > me ? nq : me);  // [nq]
+  double *sdnu = sdx + nq;          // [me]
+  double *sw = sdnu + me;           // [mi] row weights / row scalars
+  double *sd0 = sw + mi;            // [nq] diag scratch
+  double *sbx = sd0 + nq;           // [nq] best iterate
+  double *sdx2 = sbx + nq;          // [nq] refinement step
+  double *sdnu2 = sdx2 + nq;        // [me]
+  double *sre2 = sdnu2 + me;        // [me]
+  double *red = sre2 + me;          // [8]
+  __shared__ int sSlot;
+  const int tid = threadIdx.x, BS = blockDim.x;
+
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) sSlot = atomicAdd(next, 1);
+    __syncthreads();
+    const int prob = sSlot;
+    if (prob >= nprob) break;
+    const double *Hp = Hg + (size_t)prob * nq * nq, *Ap = Ag + (size_t)prob * nc * nq;
+    // H column-major == row-major for the symmetric Hessian; A column-major nc x nq -> rows
+    for (int e = tid; e < nq * nq; e += BS) sH[e] = Hp[e];
+    for (int e = tid; e < nc * nq; e += BS) {
+      const int col = e / nc, r = e - col * nc;
+      const double v = Ap[e];
+      if (r < me) sAe[r * nq + col] = v;
+      else sAi[(r - me) * nq + col] = v;
+    }
+    for (int e = tid; e < nq; e += BS) {
+      sg[e] = gg[(size_t)prob * nq + e];
+      sx[e] = 0.0;
+    }
+    for (int e = tid; e < me; e += BS) {
+      sbe[e] = log[(size_t)prob * nc + e];
+      snu[e] = 0.0;
+    }
+    // inequality row of this thread
+    const bool row = tid < mi;
+    double lo = -WBIG, hi = WBIG;
+    if (row) {
+      lo = log[(size_t)prob * nc + me + tid];
+      hi = hig[(size_t)prob * nc + me + tid];
+    }
+    const bool hasl = row && lo > -WINF, hasu = row && hi < WINF;
+    double sl = hasl ? fmax(-lo, 1.0) : 1.0, su = hasu ? fmax(hi, 1.0) : 1.0;  // x = 0 start: slack = max(bound distance, 1)
+    double zl = hasl ? 1.0 : 0.0, zu = hasu ? 1.0 : 0.0;
+    const double mtot = fmax(wblock_reduce((hasl ? 1.0 : 0.0) + (hasu ? 1.0 : 0.0), red, WSum()), 1.0);
+    __syncthreads();
+    // augmented-Lagrangian form of the same QP: H += rho Aeq'Aeq, g -= rho Aeq'beq keeps the minimiser and makes Phi
+    // positive definite along directions that only the equalities determine (stance-leg joint accelerations)
+    {
+      const double rho_eq = 10.0;
+      for (int e = tid; e < nq * nq; e += BS) {
+        const int i = e / nq, j = e - i * nq;
+        double a = 0.0;
+        for (int r = 0; r < me; ++r) a = fma(sAe[r * nq + i], sAe[r * nq + j], a);
+        sH[e] += rho_eq * a;
+      }
+      for (int i = tid; i < nq; i += BS) {
+        double a = 0.0;
+        for (int r = 0; r < me; ++r) a = fma(sAe[r * nq + i], sbe[r], a);
+        sg[i] -= rho_eq * a;
+      }
+    }
+    __syncthreads();
+
+    int status = B200QP_ACADOS_MAXITER, iter = 0;
+    double k_stat = 0.0, k_eq = 0.0, k_ineq = 0.0, k_comp = 0.0, bk[4] = {0.0, 0.0, 0.0, 0.0};
+    const double target = 1e-4 * P.kkt_tol;
+    double best = WBIG;
+    int stall = 0;
+    double rpl = 0.0, rpu = 0.0, mu_c = 1.0;
+    for (iter = 0; iter <= P.max_iter + 1; ++iter) {
+      const bool init = (iter == 0);  // iteration 0 computes the starting point (least-squares point + shifts)
+      if (!init) {
+      // residuals ---------------------------------------------------------------------------------------------------
+      double y = 0.0;
+      if (row)
+        for (int j = 0; j < nq; ++j) y = fma(sAi[tid * nq + j], sx[j], y);
+      rpl = hasl ? (-y + sl + lo) : 0.0;
+      rpu = hasu ? (y + su - hi) : 0.0;
+      if (row) sw[tid] = zu - zl;
+      for (int e = tid; e < me; e += BS) {
+        double a = -sbe[e];
+        for (int j = 0; j < nq; ++j) a = fma(sAe[e * nq + j], sx[j], a);
+        sre[e] = a;
+      }
+      __syncthreads();
+      double lm = 0.0;
+      for (int i = tid; i < nq; i += BS) {
+        double a = sg[i];
+        for (int j = 0; j < nq; ++j) a = fma(sH[i * nq + j], sx[j], a);
+        for (int r = 0; r < me; ++r) a = fma(sAe[r * nq + i], snu[r], a);
+        for (int r = 0; r < mi; ++r) a = fma(sAi[r * nq + i], sw[r], a);
+        srd[i] = a;
+        lm = fmax(lm, fabs(a));
+      }
+      double le = 0.0;
+      for (int e = tid; e < me; e += BS) le = fmax(le, fabs(sre[e]));
+      const bool bad = !(lm < WBIG) || !(fabs(y) < WBIG);
+      const int anybad = __syncthreads_or(bad ? 1 : 0);
+      k_stat = wblock_reduce(lm, red, WMax());
+      k_eq = wblock_reduce(le, red, WMax());
+      const double rpm = wblock_reduce(fmax(fabs(rpl), fabs(rpu)), red, WMax());
+      k_comp = wblock_reduce(fmax(hasl ? sl * zl : 0.0, hasu ? su * zu : 0.0), red, WMax());
+      k_ineq = wblock_reduce(fmax(hasl ? lo - y : 0.0, hasu ? y - hi : 0.0), red, WMax());
+      k_ineq = fmax(k_ineq, 0.0);
+      const double gap = wblock_reduce((hasl ? sl * zl : 0.0) + (hasu ? su * zu : 0.0), red, WSum());
+      const double rmax = anybad ? WBIG : fmax(fmax(k_stat, k_eq), fmax(rpm, k_comp));
+      if (rmax <= target) {
+        status = B200QP_ACADOS_SUCCESS;
+        for (int i = tid; i < nq; i += BS) sbx[i] = sx[i];
+        break;
+      }
+      if (rmax < 0.9 * best) {  // remember the best iterate: the endgame hits the round-off floor of large-scale data
+        best = rmax;
+        stall = 0;
+        bk[0] = k_stat; bk[1] = k_eq; bk[2] = k_ineq; bk[3] = k_comp;
+        for (int i = tid; i < nq; i += BS) sbx[i] = sx[i];
+      } else {
+        ++stall;
+      }
+      if (anybad || iter > P.max_iter || (stall >= 2 && best <= P.kkt_tol)) {
+        if (best <= P.kkt_tol) status = B200QP_ACADOS_SUCCESS;
+        else status = anybad ? B200QP_ACADOS_NAN_DETECTED : B200QP_ACADOS_MAXITER;
+        k_stat = bk[0]; k_eq = bk[1]; k_ineq = bk[2]; k_comp = bk[3];
+        break;
+      }
+      mu_c = gap / mtot;
+      }  // !init
+
+      // Phi = H + Ain' W Ain ------------------------------------------------------------------------------------------
+      if (row) sw[tid] = init ? ((hasl ? 1.0 : 0.0) + (hasu ? 1.0 : 0.0)) : ((hasl ? zl / sl : 0.0) + (hasu ? zu / su : 0.0));
+      __syncthreads();
+      for (int e = tid; e < nq * nq; e += BS) {
+        const int i = e / nq, j = e - i * nq;
+        if (j > i) continue;
+        double a = sH[e];
+        for (int r = 0; r < mi; ++r) a = fma(sAi[r * nq + i] * sw[r], sAi[r * nq + j], a);
+        sPhi[e] = a;
+      }
+      __syncthreads();
+      chol_and_inverse(sPhi, sLi, nq, sd0);
+      for (int e = tid; e < nq * me; e += BS) {  // Y[i][r] = sum_{k<=i} Li[i][k] Aeq[r][k]
+        const int i = e / me, r = e - i * me;
+        double a = 0.0;
+        for (int k = 0; k <= i; ++k) a = fma(sLi[i * nq + k], sAe[r * nq + k], a);
+        sY[e] = a;
+      }
+      __syncthreads();
+      for (int e = tid; e < me * me; e += BS) {  // S = Y'Y
+        const int r = e / me, c = e - r * me;
+        if (c > r) continue;
+        double a = 0.0;
+        for (int i = 0; i < nq; ++i) a = fma(sY[i * me + r], sY[i * me + c], a);
+        sS[e] = a;
+      }
+      __syncthreads();
+      chol_and_inverse(sS, sSi, me, sd0);
+
+      if (init) {  // starting point as in CVXOPT's coneqp: solve with W = I, then shift s and z into the interior
+        if (row) sw[tid] = (hasu ? hi : 0.0) - (hasl ? lo : 0.0);
+        for (int e = tid; e < me; e += BS) sre[e] = -sbe[e];
+        __syncthreads();
+        for (int i = tid; i < nq; i += BS) {
+          double a = sg[i];
+          for (int r = 0; r < mi; ++r) a = fma(-sAi[r * nq + i], sw[r], a);
+          srt[i] = a;
+        }
+        __syncthreads();
+        kkt_solve(nq, me, sLi, sY, sSi, srt, sre, su1, sv, sdx, sdnu);
+        for (int i = tid; i < nq; i += BS) sx[i] = sdx[i];
+        for (int r = tid; r < me; r += BS) snu[r] = sdnu[r];
+        __syncthreads();
+        double y0 = 0.0;
+        if (row)
+          for (int j = 0; j < nq; ++j) y0 = fma(sAi[tid * nq + j], sx[j], y0);
+        const double zu0 = y0 - hi, zl0 = -y0 + lo;  // z = G x - h, s = -z
+        const double smin = wblock_reduce(fmin(hasu ? -zu0 : WBIG, hasl ? -zl0 : WBIG), red, WMin());
+        const double zmin = wblock_reduce(fmin(hasu ? zu0 : WBIG, hasl ? zl0 : WBIG), red, WMin());
+        const double sh = smin > 0.0 ? 0.0 : 1.0 - smin, zh = zmin > 0.0 ? 0.0 : 1.0 - zmin;
+        su = hasu ? -zu0 + sh : 1.0;
+        sl = hasl ? -zl0 + sh : 1.0;
+        zu = hasu ? zu0 + zh : 0.0;
+        zl = hasl ? zl0 + zh : 0.0;
+        __syncthreads();
+        continue;
+      }
+      // predictor / corrector ---------------------------------------------------------------------------------------------
+      double dsl = 0.0, dsu = 0.0, dzl = 0.0, dzu = 0.0, sigma_mu = 0.0;
+      for (int pass = 0; pass < 2; ++pass) {
+        const double rcl = (pass == 0) ? sl * zl : (sl * zl + dsl * dzl - sigma_mu);
+        const double rcu = (pass == 0) ? su * zu : (su * zu + dsu * dzu - sigma_mu);
+        if (row) sw[tid] = (hasu ? (zu * rpu - rcu) / su : 0.0) - (hasl ? (zl * rpl - rcl) / sl : 0.0);
+        __syncthreads();
+        for (int i = tid; i < nq; i += BS) {  // r~ = rd + Ain' t
+          double a = srd[i];
+          for (int r = 0; r < mi; ++r) a = fma(sAi[r * nq + i], sw[r], a);
+          srt[i] = a;
+        }
+        __syncthreads();
+        kkt_solve(nq, me, sLi, sY, sSi, srt, sre, su1, sv, sdx, sdnu);
+        if (pass == 1 && mu_c < 1e-3) {
+          // one step of iterative refinement on the Newton system (Phi dx + Aeq'dnu = -r~, Aeq dx = -re): with W up to
+          // 1e12 the factored solve alone stalls the stationarity residual at the 1e-6 level on large-scale data
+          double q = 0.0;
+          if (row) {
+            for (int j = 0; j < nq; ++j) q = fma(sAi[tid * nq + j], sdx[j], q);
+            sw[tid] = q * ((hasl ? zl / sl : 0.0) + (hasu ? zu / su : 0.0));
+          }
+          __syncthreads();
+          for (int i = tid; i < nq; i += BS) {
+            double a = srt[i];
+            for (int j = 0; j < nq; ++j) a = fma(sH[i * nq + j], sdx[j], a);
+            for (int r = 0; r < mi; ++r) a = fma(sAi[r * nq + i], sw[r], a);
+            for (int r = 0; r < me; ++r) a = fma(sAe[r * nq + i], sdnu[r], a);
+            sd0[i] = a;  // = -(residual of the first block row)
+          }
+          for (int e = tid; e < me; e += BS) {
+            double a = sre[e];
+            for (int j = 0; j < nq; ++j) a = fma(sAe[e * nq + j], sdx[j], a);
+            sre2[e] = a;
+          }
+          __syncthreads();
+          kkt_solve(nq, me, sLi, sY, sSi, sd0, sre2, su1, sv, sdx2, sdnu2);
+          for (int i = tid; i < nq; i += BS) sdx[i] += sdx2[i];
+          for (int e = tid; e < me; e += BS) sdnu[e] += sdnu2[e];
+          __syncthreads();
+        }
+        double dy = 0.0;
+        if (row)
+          for (int j = 0; j < nq; ++j) dy = fma(sAi[tid * nq + j], sdx[j], dy);
+        const double nsl = hasl ? (-rpl + dy) : 0.0, nsu = hasu ? (-rpu - dy) : 0.0;
+        const double nzl = hasl ? (-rcl - zl * nsl) / sl : 0.0, nzu = hasu ? (-rcu - zu * nsu) / su : 0.0;
+        double st = 1.0;
+        if (hasl) {
+          if (nsl < 0.0) st = fmin(st, -sl / nsl);
+          if (nzl < 0.0) st = fmin(st, -zl / nzl);
+        }
+        if (hasu) {
+          if (nsu < 0.0) st = fmin(st, -su / nsu);
+          if (nzu < 0.0) st = fmin(st, -zu / nzu);
+        }
+        st = wblock_reduce(st, red, WMin());
+        if (pass == 0) {
+          const double g2 = wblock_reduce((hasl ? (sl + st * nsl) * (zl + st * nzl) : 0.0) + (hasu ? (su + st * nsu) * (zu + st * nzu) : 0.0), red, WSum());
+          const double ratio = (g2 / mtot) / fmax(mu_c, 1e-300);
+          sigma_mu = ratio * ratio * ratio * mu_c;
+          dsl = nsl; dsu = nsu; dzl = nzl; dzu = nzu;
+        } else {
+          const double a = fmin(1.0, 0.995 * st);
+          sl += a * nsl; su += a * nsu; zl += a * nzl; zu += a * nzu;
+          for (int i = tid; i < nq; i += BS) sx[i] += a * sdx[i];
+          for (int r = tid; r < me; r += BS) snu[r] += a * sdnu[r];
+        }
+        __syncthreads();
+      }
+    }
+    __syncthreads();
+    if (status == B200QP_ACADOS_SUCCESS)
+      for (int i = tid; i < nq; i += BS) xout[(size_t)prob * nq + i] = sbx[i];
+    if (tid == 0) {
+      b200qp_solver_info inf;
+      inf.status = status;
+      inf.iterations = iter > 0 ? iter - 1 : 0;
+      inf.polish_rounds = 0;
+      inf.n_free = nq;
+      inf.kkt[0] = k_stat;
+      inf.kkt[1] = k_eq;
+      inf.kkt[2] = k_ineq;
+      inf.kkt[3] = k_comp;
+      info[prob] = inf;
+    }
+  }
+}
+
+size_t wbc_smem_bytes(const WbcParams &P) {
+  const size_t nq = P.nq, me = P.neq, mi = P.nin;
+  const size_t d = nq * nq * 3 + me * nq + mi * nq + nq * me + 2 * me * me + 10 * nq + 7 * me + (nq > me ? nq : me) + mi + 8;
+  return d * sizeof(double) + 64;
+}
+
+int wbc_grid(const WbcParams &P, int num_sms) {
+  const size_t smb = wbc_smem_bytes(P);
+  int occ = 0;
+  if (cudaFuncSetAttribute(wbc_qp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smb) != cudaSuccess ||
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, wbc_qp_kernel, 64, smb) != cudaSuccess) {
+    cudaGetLastError();
+    return -1;
+  }
+  return num_sms * (occ < 1 ? 1 : occ);
+}
+
+cudaError_t launch_wbc_qp(const WbcParams &P, int n, const double *H, const double *g, const double *A, const double *lo,
+                          const double *hi, double *x, b200qp_solver_info *info, int *next, int grid, cudaStream_t st) {
+  if (grid > n) grid = n;
+  wbc_qp_kernel<<<grid, 64, wbc_smem_bytes(P), st>>>(P, n, H, g, A, lo, hi, x, info, next);
+  return cudaGetLastError();
+}
+
+}  // namespace b200qp

@@ -155,6 +155,35 @@ int32_t b200qp_gait_schedule_device(int32_t n, int32_t steps, double dt, const d
                                     double fmin, double fmax, uint8_t *d_contact, double *d_swing_time, double *d_lbu,
                                     double *d_ubu, void *stream);
 
+/* ---- whole-body-control task-space QP (kernel K3) ------------------------------------------------------------------
+ * Replaces the `wbc::QPSolver` plugin that ARC-OPT's scene calls in `wbc_scene_->solve(qp)`
+ * (ws/src/controllers/src/mit_controller/wbc_arc_opt.cpp:51-74,297) for n QPs at once:
+ *     min 1/2 x'Hx + g'x   s.t.   A[0:neq] x = lower_y[0:neq],   lower_y[neq:] <= A[neq:] x <= upper_y[neq:]
+ * Layouts follow ARC-OPT's wbc::QuadraticProgram (Eigen, column-major): per problem H [nq x nq], g [nq],
+ * A [(neq+nin) x nq] column-major, lower_y / upper_y [neq+nin]; |bound| >= 1e19 means "no bound". */
+typedef struct b200qp_wbc_config {
+  int32_t nq;         /* decision variables (reduced TSID on Go2: 18 accelerations + 12 contact forces = 30), <= 48 */
+  int32_t neq;        /* equality rows (6 floating-base dynamics + 3 per foot = 18), <= 32                          */
+  int32_t nin;        /* two-sided inequality rows (12 torque limits + 16 friction pyramid = 28), <= 64             */
+  int32_t max_batch;
+  int32_t device;
+  int32_t max_iter;   /* IPM iteration cap, 0 => 40                                                                */
+  double kkt_tol;     /* acceptance tolerance on the KKT inf-norms, 0 => 1e-6 (internal target 1e-4 of it)          */
+} b200qp_wbc_config;
+typedef struct b200qp_wbc b200qp_wbc;
+int32_t b200qp_wbc_create(const b200qp_wbc_config *cfg, b200qp_wbc **out);
+void b200qp_wbc_destroy(b200qp_wbc *h);
+/* HOST buffers; x [n][nq] is written only for problems with info.status == 0 (on a solver failure the reference
+ * falls back to zero torque, wbc_arc_opt.cpp:298-309 - the caller's job).  info.kkt = stationarity, equality,
+ * inequality, complementarity inf-norms. */
+int32_t b200qp_wbc_solve_batch(b200qp_wbc *h, int32_t n, const double *H, const double *g, const double *A,
+                               const double *lower_y, const double *upper_y, double *x, b200qp_solver_info *info);
+/* DEVICE pointers, asynchronous on the handle's stream unless sync != 0 */
+int32_t b200qp_wbc_solve_batch_device(b200qp_wbc *h, int32_t n, const double *d_H, const double *d_g, const double *d_A,
+                                      const double *d_lower_y, const double *d_upper_y, double *d_x,
+                                      b200qp_solver_info *d_info, int32_t sync);
+void *b200qp_wbc_stream(b200qp_wbc *h);
+
 /* library / device info */
 const char *b200qp_version(void);
 int32_t b200qp_device_count(void);

@@ -13,7 +13,7 @@ import numpy as np
 from . import mpc_oracle as mo
 
 
-def make_batch_cpu(n, N, seed):
+def make_batch_cpu(n, N, seed, gaits=("TROT",)):
     """Same synthetic distribution as dfki_quad_b200.sequencer.random_batch, with the gait schedule from the oracle's
     own restatement (no GPU involved)."""
     from dfki_quad_b200 import sequencer
@@ -25,7 +25,7 @@ def make_batch_cpu(n, N, seed):
             c[p], s[p] = mo.gait_update_sequence(period[p], duty[p], offset[p], dt, float(phase[p]), steps, None)
         return c, s
 
-    return sequencer.random_batch(n, N, seed, gaits=("TROT",), schedule_fn=sched)
+    return sequencer.random_batch(n, N, seed, gaits=gaits, schedule_fn=sched)
 
 
 def _params():

@@ -1,0 +1,80 @@
+"""GPU parity tests of the WBC task-space QP kernel (K3) against the numpy QP oracle, through the C ABI."""
+import numpy as np
+import pytest
+
+from oracle import qp_oracle as qo
+
+pytestmark = pytest.mark.gpu
+
+
+def _split(qp, p):
+    me = qp.neq
+    return qp.H[p], qp.g[p], qp.A[p, :me], qp.lower_y[p, :me], qp.A[p, me:], qp.lower_y[p, me:], qp.upper_y[p, me:]
+
+
+def test_wbc_parity_small():
+    from dfki_quad_b200 import wbc
+
+    n = 48
+    b = wbc.random_wbc_batch(n, seed=20261019 + 4)
+    solver = wbc.BatchedWBCSolver(max_batch=n)
+    x, info = solver.solve(b["qp"])
+    assert (info["status"] == 0).all(), info["status"]
+    assert info["kkt"].max() <= 1e-6
+    for p in range(n):
+        args = _split(b["qp"], p)
+        xr = qo.solve(*args)
+        scale = max(1.0, np.abs(xr).max())
+        assert np.abs(x[p] - xr).max() <= 1e-5 * scale, (p, np.abs(x[p] - xr).max() / scale)
+        stat, eq, ineq = qo.kkt_residuals(*args, x[p])
+        assert eq <= 1e-6 and ineq <= 1e-6, (p, eq, ineq)
+    # swing feet carry no contact force; stance forces respect the friction pyramid (mu = 0.45)
+    f = x[:, 18:].reshape(n, 4, 3)
+    assert np.abs(f[~b["contacts"]]).max() <= 1e-9
+    fs = f[b["contacts"]]
+    assert np.all(np.abs(fs[:, 0]) <= 0.45 * fs[:, 2] + 1e-6) and np.all(np.abs(fs[:, 1]) <= 0.45 * fs[:, 2] + 1e-6)
+    tau = wbc.joint_torques(b["dyn"], x)
+    from dfki_quad_b200 import go2_model as gm
+
+    assert np.all(np.abs(tau) <= gm.TAU_MAX + 1e-6)
+
+
+def test_wbc_tracks_mpc_forces_when_unconstrained():
+    """All four feet in stance, zero velocities, body reference = gravity compensation: forces follow the references."""
+    from dfki_quad_b200 import go2_model as gm
+    from dfki_quad_b200 import wbc
+
+    n = 4
+    pos = np.tile([0.0, 0.0, 0.3], (n, 1))
+    quat = np.tile([0.0, 0.0, 0.0, 1.0], (n, 1))
+    q = np.tile(gm.nominal_joint_angles(), (n, 1))
+    z = np.zeros((n, 3))
+    dyn = gm.dynamics(pos, quat, q, z, z, np.zeros((n, 12)))
+    contacts = np.ones((n, 4), bool)
+    f_ref = np.zeros((n, 4, 3))
+    f_ref[:, :, 2] = 15.019 * gm.GRAVITY / 4
+    qp = wbc.reduced_tsid_qp(dyn, contacts, np.zeros((n, 6)), np.zeros((n, 4, 3)), f_ref, gm.TAU_MAX)
+    x, info = wbc.BatchedWBCSolver(max_batch=n).solve(qp)
+    assert (info["status"] == 0).all()
+    f = x[:, 18:].reshape(n, 4, 3)
+    assert np.abs(f[:, :, 2].sum(axis=1) - 15.019 * gm.GRAVITY).max() < 0.1    # weight is carried (body task trades a little)
+    assert np.abs(x[:, :6]).max() < 0.5                                          # body stays (almost) at rest
+    assert np.abs(x[:, 6:18]).max() < 5.0
+
+
+def test_config4_full_batch():
+    """BASELINE.json configs[3]: 16384 WBC QPs fed by the MPC GRFs."""
+    from dfki_quad_b200 import wbc
+
+    n = 16384
+    b = wbc.random_wbc_batch(n, seed=20261019 + 4)
+    x, info = wbc.BatchedWBCSolver(max_batch=n).solve(b["qp"])
+    ok = info["status"] == 0
+    assert ok.mean() >= 0.999, (ok.mean(), np.unique(info["status"], return_counts=True))
+    assert info["kkt"][ok].max() <= 1e-6
+    rng = np.random.default_rng(0)
+    for p in rng.choice(np.nonzero(ok)[0], 16, replace=False):
+        xr = qo.solve(*_split(b["qp"], p))
+        assert np.abs(x[p] - xr).max() <= 1e-5 * max(1.0, np.abs(xr).max())
+    f = x[ok, 18:].reshape(-1, 4, 3)
+    assert np.abs(f[~b["contacts"][ok]]).max() <= 1e-9

@@ -151,3 +151,55 @@ def test_sharding_two_ranks_gloo(tmp_path):
                           "--master-addr", "127.0.0.1", "--master-port", "29611", str(script)], env=env,
                          capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stderr[-2000:]
+
+
+def test_go2_dynamics_consistency():
+    """Host-side rigid-body terms: total mass (= the MPC's 15.019 kg), symmetric positive definite M, foot Jacobians
+    against finite differences of the forward kinematics."""
+    from dfki_quad_b200 import go2_model as gm
+
+    rng = np.random.default_rng(0)
+    n = 2
+    quat = rng.normal(size=(n, 4))
+    quat /= np.linalg.norm(quat, axis=1, keepdims=True)
+    pos, q = rng.normal(size=(n, 3)), gm.nominal_joint_angles() + rng.uniform(-0.3, 0.3, (n, 12))
+    v, w, qd = rng.normal(size=(n, 3)), rng.normal(size=(n, 3)), rng.normal(size=(n, 12))
+    D = gm.dynamics(pos, quat, q, v, w, qd)
+    assert np.allclose(D["M"][:, 0, 0], 15.019, atol=1e-9) and np.linalg.eigvalsh(D["M"]).min() > 1e-4
+    eps = 1e-6
+    for k in list(range(3)) + list(range(6, 18)):  # translations and joints (rotations need the quaternion exponential)
+        dp, dq = np.zeros((n, 3)), np.zeros((n, 12))
+        if k < 3:
+            dp[:, k] = eps
+        else:
+            dq[:, k - 6] = eps
+        fp = gm.dynamics(pos + dp, quat, q + dq, v, w, qd)["foot_pos"]
+        fm = gm.dynamics(pos - dp, quat, q - dq, v, w, qd)["foot_pos"]
+        assert np.abs((fp - fm) / (2 * eps) - D["foot_J"][:, :, :, k]).max() < 1e-7
+    assert np.allclose(D["foot_vel"], np.einsum("nfij,nj->nfi", D["foot_J"], np.concatenate([v, w, qd], axis=1)))
+
+
+def test_tsid_scene_against_oracle():
+    """Reduced-TSID assembly is a well-posed strictly convex QP; the two oracle solvers agree on it."""
+    from dfki_quad_b200 import go2_model as gm
+    from dfki_quad_b200 import wbc
+    from oracle import qp_oracle as qo
+
+    N, n = 10, 4
+    zf = np.zeros((n, N, 12))
+    zf[:, :, 2::3] = 40.0
+    xp = np.zeros((n, N + 1, 13))
+    xp[:, :, 5] = 0.3
+    b = wbc.random_wbc_batch(n, seed=5, schedule_fn=_oracle_schedule, mpc_solution=(zf, xp))
+    qp = b["qp"]
+    assert qp.A.shape == (n, 46, 30) and qp.neq == 18
+    for p in range(n):
+        args = (qp.H[p], qp.g[p], qp.A[p, :18], qp.lower_y[p, :18], qp.A[p, 18:], qp.lower_y[p, 18:], qp.upper_y[p, 18:])
+        x, it = qo.solve_ipm(*args)
+        x2, ok = qo.solve_active_set(*args, x)
+        assert ok and np.abs(x - x2).max() <= 1e-5 * max(1.0, np.abs(x2).max())
+        stat, eq, ineq = qo.kkt_residuals(*args, x2)
+        assert max(stat, eq, ineq) <= 1e-7
+        f = x2[18:].reshape(4, 3)
+        assert np.abs(f[~b["contacts"][p]]).max() <= 1e-9
+        assert np.abs(wbc.joint_torques({k: v[p:p + 1] for k, v in b["dyn"].items()}, x2[None])).max() <= gm.TAU_MAX.max() + 1e-6
