@@ -29,6 +29,8 @@ WORKLOADS = {
                     seed=20261019 + 2, kernel="mpc_admm_kernel<64,64>"),
     "config3": dict(name="go2_mixed_sparse_mpc_h16_riccati", horizon=16, batch=16384, gaits=("TROT", "PACE", "BOUND"),
                     solver="SPARSE_RICCATI", seed=20261019 + 3, kernel="mpc_riccati_kernel<64>"),
+    "config4": dict(name="go2_wbc_reduced_tsid_qp", horizon=10, batch=16384, gaits=("TROT",), solver="WBC_DENSE_IPM",
+                    seed=20261019 + 4, kernel="wbc_qp_kernel"),
 }
 
 
@@ -286,6 +288,109 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
+def run_b200_wbc(args):
+    """BASELINE.json configs[3]: batched WBC task-space QP (reported beside the headline metric, not instead of it)."""
+    import torch
+
+    from dfki_quad_b200 import wbc
+
+    rank, local, world = dist_env()
+    if world > 1:
+        import torch.distributed as dist
+
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = local
+    torch.cuda.set_device(dev)
+    wl = WORKLOADS["config4"]
+    B = args.batch or wl["batch"]
+    b = wbc.random_wbc_batch(B, seed=wl["seed"] + 1000 * rank, device=dev)
+    solver = wbc.BatchedWBCSolver(max_batch=B, device=dev)
+    H, g, A, lo, hi = solver.abi_arrays(b["qp"])
+    ext = torch.cuda.ExternalStream(solver.stream(), device=dev)
+    with torch.cuda.stream(ext):
+        dH, dg, dA, dlo, dhi = (torch.from_numpy(a).to(dev) for a in (H, g, A, lo, hi))
+        dx = torch.zeros((B, 30), dtype=torch.float64, device=dev)
+        dinfo = torch.zeros((B, 48), dtype=torch.uint8, device=dev)
+        flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    ext.synchronize()
+
+    def step():
+        solver.solve_device(B, dH.data_ptr(), dg.data_ptr(), dA.data_ptr(), dlo.data_ptr(), dhi.data_ptr(), dx.data_ptr(),
+                            dinfo.data_ptr(), sync=False)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    evs = []
+    with ClockSampler(dev) as clocks:
+        barrier()
+        for _ in range(args.steps):
+            with torch.cuda.stream(ext):
+                flush.zero_()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(ext)
+                step()
+                e1.record(ext)
+            evs.append((e0, e1))
+        barrier()
+    total_ms = float(sum(a.elapsed_time(c) for a, c in evs))
+    info = np.frombuffer(dinfo.cpu().numpy().tobytes(), dtype=np.dtype(
+        [("status", "i4"), ("iterations", "i4"), ("polish_rounds", "i4"), ("n_free", "i4"), ("kkt", "f8", (4,))]))
+    conv = (info["status"] == 0) & (info["kkt"].max(axis=1) <= KKT_TOL)
+    xh = np.zeros((B, 30))
+    solver.solve_abi(H, g, A, lo, hi, xh)
+    barrier()
+    t0 = time.perf_counter()
+    conv_e2e = 0
+    for _ in range(args.steps):
+        _, inf = solver.solve_abi(H, g, A, lo, hi, xh)
+        conv_e2e += int(((inf["status"] == 0) & (inf["kkt"].max(axis=1) <= KKT_TOL)).sum())
+    e2e_s = time.perf_counter() - t0
+    stats = torch.tensor([total_ms, e2e_s], dtype=torch.float64, device=dev)
+    counts = torch.tensor([float(conv.sum()) * args.steps, conv_e2e, B * args.steps], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(stats, op=dist.ReduceOp.MAX)
+        dist.all_reduce(counts, op=dist.ReduceOp.SUM)
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        ab = 8 * (900 + 30 + 46 * 30 + 2 * 46 + 30) + 48
+        kern_s = total_ms / args.steps * 1e-3
+        line = {
+            "metric": "WBC task-space QP solves/sec (Go2 reduced TSID, 30 vars, 18 eq, 28 ineq)", "value": counts[0].item() / (stats[0].item() * 1e-3),
+            "unit": "solves/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": stats[0].item() / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": wl["name"], "batch_per_gpu": B, "solver": wl["solver"], "l2": "256 MiB flush between timed iterations",
+                       "converged_fraction": counts[0].item() / counts[2].item(), "mean_iterations": float(info["iterations"].mean()),
+                       "kkt_max": float(info["kkt"][conv].max()), "parallelism": f"shard{world}"},
+            "e2e": {"value": counts[1].item() / stats[1].item(), "unit": "solves/s", "h2d_bytes_per_step": int(B * (ab - 48 - 240) + B * 240),
+                    "d2h_bytes_per_step": int(B * (240 + 48))},
+            "gpu_launches": args.steps, "clocks": clocks.summary(),
+            "roofline": {"bound": "hbm", "achieved": ab * B / kern_s / 1e9, "peak": peak, "unit": "GB/s", "frac": ab * B / kern_s / 1e9 / peak,
+                         "traffic": None, "peak_source": peak_src, "kernel": wl["kernel"], "algorithmic_bytes_per_solve": ab},
+        }
+        if not args.no_cpu_baseline:
+            from oracle import qp_oracle as qo
+
+            t0 = time.perf_counter()
+            k = 0
+            qp = b["qp"]
+            while time.perf_counter() - t0 < args.cpu_budget and k < B:
+                qo.solve(qp.H[k], qp.g[k], qp.A[k, :18], qp.lower_y[k, :18], qp.A[k, 18:], qp.lower_y[k, 18:], qp.upper_y[k, 18:])
+                k += 1
+            line["cpu_baseline"] = {"value": k / (time.perf_counter() - t0), "unit": "solves/s", "cores": 1, "kind": "port",
+                                    "sample": f"first {k} problems, numpy IPM + active-set oracle, 1 thread"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -302,6 +407,8 @@ def main():
         args.warmup = 3
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "config4":
+        run_b200_wbc(args)
     else:
         run_b200(args)
 

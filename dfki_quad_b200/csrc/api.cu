@@ -19,7 +19,7 @@ int admm_occupancy(int bin);
 cudaError_t launch_mpc_riccati(const MpcParams &P, int n, const double *in, const uint8_t *contact, double *forces,
                                double *xpred, b200qp_solver_info *info, double *lam_box, double *lam_g, double *scratch,
                                int *next, int grid, cudaStream_t st);
-int riccati_grid(int num_sms);
+int riccati_grid(int num_sms, int horizon);
 struct WbcParams {
   int nq, neq, nin;
   double kkt_tol;
@@ -159,7 +159,7 @@ int32_t b200qp_mpc_create(const b200qp_mpc_config *cfg, b200qp_mpc **out) {
     }
   }
   if (cfg->solver == B200QP_SOLVER_SPARSE_RICCATI) {
-    int g = riccati_grid(h->num_sms);
+    int g = riccati_grid(h->num_sms, cfg->horizon);
     if ((size_t)g > nb) g = (int)nb;
     h->ric_grid = g;
     CK(cudaMalloc(&h->d_ric_scratch, (size_t)g * B200QP_MAX_HORIZON * 288 * sizeof(double)));

@@ -72,7 +72,8 @@ __global__ void __launch_bounds__(BS) mpc_riccati_kernel(const MpcParams P, int 
   __shared__ double sRb[MAXH * 4 * 6];  // R~ blocks per foot: xx yy zz xz yz (xy = 0) + pad
   __shared__ double sBwsum[MAXH * 6];
   __shared__ double sYaw[MAXH + 1], sX0[13], sRot[9], sVec[64], red[4 * 8];
-  __shared__ unsigned char sOn[MAXH * 4];
+  __shared__ unsigned char sOn[MAXH * 4], sAct[MAXH * 12];
+  __shared__ int sNu[MAXH];
   __shared__ int sSlot;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -116,6 +117,12 @@ __global__ void __launch_bounds__(BS) mpc_riccati_kernel(const MpcParams P, int 
     }
     if (tid < 4 * N) sOn[tid] = ct[tid] != 0;
     __syncthreads();
+    if (tid < N) {  // compact list of the stance inputs of stage tid
+      int m = 0;
+      for (int j = 0; j < 12; ++j)
+        if (sOn[tid * 4 + j / 3]) sAct[12 * tid + m++] = (unsigned char)j;
+      sNu[tid] = m;
+    }
     if (tid == 0) {  // yaw unwrap, mpc.cpp:334-344
       double before = sVec[63];
       for (int k = 0; k <= N; ++k) {
@@ -354,66 +361,73 @@ __global__ void __launch_bounds__(BS) mpc_riccati_kernel(const MpcParams P, int 
       for (int e = tid; e < 144; e += BS) sP[e] = ((e / 12) == (e % 12)) ? P.w[e / 12] : 0.0;
       __syncthreads();
 
-      // (D) Riccati backward sweep (matrices) ------------------------------------------------------------------------------
+      // (D) Riccati backward sweep (matrices), compacted to the nu_k stance inputs of every stage ---------------------------
       double *Pc = sP, *Pnx = sPn;
       for (int k = N - 1; k >= 0; --k) {
         const double *Bwk = sBw + k * 36;
+        const int nu = sNu[k];
+        const unsigned char *act = sAct + 12 * k;
         for (int e = tid; e < 144; e += BS) {
-          const int i = e / 12, j = e - 12 * i, f = j / 3, c = j - 3 * f;
-          const double *Bw = Bwk + 9 * f;
-          sPB[e] = Pc[12 * i + 6] * Bw[c] + Pc[12 * i + 7] * Bw[3 + c] + Pc[12 * i + 8] * Bw[6 + c] + dm * Pc[12 * i + 9 + c];
-          // T = P A
-          double t = Pc[e];
+          const int i = e / 12, j = e - 12 * i;
+          if (j < nu) {  // PB[i][m], m = compact input index
+            const int jj = act[j], f = jj / 3, c = jj - 3 * f;
+            const double *Bw = Bwk + 9 * f;
+            sPB[e] = Pc[12 * i + 6] * Bw[c] + Pc[12 * i + 7] * Bw[3 + c] + Pc[12 * i + 8] * Bw[6 + c] + dm * Pc[12 * i + 9 + c];
+          }
+          double t = Pc[e];  // T = P A
           if (j >= 6 && j < 9) t += dt * (Pc[12 * i] * sRot[j - 6] + Pc[12 * i + 1] * sRot[3 + j - 6] + Pc[12 * i + 2] * sRot[6 + j - 6]);
           else if (j >= 9) t += dt * Pc[12 * i + j - 6];
           sT[e] = t;
         }
         __syncthreads();
         for (int e = tid; e < 144; e += BS) {
-          const int a = e / 12, j = e - 12 * a, fa = a / 3, ca = a - 3 * fa, fj = j / 3, cj = j - 3 * fj;
-          const bool ona = sOn[k * 4 + fa], onj = sOn[k * 4 + fj];
+          const int a = e / 12, j = e - 12 * a;
+          if (a >= nu) continue;
+          const int aa = act[a], fa = aa / 3, ca = aa - 3 * fa;
           const double *Bw = Bwk + 9 * fa;
-          double h = Bw[ca] * sPB[12 * 6 + j] + Bw[3 + ca] * sPB[12 * 7 + j] + Bw[6 + ca] * sPB[12 * 8 + j] + dm * sPB[12 * (9 + ca) + j];
-          if (fa == fj) {
-            const double *Rb = sRb + 6 * (k * 4 + fa);
-            if (ca == cj) h += Rb[ca];
-            else if (ca + cj == 2) h += Rb[3];       // (x,z)
-            else if (ca + cj == 3) h += Rb[4];       // (y,z)
+          if (j < nu) {  // Huu[a][j] on the compact index set
+            const int jj = act[j], fj = jj / 3, cj = jj - 3 * fj;
+            double h = Bw[ca] * sPB[12 * 6 + j] + Bw[3 + ca] * sPB[12 * 7 + j] + Bw[6 + ca] * sPB[12 * 8 + j] + dm * sPB[12 * (9 + ca) + j];
+            if (fa == fj) {
+              const double *Rb = sRb + 6 * (k * 4 + fa);
+              if (ca == cj) h += Rb[ca];
+              else if (ca + cj == 2) h += Rb[3];  // (x,z)
+              else if (ca + cj == 3) h += Rb[4];  // (y,z)
+            }
+            sHuu[e] = h;
           }
-          if (!ona || !onj) h = (a == j) ? 1.0 : 0.0;
-          sHuu[e] = h;
-          // Hux[a][col] = sum_i PB[i][a] A[i][col]
-          const int col = j;
+          const int col = j;  // Hux[a][col] = sum_i PB[i][a] A[i][col]
           double x = sPB[12 * col + a];
           if (col >= 6 && col < 9) x += dt * (sPB[a] * sRot[col - 6] + sPB[12 + a] * sRot[3 + col - 6] + sPB[24 + a] * sRot[6 + col - 6]);
           else if (col >= 9) x += dt * sPB[12 * (col - 6) + a];
-          sHux[e] = ona ? x : 0.0;
+          sHux[e] = x;
         }
         __syncthreads();
         if (warp == 0) {  // Cholesky Huu = L L' and L^-1 inside one warp (explicit Huu^-1 loses the IPM endgame accuracy)
-          const double od = (lane < 12) ? sHuu[13 * lane] : 1.0;  // original diagonal, for the round-off pivot floor
-          for (int p = 0; p < 12; ++p) {
+          const double od = (lane < nu) ? sHuu[13 * lane] : 1.0;  // original diagonal, for the round-off pivot floor
+          for (int p = 0; p < nu; ++p) {
             const double flo = 1e-13 * __shfl_sync(0xffffffffu, od, p);
             const double piv = sHuu[13 * p];
             const double d = sqrt((piv > flo) ? piv : flo);
             __syncwarp();
-            if (lane < 12) {
+            if (lane < nu) {
               if (lane == p) sHuu[13 * p] = d;
               else if (lane > p) sHuu[12 * lane + p] /= d;
             }
             __syncwarp();
-            for (int e = lane; e < 144; e += 32) {
-              const int i = e / 12, j = e - 12 * i;
-              if (j > p && j <= i) sHuu[e] -= sHuu[12 * i + p] * sHuu[12 * j + p];
+            const int rem = nu - p - 1;
+            for (int e = lane; e < rem * rem; e += 32) {
+              const int i = p + 1 + e / rem, j = p + 1 + e % rem;
+              if (j <= i) sHuu[12 * i + j] -= sHuu[12 * i + p] * sHuu[12 * j + p];
             }
             __syncwarp();
           }
-          if (lane < 12) {  // column `lane` of X = L^-1 by forward substitution
+          if (lane < nu) {  // column `lane` of X = L^-1 by forward substitution
             const int j = lane;
             for (int i = 0; i < j; ++i) sLi[12 * i + j] = 0.0;
-            for (int i = j; i < 12; ++i) {
+            for (int i = j; i < nu; ++i) {
               double acc = (i == j) ? 1.0 : 0.0;
-              for (int k = j; k < i; ++k) acc -= sHuu[12 * i + k] * sLi[12 * k + j];
+              for (int kk2 = j; kk2 < i; ++kk2) acc -= sHuu[12 * i + kk2] * sLi[12 * kk2 + j];
               sLi[12 * i + j] = acc / sHuu[13 * i];
             }
           }
@@ -428,7 +442,7 @@ __global__ void __launch_bounds__(BS) mpc_riccati_kernel(const MpcParams P, int 
           }
         }
         __syncthreads();
-        for (int e = tid; e < 144; e += BS) {  // Y = L^-1 Hux
+        for (int e = tid; e < 12 * nu; e += BS) {  // Y = L^-1 Hux   (nu x 12)
           const int j = e / 12, col = e - 12 * j;
           double acc = 0.0;
           for (int a = 0; a <= j; ++a) acc = fma(sLi[12 * j + a], sHux[12 * a + col], acc);
@@ -437,13 +451,15 @@ __global__ void __launch_bounds__(BS) mpc_riccati_kernel(const MpcParams P, int 
         __syncthreads();
         for (int e = tid; e < 144; e += BS) {  // K = -L^-T Y ;  P <- Pn - Y'Y (symmetric by construction) ; spill K, L^-1
           const int j = e / 12, col = e - 12 * j;
-          double acc = 0.0, pp = Pnx[e];
-          for (int a = j; a < 12; ++a) acc = fma(sLi[12 * a + j], sT[12 * a + col], acc);
-#pragma unroll
-          for (int a = 0; a < 12; ++a) pp = fma(-sT[12 * a + j], sT[12 * a + col], pp);
+          double pp = Pnx[e];
+          for (int a = 0; a < nu; ++a) pp = fma(-sT[12 * a + j], sT[12 * a + col], pp);
           Pnx[e] = pp;
-          Ks[(size_t)k * 288 + e] = -acc;
-          Ks[(size_t)k * 288 + 144 + e] = sLi[e];
+          if (j < nu) {
+            double acc = 0.0;
+            for (int a = j; a < nu; ++a) acc = fma(sLi[12 * a + j], sT[12 * a + col], acc);
+            Ks[(size_t)k * 288 + e] = -acc;
+            Ks[(size_t)k * 288 + 144 + e] = (col < nu) ? sLi[e] : 0.0;
+          }
         }
         __syncthreads();
         double *tmp = Pc;
@@ -472,41 +488,40 @@ __global__ void __launch_bounds__(BS) mpc_riccati_kernel(const MpcParams P, int 
         }
         __syncthreads();
         if (warp == 0) {
-          // vector backward sweep: lanes 0..11 hold p
+          // vector backward sweep: lanes 0..11 hold p; compact input quantities live in lanes < nu
           double pv = 0.0;  // p[lane]
           double pre[9];
           for (int m = 0; m < 9; ++m) pre[m] = Ks[(size_t)(N - 1) * 288 + lane + 32 * m];
           for (int k = N - 1; k >= 0; --k) {
+            const int nu = sNu[k];
             for (int m = 0; m < 9; ++m) sKbuf[lane + 32 * m] = pre[m];
             if (k > 0)
               for (int m = 0; m < 9; ++m) pre[m] = Ks[(size_t)(k - 1) * 288 + lane + 32 * m];
             if (lane < 12) sVec[lane] = pv;
             __syncwarp();
-            double hu = 0.0;
-            if (lane < 12) {
-              const int f = lane / 3, c = lane - 3 * f;
-              if (sOn[k * 4 + f]) {
-                const double *Bw = sBw + (k * 4 + f) * 9;
-                hu = sRt12[12 * k + lane] + Bw[c] * sVec[6] + Bw[3 + c] * sVec[7] + Bw[6 + c] * sVec[8] + dm * sVec[9 + c];
-              }
-              sVec[16 + lane] = hu;
+            if (lane < nu) {
+              const int jj = sAct[12 * k + lane], f = jj / 3, c = jj - 3 * f;
+              const double *Bw = sBw + (k * 4 + f) * 9;
+              sVec[16 + lane] = sRt12[12 * k + jj] + Bw[c] * sVec[6] + Bw[3 + c] * sVec[7] + Bw[6 + c] * sVec[8] + dm * sVec[9 + c];
             }
             __syncwarp();
-            double yv = 0.0;
-            if (lane < 12) {
+            if (lane < nu) {
+              double yv = 0.0;
               for (int a = 0; a <= lane; ++a) yv = fma(sKbuf[144 + 12 * lane + a], sVec[16 + a], yv);
               sVec[32 + lane] = yv;  // y = L^-1 hu
             }
             __syncwarp();
             if (lane < 12) {
-              double kk = 0.0, pn = sVec[lane];
-              for (int a = lane; a < 12; ++a) kk = fma(sKbuf[144 + 12 * a + lane], sVec[32 + a], kk);
-#pragma unroll
-              for (int a = 0; a < 12; ++a) pn = fma(sKbuf[12 * a + lane], sVec[16 + a], pn);
+              double pn = sVec[lane];
+              for (int a = 0; a < nu; ++a) pn = fma(sKbuf[12 * a + lane], sVec[16 + a], pn);
               if (lane >= 6 && lane < 9) pn += dt * (sRot[lane - 6] * sVec[0] + sRot[3 + lane - 6] * sVec[1] + sRot[6 + lane - 6] * sVec[2]);
               else if (lane >= 9) pn += dt * sVec[lane - 6];
-              sKK[12 * k + lane] = -kk;
               pv = pn;
+              if (lane < nu) {
+                double kk = 0.0;
+                for (int a = lane; a < nu; ++a) kk = fma(sKbuf[144 + 12 * a + lane], sVec[32 + a], kk);
+                sKK[12 * k + lane] = -kk;
+              }
             }
             __syncwarp();
           }
@@ -515,20 +530,25 @@ __global__ void __launch_bounds__(BS) mpc_riccati_kernel(const MpcParams P, int 
           for (int m = 0; m < 5; ++m)
             if (lane + 32 * m < 144) pre[m] = Ks[lane + 32 * m];
           for (int k = 0; k < N; ++k) {
+            const int nu = sNu[k];
             for (int m = 0; m < 5; ++m)
               if (lane + 32 * m < 144) sKbuf[lane + 32 * m] = pre[m];
             if (k + 1 < N)
               for (int m = 0; m < 5; ++m)
                 if (lane + 32 * m < 144) pre[m] = Ks[(size_t)(k + 1) * 288 + lane + 32 * m];
-            if (lane < 12) sVec[lane] = dx;
-            __syncwarp();
             if (lane < 12) {
+              sVec[lane] = dx;
+              sVec[16 + lane] = 0.0;
+              sDU[12 * k + lane] = 0.0;
+            }
+            __syncwarp();
+            if (lane < nu) {
               double du = sKK[12 * k + lane];
 #pragma unroll
               for (int i = 0; i < 12; ++i) du = fma(sKbuf[12 * lane + i], sVec[i], du);
-              if (!sOn[k * 4 + lane / 3]) du = 0.0;
-              sDU[12 * k + lane] = du;
-              sVec[16 + lane] = du;
+              const int jj = sAct[12 * k + lane];
+              sDU[12 * k + jj] = du;
+              sVec[16 + jj] = du;
             }
             __syncwarp();
             if (lane < 12) {
@@ -641,9 +661,11 @@ __global__ void __launch_bounds__(BS) mpc_riccati_kernel(const MpcParams P, int 
   (void)NS;
 }
 
-int riccati_grid(int num_sms) {
+int riccati_grid(int num_sms, int horizon) {
   int occ = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, mpc_riccati_kernel<96>, 96, 0) != cudaSuccess) {
+  const cudaError_t e = (4 * horizon <= 64) ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, mpc_riccati_kernel<64>, 64, 0)
+                                            : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, mpc_riccati_kernel<96>, 96, 0);
+  if (e != cudaSuccess) {
     cudaGetLastError();
     occ = 1;
   }

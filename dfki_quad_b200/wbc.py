@@ -134,18 +134,27 @@ class BatchedWBCSolver:
         except Exception:
             pass
 
-    def solve(self, qp: QuadraticProgram):
-        """-> (x [n,nq], info structured array).  Failed problems keep zeros."""
+    def abi_arrays(self, qp: QuadraticProgram):
+        """Column-major (Eigen) layouts of the C ABI, as ARC-OPT's QuadraticProgram already holds them."""
         n = qp.H.shape[0]
         nq, nc = self.cfg.nq, self.cfg.neq + self.cfg.nin
         assert qp.neq == self.cfg.neq and qp.A.shape == (n, nc, nq)
-        # Eigen column-major layouts, as ARC-OPT's QuadraticProgram holds them
         H = np.ascontiguousarray(np.transpose(qp.H, (0, 2, 1)))
         A = np.ascontiguousarray(np.transpose(qp.A, (0, 2, 1)))  # [n][nq][nc] == column-major nc x nq
         g = np.ascontiguousarray(qp.g)
         lo = np.ascontiguousarray(np.clip(qp.lower_y, -INF, INF))
         hi = np.ascontiguousarray(np.clip(qp.upper_y, -INF, INF))
-        x = np.zeros((n, nq))
+        return H, g, A, lo, hi
+
+    def solve(self, qp: QuadraticProgram):
+        """-> (x [n,nq], info structured array).  Failed problems keep zeros."""
+        return self.solve_abi(*self.abi_arrays(qp))
+
+    def solve_abi(self, H, g, A, lo, hi, x=None):
+        """b200qp_wbc_solve_batch on arrays that are already in the ABI layout (no host-side reshuffling)."""
+        n, nq = g.shape
+        if x is None:
+            x = np.zeros((n, nq))
         info = (_lib.SolverInfo * max(n, 1))()
         rc = self._lib.b200qp_wbc_solve_batch(self._h, n, H.ctypes.data, g.ctypes.data, A.ctypes.data, lo.ctypes.data,
                                               hi.ctypes.data, x.ctypes.data, C.addressof(info))
