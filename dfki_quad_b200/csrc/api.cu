@@ -1,5 +1,6 @@
 // C ABI of libb200qp.so (include/b200qp.h): handle management, staging buffers, kernel launches.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -72,6 +73,7 @@ struct b200qp_mpc {
   int last_n = 0;
   int last_launches = 0;
   bool want_duals = false;
+  long long *d_dbg_cycles = nullptr;  // optional per-phase cycle accounting (B200QP_PHASE_CYCLES=1)
 };
 
 static void fill_params(b200qp_mpc *h) {
@@ -155,7 +157,7 @@ int32_t b200qp_mpc_create(const b200qp_mpc_config *cfg, b200qp_mpc **out) {
       int g = h->num_sms * admm_occupancy(b);
       if ((size_t)g > nb) g = (int)nb;
       h->grid[b] = g;
-      CK(cudaMalloc(&h->d_hscratch[b], (size_t)g * bs * bs * sizeof(double)));
+      CK(cudaMalloc(&h->d_hscratch[b], (size_t)g * ((size_t)bs * bs + B200QP_MAX_HORIZON * 36) * sizeof(double)));
     }
   }
   if (cfg->solver == B200QP_SOLVER_SPARSE_RICCATI) {
@@ -163,6 +165,10 @@ int32_t b200qp_mpc_create(const b200qp_mpc_config *cfg, b200qp_mpc **out) {
     if ((size_t)g > nb) g = (int)nb;
     h->ric_grid = g;
     CK(cudaMalloc(&h->d_ric_scratch, (size_t)g * B200QP_MAX_HORIZON * 288 * sizeof(double)));
+  }
+  if (getenv("B200QP_PHASE_CYCLES")) {
+    CK(cudaMalloc(&h->d_dbg_cycles, nb * 10 * sizeof(long long)));
+    CK(cudaMemset(h->d_dbg_cycles, 0, nb * 10 * sizeof(long long)));
   }
   CK(cudaMallocHost(&h->h_in, nb * in_d * sizeof(double)));
   CK(cudaMallocHost(&h->h_contact, nb * N * 4));
@@ -249,6 +255,7 @@ static int32_t solve_device_impl(b200qp_mpc *h, int32_t n, const double *d_in, c
       B.dbg_index = dbg_index;
       B.dbg_H = dbg_H;
       B.dbg_g = dbg_g;
+      B.dbg_cycles = h->d_dbg_cycles;
       int g = h->grid[b];
       if (g > n) g = n;
       CK(launch_mpc_admm(b, h->P, B, g, h->stream));
@@ -408,6 +415,13 @@ int32_t b200qp_mpc_last_timing(b200qp_mpc *h, float *kernel_ms, int32_t *kernel_
 }
 
 void *b200qp_mpc_stream(b200qp_mpc *h) { return h ? (void *)h->stream : nullptr; }
+
+/* development hook (not part of the public header): per-phase cycle counters of the last solve, [n][10] */
+int32_t b200qp_dev_phase_cycles(b200qp_mpc *h, int32_t n, long long *out) {
+  if (!h || !h->d_dbg_cycles || !out) return B200QP_ERR_ARG;
+  CK(cudaMemcpy(out, h->d_dbg_cycles, (size_t)n * 10 * sizeof(long long), cudaMemcpyDeviceToHost));
+  return B200QP_OK;
+}
 
 int32_t b200qp_gait_schedule_device(int32_t n, int32_t steps, double dt, const double *d_period, const double *d_duty,
                                     const double *d_offset, const double *d_phase, const uint8_t *d_measured_contact,

@@ -38,6 +38,7 @@ struct MpcBuffers {
   int dbg_index;
   double *dbg_H;
   double *dbg_g;
+  long long *dbg_cycles;  // [n][10] per-phase cycles of thread 0, or nullptr
 };
 
 // Eigen::Quaternion::toRotationMatrix for q = (x, y, z, w); R is row-major [3][3].

@@ -15,6 +15,16 @@
 
 namespace b200qp {
 
+// optional per-phase cycle accounting (B.dbg_cycles != nullptr): thread 0 accumulates clock64() deltas per phase
+#define PH(idx)                                  \
+  do {                                           \
+    if (timing && tid == 0) {                    \
+      const long long t__ = clock64();           \
+      cyc[idx] += t__ - tlast;                   \
+      tlast = t__;                               \
+    }                                            \
+  } while (0)
+
 // ---------------------------------------------------------------------------------------------------------------
 // per-foot constraint rows (reduced problem), in the order
 //   0: fx in [-fmax, fmax]   1: fy in [-fmax, fmax]   2: fz in [fmin, fmax]            (mpc.cpp:103-109)
@@ -50,65 +60,43 @@ __device__ __forceinline__ double foot_at(int c, const double (&w)[7], double mu
   return (c == 0) ? (w[0] + w[3] + w[4]) : (c == 1) ? (w[1] + w[5] + w[6]) : (w[2] + mu * ((w[4] - w[3]) + (w[6] - w[5])));
 }
 
-// Reduced row echelon form of the active rows of one foot: returns nz = 3 - rank, particular solution cf and
-// null-space basis Z (column q at Z[3q..3q+2]).
-__device__ int foot_nullspace(unsigned actl, unsigned actu, double mu, const double (&lo)[7], const double (&hi)[7],
-                              double (&cf)[3], double (&Z)[9]) {
-  double M[7][4];
-  int m = 0;
-  for (int r = 0; r < 7; ++r) {
-    const bool l = (actl >> r) & 1u, u = (actu >> r) & 1u;
-    if (l || u) {
-      double a[3];
-      foot_row_vec(r, mu, a);
-      M[m][0] = a[0];
-      M[m][1] = a[1];
-      M[m][2] = a[2];
-      M[m][3] = l ? lo[r] : hi[r];
-      ++m;
-    }
-  }
-  int piv[3];
-  int np = 0;
-  for (int col = 0; col < 3 && np < m; ++col) {
-    int p = np;
-    double best = fabs(M[np][col]);
-    for (int q = np + 1; q < m; ++q)
-      if (fabs(M[q][col]) > best) {
-        best = fabs(M[q][col]);
-        p = q;
-      }
-    if (best < 1e-12) continue;
-    for (int t = 0; t < 4; ++t) {
-      const double tmp = M[np][t];
-      M[np][t] = M[p][t];
-      M[p][t] = tmp;
-    }
-    const double inv = 1.0 / M[np][col];
-    for (int t = 0; t < 4; ++t) M[np][t] *= inv;
-    for (int q = 0; q < m; ++q)
-      if (q != np) {
-        const double f = M[q][col];
-        if (f != 0.0)
-          for (int t = 0; t < 4; ++t) M[q][t] -= f * M[np][t];
-      }
-    piv[np++] = col;
-  }
-  cf[0] = cf[1] = cf[2] = 0.0;
-  for (int i = 0; i < np; ++i) cf[piv[i]] = M[i][3];
+// Null space of the active rows of one foot in closed form (register-only; a generic 7x4 rref through local memory
+// cost 20 % of the kernel): returns nz = 3 - rank, particular solution cf and basis Z (column q at Z[3q..3q+2]).
+// Rows: 0/1/2 boxes on x/y/z, 3: x - mu z = 0, 4: x + mu z = 0, 5: y - mu z = 0, 6: y + mu z = 0.  Inconsistent
+// combinations (only produced by a bad active-set guess) are resolved by priority: z box, cone apex, x box + cone.
+__device__ __forceinline__ int foot_nullspace(unsigned actl, unsigned actu, double mu, const double (&lo)[7],
+                                              const double (&hi)[7], double *cf, double *Z) {  // cf, Z: shared memory
+  const unsigned act = actl | actu;
+  const bool bx = act & 1u, by = act & 2u, bz = act & 4u;
+  const double vx = (actl & 1u) ? lo[0] : hi[0], vy = (actl & 2u) ? lo[1] : hi[1], vz = (actl & 4u) ? lo[2] : hi[2];
+  const bool x3 = act & 8u, x4 = act & 16u, y5 = act & 32u, y6 = act & 64u;
+  const double imu = (mu > 0.0) ? 1.0 / mu : 0.0;
+  // slope of the tie x = sx mu z (0 when not tied to z by exactly one cone row)
+  const double sx = (x3 && !x4) ? 1.0 : ((x4 && !x3) ? -1.0 : 0.0);
+  const double sy = (y5 && !y6) ? 1.0 : ((y6 && !y5) ? -1.0 : 0.0);
+  bool zfix = bz;
+  double zval = vz;
+  if (!zfix && ((x3 && x4) || (y5 && y6))) { zfix = true; zval = 0.0; }          // apex: x (or y) = 0 and z = 0
+  if (!zfix && bx && sx != 0.0 && mu > 0.0) { zfix = true; zval = sx * vx * imu; }  // x box and one x-cone row pin z
+  if (!zfix && by && sy != 0.0 && mu > 0.0) { zfix = true; zval = sy * vy * imu; }
   int nz = 0;
-  for (int col = 0; col < 3; ++col) {
-    bool isp = false;
-    for (int i = 0; i < np; ++i) isp |= (piv[i] == col);
-    if (isp) continue;
-    double v[3] = {0.0, 0.0, 0.0};
-    v[col] = 1.0;
-    for (int i = 0; i < np; ++i) v[piv[i]] = -M[i][col];
-    Z[3 * nz + 0] = v[0];
-    Z[3 * nz + 1] = v[1];
-    Z[3 * nz + 2] = v[2];
-    ++nz;
-  }
+  // x
+  double xc = 0.0, xt = 0.0;  // x = xc + xt * z_free
+  bool xfree = false;
+  if (x3 && x4) xc = 0.0;
+  else if (bx) xc = vx;
+  else if (sx != 0.0) { if (zfix) xc = sx * mu * zval; else xt = sx * mu; }
+  else xfree = true;
+  double yc = 0.0, yt = 0.0;
+  bool yfree = false;
+  if (y5 && y6) yc = 0.0;
+  else if (by) yc = vy;
+  else if (sy != 0.0) { if (zfix) yc = sy * mu * zval; else yt = sy * mu; }
+  else yfree = true;
+  cf[0] = xc; cf[1] = yc; cf[2] = zfix ? zval : 0.0;
+  if (xfree) { Z[3 * nz] = 1.0; Z[3 * nz + 1] = 0.0; Z[3 * nz + 2] = 0.0; ++nz; }
+  if (yfree) { Z[3 * nz] = 0.0; Z[3 * nz + 1] = 1.0; Z[3 * nz + 2] = 0.0; ++nz; }
+  if (!zfix) { Z[3 * nz] = xt; Z[3 * nz + 1] = yt; Z[3 * nz + 2] = 1.0; ++nz; }
   return nz;
 }
 
@@ -223,14 +211,101 @@ __device__ void nnls3(const double (*M)[3], int m, const double (&b)[3], double 
 // dense helpers on the shared-memory matrix K (column-major, odd leading dimension LD => row and column
 // accesses across a warp are both bank-conflict free for 8-byte words)
 
-// in-place Gauss-Jordan inverse of an SPD matrix (no pivoting), thread i owns row i.  Per pivot p: the pivot row is
-// staged in prow[], every other row does a rank-1 update against it, and the pivot row itself is rescaled with one
-// element per thread (no single-thread tail, no divergent long branch).
+// In-place Gauss-Jordan inverse of an SPD matrix (no pivoting), thread i owns row i.
+// Blocked: 4 pivots per step.  With D = A[P,P], the block step is
+//     A[P,P] <- D^-1,  A[P,R] <- D^-1 A[P,R],  A[R,P] <- -A[R,P] D^-1,  A[R,R] <- A[R,R] - A[R,P] D^-1 A[P,R]
+// so every row element is read and written once per FOUR pivots, one reciprocal pair and two barriers per four pivots
+// (the scalar sweep was bound by exactly that per-pivot latency).  The old pivot rows are staged in prow4[j][4]; the new
+// pivot rows are produced column-wise (thread j writes A[P, j]) so that no thread runs a long divergent branch.
+// The last n mod 4 pivots use the scalar step.
 template <int LD>
-__device__ __forceinline__ void gj_invert(double *K, int n, double *prow) {
+__device__ __forceinline__ void gj_invert(double *K, int n, double *prow4) {
   const int i = threadIdx.x;
   double *Ki = K + i;
-  for (int p = 0; p < n; ++p) {
+  int p0 = 0;
+  for (; p0 + 3 < n; p0 += 4) {
+    if (i < n) {  // stage column i of the 4 pivot rows: prow4[i][q] = A[p0+q][i]
+      double2 a, b;
+      a.x = K[i * LD + p0];
+      a.y = K[i * LD + p0 + 1];
+      b.x = K[i * LD + p0 + 2];
+      b.y = K[i * LD + p0 + 3];
+      *reinterpret_cast<double2 *>(prow4 + 4 * i) = a;
+      *reinterpret_cast<double2 *>(prow4 + 4 * i + 2) = b;
+    }
+    __syncthreads();
+    if (i < n) {
+      // D[q][q'] = A[p0+q][p0+q'] = prow4[p0+q'][q]; 4x4 inverse through 2x2 blocks (two reciprocals)
+      double D[4][4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const double2 a = *reinterpret_cast<const double2 *>(prow4 + 4 * (p0 + c));
+        const double2 b = *reinterpret_cast<const double2 *>(prow4 + 4 * (p0 + c) + 2);
+        D[0][c] = a.x; D[1][c] = a.y; D[2][c] = b.x; D[3][c] = b.y;
+      }
+      const double r1 = 1.0 / (D[0][0] * D[1][1] - D[0][1] * D[1][0]);
+      const double i00 = D[1][1] * r1, i01 = -D[0][1] * r1, i10 = -D[1][0] * r1, i11 = D[0][0] * r1;  // A11^-1
+      // T = A21 A11^-1
+      const double t00 = D[2][0] * i00 + D[2][1] * i10, t01 = D[2][0] * i01 + D[2][1] * i11;
+      const double t10 = D[3][0] * i00 + D[3][1] * i10, t11 = D[3][0] * i01 + D[3][1] * i11;
+      // S = A22 - T A12
+      const double s00 = D[2][2] - (t00 * D[0][2] + t01 * D[1][2]), s01 = D[2][3] - (t00 * D[0][3] + t01 * D[1][3]);
+      const double s10 = D[3][2] - (t10 * D[0][2] + t11 * D[1][2]), s11 = D[3][3] - (t10 * D[0][3] + t11 * D[1][3]);
+      const double r2 = 1.0 / (s00 * s11 - s01 * s10);
+      const double j00 = s11 * r2, j01 = -s01 * r2, j10 = -s10 * r2, j11 = s00 * r2;  // S^-1
+      // U = A11^-1 A12 ; E12 = -U S^-1 ; E21 = -S^-1 T ; E11 = A11^-1 + U S^-1 T
+      const double u00 = i00 * D[0][2] + i01 * D[1][2], u01 = i00 * D[0][3] + i01 * D[1][3];
+      const double u10 = i10 * D[0][2] + i11 * D[1][2], u11 = i10 * D[0][3] + i11 * D[1][3];
+      double E[4][4];
+      E[2][2] = j00; E[2][3] = j01; E[3][2] = j10; E[3][3] = j11;
+      E[0][2] = -(u00 * j00 + u01 * j10); E[0][3] = -(u00 * j01 + u01 * j11);
+      E[1][2] = -(u10 * j00 + u11 * j10); E[1][3] = -(u10 * j01 + u11 * j11);
+      E[2][0] = -(j00 * t00 + j01 * t10); E[2][1] = -(j00 * t01 + j01 * t11);
+      E[3][0] = -(j10 * t00 + j11 * t10); E[3][1] = -(j10 * t01 + j11 * t11);
+      E[0][0] = i00 - (E[0][2] * t00 + E[0][3] * t10); E[0][1] = i01 - (E[0][2] * t01 + E[0][3] * t11);
+      E[1][0] = i10 - (E[1][2] * t00 + E[1][3] * t10); E[1][1] = i11 - (E[1][2] * t01 + E[1][3] * t11);
+      const bool inP = (i >= p0) && (i < p0 + 4);
+      // column duty: new pivot-row entries of column i
+      {
+        const double2 a = *reinterpret_cast<const double2 *>(prow4 + 4 * i);
+        const double2 b = *reinterpret_cast<const double2 *>(prow4 + 4 * i + 2);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const double v = inP ? E[q][i - p0] : (E[q][0] * a.x + E[q][1] * a.y + E[q][2] * b.x + E[q][3] * b.y);
+          K[i * LD + p0 + q] = v;
+        }
+      }
+      if (!inP) {  // row duty
+        const double c0 = Ki[p0 * LD], c1 = Ki[(p0 + 1) * LD], c2 = Ki[(p0 + 2) * LD], c3 = Ki[(p0 + 3) * LD];
+        const double w0 = c0 * E[0][0] + c1 * E[1][0] + c2 * E[2][0] + c3 * E[3][0];
+        const double w1 = c0 * E[0][1] + c1 * E[1][1] + c2 * E[2][1] + c3 * E[3][1];
+        const double w2 = c0 * E[0][2] + c1 * E[1][2] + c2 * E[2][2] + c3 * E[3][2];
+        const double w3 = c0 * E[0][3] + c1 * E[1][3] + c2 * E[2][3] + c3 * E[3][3];
+        int j = 0;
+        for (; j + 1 < n; j += 2) {
+          const double2 a0 = *reinterpret_cast<const double2 *>(prow4 + 4 * j);
+          const double2 b0 = *reinterpret_cast<const double2 *>(prow4 + 4 * j + 2);
+          const double2 a1 = *reinterpret_cast<const double2 *>(prow4 + 4 * j + 4);
+          const double2 b1 = *reinterpret_cast<const double2 *>(prow4 + 4 * j + 6);
+          const double k0 = Ki[j * LD], k1 = Ki[(j + 1) * LD];
+          Ki[j * LD] = k0 - (w0 * a0.x + w1 * a0.y + w2 * b0.x + w3 * b0.y);
+          Ki[(j + 1) * LD] = k1 - (w0 * a1.x + w1 * a1.y + w2 * b1.x + w3 * b1.y);
+        }
+        if (j < n) {
+          const double2 a0 = *reinterpret_cast<const double2 *>(prow4 + 4 * j);
+          const double2 b0 = *reinterpret_cast<const double2 *>(prow4 + 4 * j + 2);
+          Ki[j * LD] -= (w0 * a0.x + w1 * a0.y + w2 * b0.x + w3 * b0.y);
+        }
+        Ki[p0 * LD] = -w0;
+        Ki[(p0 + 1) * LD] = -w1;
+        Ki[(p0 + 2) * LD] = -w2;
+        Ki[(p0 + 3) * LD] = -w3;
+      }
+    }
+    __syncthreads();
+  }
+  double *prow = prow4;
+  for (int p = p0; p < n; ++p) {  // scalar tail
     double pi = 0.0;
     if (i < n) {
       pi = K[i * LD + p];  // pivot row element (p, i)
@@ -241,17 +316,7 @@ __device__ __forceinline__ void gj_invert(double *K, int n, double *prow) {
       const double d = 1.0 / prow[p];
       if (i != p) {
         const double f = Ki[p * LD] * d;
-        int j = 0;
-        for (; j + 3 < n; j += 4) {
-          const double2 p01 = *reinterpret_cast<const double2 *>(prow + j);
-          const double2 p23 = *reinterpret_cast<const double2 *>(prow + j + 2);
-          const double k0 = Ki[j * LD], k1 = Ki[(j + 1) * LD], k2 = Ki[(j + 2) * LD], k3 = Ki[(j + 3) * LD];
-          Ki[j * LD] = fma(-f, p01.x, k0);
-          Ki[(j + 1) * LD] = fma(-f, p01.y, k1);
-          Ki[(j + 2) * LD] = fma(-f, p23.x, k2);
-          Ki[(j + 3) * LD] = fma(-f, p23.y, k3);
-        }
-        for (; j < n; ++j) Ki[j * LD] = fma(-f, prow[j], Ki[j * LD]);
+        for (int j = 0; j < n; ++j) Ki[j * LD] = fma(-f, prow[j], Ki[j * LD]);
         Ki[p * LD] = -f;
       }
       K[i * LD + p] = (i == p) ? d : pi * d;  // rescaled pivot row, element (p, i)
@@ -320,20 +385,23 @@ __global__ void __launch_bounds__(BS) mpc_admm_kernel(const MpcParams P, const M
   double *s_r = s_xt + BS;          // [BS] H x + g
   double *s_c = s_r + BS;           // [BS] particular solution of the polish
   double *s_w = s_c + BS;           // [BS] reduced solution
-  double *prow = s_w + BS;          // [BS] pivot row
-  double *red = prow + BS;          // [4 * 32]
-  __shared__ double s_Bw[MAXH * 36];       // Bw_kf, row-major 3x3 per (k,f); zero for swing feet
-  __shared__ double s_lw[(MAXH + 2) * 3];  // adjoint, angular-velocity part, per stage
-  __shared__ double s_lv[(MAXH + 2) * 3];  // adjoint, linear-velocity part
-  __shared__ double s_qe[(MAXH + 1) * 12]; // Q e_k (free-response error), later reused for suffix sums
+  double *prow = s_w + BS;          // [4 * BS] staged pivot rows (4 per block step)
+  double *red = prow + 4 * BS;      // [4 * 32]
+  // Stage quantities are only needed while K is not (assembly before the first factorisation, outputs after the solve), so
+  // they alias the K region: one more resident block per SM.  Bw is parked in the per-block global scratch in between.
+  double *s_Bw = K;                        // [MAXH * 36] Bw_kf, row-major 3x3 per (k,f); zero for swing feet
+  double *s_qe = s_Bw + MAXH * 36;         // [(MAXH + 1) * 12] Q e_k (free-response error), later reused for suffix sums
+  double *s_lw = s_qe + (MAXH + 1) * 12;   // [(MAXH + 2) * 3] adjoint, angular-velocity part, per stage
+  double *s_lv = s_lw + (MAXH + 2) * 3;    // [(MAXH + 2) * 3] adjoint, linear-velocity part
+  double *s_bw = s_lv + (MAXH + 2) * 3;    // [MAXH * 6] per-stage input effect on (omega, v) for the roll-out
+  double *s_X = s_bw + MAXH * 6;           // [(MAXH + 1) * 13]
+  static_assert(MAXH * 36 + (MAXH + 1) * 12 + 2 * (MAXH + 2) * 3 + MAXH * 6 + (MAXH + 1) * 13 <= NV * LD, "alias region");
   __shared__ double s_yawd[MAXH + 1];
   __shared__ double s_x0[13];
   __shared__ double s_Rt[9];   // Rt(psi0) row-major
   __shared__ double s_G2[9];   // dt^2 Rt^T Qth Rt
   __shared__ double s_fZ[MAXF * 9];
   __shared__ double s_fc[MAXF * 3];
-  __shared__ double s_bw[MAXH * 6];  // per-stage input effect on (omega, v) for the roll-out
-  __shared__ double s_X[(MAXH + 1) * 13];
   __shared__ short s_fidx[MAXH * 4];  // (k,f) -> free foot index or -1
   __shared__ unsigned char s_fk[MAXF], s_ff[MAXF], s_fnz[MAXF];
   __shared__ short s_foff[MAXF + 1];
@@ -346,7 +414,8 @@ __global__ void __launch_bounds__(BS) mpc_admm_kernel(const MpcParams P, const M
   const int tid = threadIdx.x;
   const int N = P.N;
   const double dt = P.dt, mu = P.mu;
-  double *Hs = B.hscratch + (size_t)blockIdx.x * BS * BS;
+  double *Hs = B.hscratch + (size_t)blockIdx.x * (BS * BS + MAXH * 36);
+  double *Bw_park = Hs + BS * BS;
   double lo[7], hi[7];
   foot_bounds(P.fmin, P.fmax, lo, hi);
 
@@ -361,6 +430,9 @@ __global__ void __launch_bounds__(BS) mpc_admm_kernel(const MpcParams P, const M
     const uint8_t *ct = B.contact + (size_t)prob * N * 4;
     const double mass = rec[13];
 
+    const bool timing = B.dbg_cycles != nullptr;
+    long long cyc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    long long tlast = timing ? clock64() : 0;
     // ---- phase 0: per-stage quantities -------------------------------------------------------------------
     if (tid <= N) {
       double R[3][3];
@@ -531,6 +603,7 @@ __global__ void __launch_bounds__(BS) mpc_admm_kernel(const MpcParams P, const M
     }
     __syncthreads();
 
+    PH(0);
     // ---- phase 1: condensed reduced Hessian and gradient (K1) ------------------------------------------------
     const bool act = tid < n;
     const int fa = act ? tid / 3 : 0;
@@ -556,23 +629,22 @@ __global__ void __launch_bounds__(BS) mpc_admm_kernel(const MpcParams P, const M
         for (int cc = 0; cc < 3; ++cc) h[cc] = v0 * Bwb[cc] + v1 * Bwb[3 + cc] + v2 * Bwb[6 + cc];
         h[ca] += cnt * lv + S2 * lp;
         if (b == fa) h[ca] += P.alpha;
-        for (int cc = 0; cc < 3; ++cc) {
-          K[(3 * b + cc) * LD + tid] = h[cc];
-          Hs[(3 * b + cc) * BS + tid] = h[cc];
-        }
+        for (int cc = 0; cc < 3; ++cc) Hs[(3 * b + cc) * BS + tid] = h[cc];
       }
       gi = Bwa[ca] * s_lw[3 * (j + 1)] + Bwa[3 + ca] * s_lw[3 * (j + 1) + 1] + Bwa[6 + ca] * s_lw[3 * (j + 1) + 2] +
            dm * s_lv[3 * (j + 1) + ca];
       s_g[tid] = gi;
     }
+    for (int e = tid; e < N * 36; e += BS) Bw_park[e] = s_Bw[e];
     __syncthreads();
     if (prob == B.dbg_index && B.dbg_H != nullptr) {
       if (act) {
-        for (int jx = 0; jx < n; ++jx) B.dbg_H[(size_t)jx * n + tid] = K[jx * LD + tid];
+        for (int jx = 0; jx < n; ++jx) B.dbg_H[(size_t)jx * n + tid] = Hs[jx * BS + tid];
         B.dbg_g[tid] = gi;
       }
     }
 
+    PH(1);
     // ---- phase 2: ADMM (K2a) -------------------------------------------------------------------------------------
     const double Ei = (ca == 2) ? (1.0 + 4.0 * mu * mu) : 3.0;  // diag(A^T A)
     double rho = P.rho0;
@@ -607,6 +679,7 @@ __global__ void __launch_bounds__(BS) mpc_admm_kernel(const MpcParams P, const M
           __syncthreads();
           gj_invert<LD>(K, n, prow);
           need_factor = false;
+          PH(2);
         }
         const double rinv = 1.0 / rho;
         int it_block = 0;
@@ -637,6 +710,7 @@ __global__ void __launch_bounds__(BS) mpc_admm_kernel(const MpcParams P, const M
             }
           }
         }
+        PH(3);
         // residuals (OSQP termination test) on the true H
         __syncthreads();
         if (act) s_v[tid] = x;
@@ -681,6 +755,7 @@ __global__ void __launch_bounds__(BS) mpc_admm_kernel(const MpcParams P, const M
       }
       if (status == B200QP_ACADOS_NAN_DETECTED) break;
 
+      PH(4);
       // ---- phase 3: polish = primal-dual active-set sweeps in the null space of the active rows --------------
       if (act && ca == 2) {
         unsigned al = 0, au = 0;
@@ -697,11 +772,7 @@ __global__ void __launch_bounds__(BS) mpc_admm_kernel(const MpcParams P, const M
         ++rounds_total;
         __syncthreads();
         if (act && ca == 2) {
-          double cf[3], Z[9];
-          const int nz = foot_nullspace(s_actl[fa], s_actu[fa], mu, lo, hi, cf, Z);
-          s_fnz[fa] = (unsigned char)nz;
-          for (int t = 0; t < 3; ++t) s_fc[3 * fa + t] = cf[t];
-          for (int t = 0; t < 3 * nz; ++t) s_fZ[9 * fa + t] = Z[t];
+          s_fnz[fa] = (unsigned char)foot_nullspace(s_actl[fa], s_actu[fa], mu, lo, hi, s_fc + 3 * fa, s_fZ + 9 * fa);
         }
         __syncthreads();
         if (tid == 0) {
@@ -720,6 +791,7 @@ __global__ void __launch_bounds__(BS) mpc_admm_kernel(const MpcParams P, const M
         if (act) s_c[tid] = s_fc[tid];
         __syncthreads();
         const int nr = s_foff[nf];
+        PH(5);
         // hc = H c + g
         if (act) s_r[tid] = matvec_glob<BS>(Hs, n, s_c) + gi;
         // reduced Hessian Hr = Z^T H Z into K
@@ -746,7 +818,9 @@ __global__ void __launch_bounds__(BS) mpc_admm_kernel(const MpcParams P, const M
         __syncthreads();
         double grp = 0.0;
         if (tid < nr) grp = vp[0] * s_r[3 * ap] + vp[1] * s_r[3 * ap + 1] + vp[2] * s_r[3 * ap + 2];
+        PH(6);
         gj_invert<LD>(K, nr, prow);
+        PH(7);
         if (tid < nr) s_v[tid] = -grp;
         __syncthreads();
         double wred = 0.0;
@@ -771,6 +845,7 @@ __global__ void __launch_bounds__(BS) mpc_admm_kernel(const MpcParams P, const M
             if (tid < nr) wred += matvec_smem<LD>(K, nr, s_v);
           }
         }
+        PH(8);
         // per-foot optimality check: feasibility, NNLS duals over the geometrically tight rows, new active set
         double chk[3] = {0.0, 0.0, 0.0};  // stat, viol, comp
         bool bad = false;
@@ -781,50 +856,78 @@ __global__ void __launch_bounds__(BS) mpc_admm_kernel(const MpcParams P, const M
           foot_rows_eval(fx, fy, fz, mu, ax);
           const double sc = fmax(1.0, fmax(fabs(fx), fmax(fabs(fy), fabs(fz))));
           const double ttol = 1e-9 * sc;
-          double Mc[14][3];
-          int tagr[14];
-          int m = 0;
-          unsigned nl = 0, nu = 0;
+          unsigned nl = 0, nu = 0, tl = 0, tu = 0;  // violated rows (lower / upper side), tight rows
+#pragma unroll
           for (int r = 0; r < 7; ++r) {
-            double a[3];
-            foot_row_vec(r, mu, a);
             if (lo[r] > -BIG) {
               const double s = ax[r] - lo[r];
               if (s < -ttol) nl |= 1u << r;
               chk[1] = fmax(chk[1], -s);
-              if (fabs(s) <= ttol) {
-                Mc[m][0] = -a[0]; Mc[m][1] = -a[1]; Mc[m][2] = -a[2];
-                tagr[m++] = -(r + 1);
-              }
+              if (fabs(s) <= ttol) tl |= 1u << r;
             }
             if (hi[r] < BIG) {
               const double s = hi[r] - ax[r];
               if (s < -ttol) nu |= 1u << r;
               chk[1] = fmax(chk[1], -s);
-              if (fabs(s) <= ttol) {
+              if (fabs(s) <= ttol) tu |= 1u << r;
+            }
+          }
+          const double rx = s_r[3 * fa], ry = s_r[3 * fa + 1], rz = s_r[3 * fa + 2];
+          if (((tl | tu) & 3u) == 0u) {
+            // Fast path (no x/y box row tight - always the case for mu < 1): sign-feasible multipliers in closed form.
+            //   r_x + a3 - a4 = 0,  r_y + b5 - b6 = 0,  r_z - mu (a3 + a4 + b5 + b6) - c_l + c_u = 0,  all >= 0 and
+            //   non-zero only on tight rows; the minimal-sum split of the cone multipliers is the feasible one.
+            const double a3 = (tu & 8u) ? fmax(-rx, 0.0) : 0.0, a4 = (tl & 16u) ? fmax(rx, 0.0) : 0.0;
+            const double b5 = (tu & 32u) ? fmax(-ry, 0.0) : 0.0, b6 = (tl & 64u) ? fmax(ry, 0.0) : 0.0;
+            const double t = rz - mu * ((a3 + a4) + (b5 + b6));
+            const double cl = (tl & 4u) ? fmax(t, 0.0) : 0.0, cu = (tu & 4u) ? fmax(-t, 0.0) : 0.0;
+            chk[0] = fmax(fabs(rx + a3 - a4), fmax(fabs(ry + b5 - b6), fabs(t - cl + cu)));
+            ynew[2] = cu - cl;
+            ynew[3] = a3; ynew[4] = -a4; ynew[5] = b5; ynew[6] = -b6;
+            if (a3 > 0.0) nu |= 8u;
+            if (a4 > 0.0) nl |= 16u;
+            if (b5 > 0.0) nu |= 32u;
+            if (b6 > 0.0) nl |= 64u;
+            if (cl > 0.0) nl |= 4u;
+            if (cu > 0.0) nu |= 4u;
+            chk[2] = fmax(fmax(a3 * fabs(ax[3]), a4 * fabs(ax[4])), fmax(fmax(b5 * fabs(ax[5]), b6 * fabs(ax[6])),
+                          fmax(cl * fabs(ax[2] - lo[2]), cu * fabs(hi[2] - ax[2]))));
+            bad = !(chk[0] < BIG) || !(sc < BIG);
+          } else {  // general case: Lawson-Hanson NNLS over the tight rows
+            double Mc[14][3];
+            int tagr[14];
+            int m = 0;
+            for (int r = 0; r < 7; ++r) {
+              double a[3];
+              foot_row_vec(r, mu, a);
+              if ((tl >> r) & 1u) {
+                Mc[m][0] = -a[0]; Mc[m][1] = -a[1]; Mc[m][2] = -a[2];
+                tagr[m++] = -(r + 1);
+              }
+              if ((tu >> r) & 1u) {
                 Mc[m][0] = a[0]; Mc[m][1] = a[1]; Mc[m][2] = a[2];
                 tagr[m++] = (r + 1);
               }
             }
-          }
-          const double b3[3] = {-s_r[3 * fa], -s_r[3 * fa + 1], -s_r[3 * fa + 2]};
-          double coef[14], res[3] = {b3[0], b3[1], b3[2]};
-          if (m > 0) nnls3(Mc, m, b3, coef, res);
-          chk[0] = fmax(fabs(res[0]), fmax(fabs(res[1]), fabs(res[2])));
-          bad = !(chk[0] < BIG) || !(sc < BIG);
-          for (int q = 0; q < m; ++q)
-            if (coef[q] > 0.0) {
-              const int r = (tagr[q] > 0 ? tagr[q] : -tagr[q]) - 1;
-              if (tagr[q] > 0) {
-                nu |= 1u << r;
-                ynew[r] += coef[q];
-                chk[2] = fmax(chk[2], coef[q] * fabs(hi[r] - ax[r]));
-              } else {
-                nl |= 1u << r;
-                ynew[r] -= coef[q];
-                chk[2] = fmax(chk[2], coef[q] * fabs(ax[r] - lo[r]));
+            const double b3[3] = {-rx, -ry, -rz};
+            double coef[14], res[3] = {b3[0], b3[1], b3[2]};
+            if (m > 0) nnls3(Mc, m, b3, coef, res);
+            chk[0] = fmax(fabs(res[0]), fmax(fabs(res[1]), fabs(res[2])));
+            bad = !(chk[0] < BIG) || !(sc < BIG);
+            for (int q = 0; q < m; ++q)
+              if (coef[q] > 0.0) {
+                const int r = (tagr[q] > 0 ? tagr[q] : -tagr[q]) - 1;
+                if (tagr[q] > 0) {
+                  nu |= 1u << r;
+                  ynew[r] += coef[q];
+                  chk[2] = fmax(chk[2], coef[q] * fabs(hi[r] - ax[r]));
+                } else {
+                  nl |= 1u << r;
+                  ynew[r] -= coef[q];
+                  chk[2] = fmax(chk[2], coef[q] * fabs(ax[r] - lo[r]));
+                }
               }
-            }
+          }
           if (nl != s_actl[fa] || nu != s_actu[fa]) s_changed = 1;
           s_actl[fa] = (unsigned short)nl;
           s_actu[fa] = (unsigned short)nu;
@@ -853,10 +956,12 @@ __global__ void __launch_bounds__(BS) mpc_admm_kernel(const MpcParams P, const M
       }
     }
 
+    PH(9);
     // ---- phase 4: outputs -------------------------------------------------------------------------------------
     __syncthreads();
     if (status == B200QP_ACADOS_SUCCESS) {
       if (act) s_xt[tid] = xsol;
+      for (int e = tid; e < N * 36; e += BS) s_Bw[e] = Bw_park[e];
       __syncthreads();
       double *fo = B.forces + (size_t)prob * N * 12;
       for (int e = tid; e < N * 12; e += BS) {
@@ -935,6 +1040,8 @@ __global__ void __launch_bounds__(BS) mpc_admm_kernel(const MpcParams P, const M
         for (int e = tid; e < (N + 1) * 13; e += BS) xo[e] = s_X[e];
       }
     }
+    if (timing && tid == 0)
+      for (int q = 0; q < 10; ++q) B.dbg_cycles[(size_t)prob * 10 + q] = cyc[q];
     if (tid == 0) {
       b200qp_solver_info inf;
       inf.status = status;
@@ -976,7 +1083,7 @@ __global__ void mpc_bin_kernel(int n, int N, const uint8_t *__restrict__ contact
 
 template <int BS, int NV>
 static size_t admm_smem_bytes() {
-  return sizeof(double) * ((size_t)NV * (NV + 1) + 7 * BS + 4 * 32);
+  return sizeof(double) * ((size_t)NV * (NV + 1) + 10 * BS + 4 * 32);
 }
 
 template <int BS, int NV>
