@@ -76,6 +76,15 @@ struct b200qp_mpc {
   long long *d_dbg_cycles = nullptr;  // optional per-phase cycle accounting (B200QP_PHASE_CYCLES=1)
 };
 
+static bool is_pinned(const void *p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeHost;
+}
+
 static void fill_params(b200qp_mpc *h) {
   const b200qp_mpc_config &c = h->cfg;
   MpcParams &P = h->P;
@@ -301,30 +310,53 @@ int32_t b200qp_mpc_solve_batch(b200qp_mpc *h, int32_t n, const double *in, const
   const int N = h->cfg.horizon;
   const size_t in_b = (size_t)n * b200qp_mpc_in_doubles(N) * sizeof(double);
   const size_t f_b = (size_t)n * N * 12 * sizeof(double), x_b = (size_t)n * (N + 1) * 13 * sizeof(double);
-  // stage through pinned memory so the copies are asynchronous DMA
-  memcpy(h->h_in, in, in_b);
-  memcpy(h->h_contact, contact, (size_t)n * N * 4);
-  CK(cudaMemcpyAsync(h->d_in, h->h_in, in_b, cudaMemcpyHostToDevice, h->stream));
-  CK(cudaMemcpyAsync(h->d_contact, h->h_contact, (size_t)n * N * 4, cudaMemcpyHostToDevice, h->stream));
+  // Inputs: DMA straight from the caller's buffers when they are page-locked (cudaHostAlloc / cudaHostRegister /
+  // torch pin_memory), else stage through the handle's pinned buffers.
+  const bool in_pinned = is_pinned(in) && is_pinned(contact);
+  const double *src_in = in;
+  const uint8_t *src_ct = contact;
+  if (!in_pinned) {
+    memcpy(h->h_in, in, in_b);
+    memcpy(h->h_contact, contact, (size_t)n * N * 4);
+    src_in = h->h_in;
+    src_ct = h->h_contact;
+  }
+  CK(cudaMemcpyAsync(h->d_in, src_in, in_b, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->d_contact, src_ct, (size_t)n * N * 4, cudaMemcpyHostToDevice, h->stream));
   int32_t rc = solve_device_impl(h, n, h->d_in, h->d_contact, h->d_forces, h->d_xpred, h->d_info, -1, nullptr, nullptr);
   if (rc != B200QP_OK) return rc;
-  CK(cudaMemcpyAsync(h->h_forces, h->d_forces, f_b, cudaMemcpyDeviceToHost, h->stream));
-  CK(cudaMemcpyAsync(h->h_xpred, h->d_xpred, x_b, cudaMemcpyDeviceToHost, h->stream));
+  // The per-problem status comes back first: failed problems must leave the caller's output slots untouched
+  // (mpc.cpp:447-455), so the outputs can only be written in place when every problem succeeded.
   CK(cudaMemcpyAsync(h->h_info, h->d_info, (size_t)n * sizeof(b200qp_solver_info), cudaMemcpyDeviceToHost, h->stream));
+  const bool out_pinned = is_pinned(forces) && is_pinned(xpred);
+  if (!out_pinned) {
+    CK(cudaMemcpyAsync(h->h_forces, h->d_forces, f_b, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(h->h_xpred, h->d_xpred, x_b, cudaMemcpyDeviceToHost, h->stream));
+  }
   CK(cudaStreamSynchronize(h->stream));
-  // failed problems leave the caller's output slots untouched (mpc.cpp:447-455)
   const size_t f1 = (size_t)N * 12, x1 = (size_t)(N + 1) * 13;
   bool all_ok = true;
   for (int p = 0; p < n; ++p) all_ok &= (h->h_info[p].status == B200QP_ACADOS_SUCCESS);
-  if (all_ok) {
-    memcpy(forces, h->h_forces, f_b);
-    memcpy(xpred, h->h_xpred, x_b);
+  if (out_pinned && all_ok) {
+    CK(cudaMemcpyAsync(forces, h->d_forces, f_b, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(xpred, h->d_xpred, x_b, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
   } else {
-    for (int p = 0; p < n; ++p)
-      if (h->h_info[p].status == B200QP_ACADOS_SUCCESS) {
-        memcpy(forces + p * f1, h->h_forces + p * f1, f1 * sizeof(double));
-        memcpy(xpred + p * x1, h->h_xpred + p * x1, x1 * sizeof(double));
-      }
+    if (out_pinned) {
+      CK(cudaMemcpyAsync(h->h_forces, h->d_forces, f_b, cudaMemcpyDeviceToHost, h->stream));
+      CK(cudaMemcpyAsync(h->h_xpred, h->d_xpred, x_b, cudaMemcpyDeviceToHost, h->stream));
+      CK(cudaStreamSynchronize(h->stream));
+    }
+    if (all_ok) {
+      memcpy(forces, h->h_forces, f_b);
+      memcpy(xpred, h->h_xpred, x_b);
+    } else {
+      for (int p = 0; p < n; ++p)
+        if (h->h_info[p].status == B200QP_ACADOS_SUCCESS) {
+          memcpy(forces + p * f1, h->h_forces + p * f1, f1 * sizeof(double));
+          memcpy(xpred + p * x1, h->h_xpred + p * x1, x1 * sizeof(double));
+        }
+    }
   }
   memcpy(info, h->h_info, (size_t)n * sizeof(b200qp_solver_info));
   return B200QP_OK;
