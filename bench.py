@@ -102,6 +102,16 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def profiled_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed ncu --set full capture
+    (profiles/ncu_traffic.json, written by scripts/summarise_profile.py); None if that kernel was not captured."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        return json.load(open(p)).get(kernel, {}).get("dram_bytes_per_launch")
+    except Exception:
+        return None
+
+
 def dist_env():
     return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
 
@@ -246,6 +256,11 @@ def run_b200(args):
 
     if rank == 0:
         peak, peak_src = measured_peaks()
+        try:
+            fp64_peak = _lib.fp64_peak_tflops(dev)
+        except Exception:
+            fp64_peak = None
+        traffic = profiled_traffic(wl["kernel"])
         ab = algorithmic_bytes(N)
         # dominant kernel = mpc_admm_kernel<64,64> (all trot problems land in the n<=64 bin); the step's event time
         # also contains the bin kernel and two empty-bin launches (a few microseconds)
@@ -274,10 +289,12 @@ def run_b200(args):
             "gpu_launches": int(launches_per_step * args.steps),
             "clocks": clocks.summary(),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "kernel": wl["kernel"],
+                         "traffic": traffic, "peak_source": peak_src, "kernel": wl["kernel"],
                          "algorithmic_bytes_per_solve": ab,
                          "note": "latency/FP64-bound on-chip solve: HBM fraction is tiny by design (SURVEY.md 8d)"},
-            "fp64": {"flops_per_step": fl, "achieved_tflops": fl / kern_s / 1e12, "nominal_peak_tflops": 37.0},
+            "fp64": {"flops_per_step": fl, "achieved_tflops": fl / kern_s / 1e12, "measured_peak_tflops": fp64_peak,
+                     "frac": fl / kern_s / 1e12 / fp64_peak if fp64_peak else None, "nominal_peak_tflops": 37.0,
+                     "note": "algorithmic FP64 FLOPs of the method as implemented / step time; peak = DFMA microbenchmark on this GPU"},
         }
         if cpu is not None and "error" not in cpu:
             line["cpu_baseline"] = {"value": cpu["solved"] / cpu["seconds"], "unit": "solves/s", "cores": cpu["cores"],

@@ -41,7 +41,7 @@ class WbcConfig(C.Structure):
 
 
 EXPORTS = [
-    "b200qp_version", "b200qp_device_count", "b200qp_last_error", "b200qp_mpc_create", "b200qp_mpc_destroy",
+    "b200qp_version", "b200qp_device_count", "b200qp_last_error", "b200qp_fp64_peak_tflops", "b200qp_mpc_create", "b200qp_mpc_destroy",
     "b200qp_mpc_set_state_weights", "b200qp_mpc_set_input_weights", "b200qp_mpc_set_fmax", "b200qp_mpc_set_mu",
     "b200qp_mpc_solve_batch", "b200qp_mpc_solve_batch_device", "b200qp_mpc_get_duals", "b200qp_mpc_get_condensed",
     "b200qp_mpc_last_timing", "b200qp_mpc_stream", "b200qp_gait_schedule", "b200qp_gait_schedule_device",
@@ -64,6 +64,7 @@ def load() -> C.CDLL:
     lib.b200qp_version.restype = C.c_char_p
     lib.b200qp_last_error.restype = C.c_char_p
     lib.b200qp_device_count.restype = i32
+    lib.b200qp_fp64_peak_tflops.argtypes = [i32, p(dbl)]
     lib.b200qp_mpc_create.argtypes = [p(MpcConfig), p(vp)]
     lib.b200qp_mpc_create.restype = i32
     lib.b200qp_mpc_destroy.argtypes = [vp]
@@ -94,6 +95,12 @@ def load() -> C.CDLL:
             fn.restype = i32
     _lib = lib
     return lib
+
+
+def fp64_peak_tflops(device=0) -> float:
+    v = C.c_double()
+    check(load().b200qp_fp64_peak_tflops(device, C.byref(v)), "b200qp_fp64_peak_tflops")
+    return v.value
 
 
 def last_error() -> str:

@@ -16,6 +16,7 @@ cudaError_t launch_mpc_bin(int n, int N, const uint8_t *contact, int *bin_count,
                            b200qp_solver_info *info, cudaStream_t st);
 cudaError_t launch_mpc_admm(int bin, const MpcParams &P, const MpcBuffers &B, int grid, cudaStream_t st);
 int admm_block_size(int bin);
+cudaError_t fp64_peak(int num_sms, double *tflops);
 int admm_occupancy(int bin);
 cudaError_t launch_mpc_riccati(const MpcParams &P, int n, const double *in, const uint8_t *contact, double *forces,
                                double *xpred, b200qp_solver_info *info, double *lam_box, double *lam_g, double *scratch,
@@ -111,6 +112,17 @@ extern "C" {
 
 const char *b200qp_version(void) { return "b200qp 0.1 (sm_100a)"; }
 const char *b200qp_last_error(void) { return g_err.c_str(); }
+int32_t b200qp_fp64_peak_tflops(int32_t device, double *tflops) {
+  if (!tflops) return B200QP_ERR_ARG;
+  int ndev = 0;
+  CK(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) return B200QP_ERR_CUDA;
+  CK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  CK(fp64_peak(prop.multiProcessorCount, tflops));
+  return B200QP_OK;
+}
 int32_t b200qp_device_count(void) {
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;

@@ -59,3 +59,44 @@ cudaError_t launch_gait_schedule(int n, int steps, double dt, const double *peri
 }
 
 }  // namespace b200qp
+
+// ---- FP64 FMA peak microbenchmark (roofline denominator for the on-chip solve kernels; MEASURED_PEAKS.json has no
+// FP64 entry).  8 independent DFMA chains per thread, 1024 threads per block, 8 blocks per SM.
+namespace b200qp {
+__global__ void fp64_peak_kernel(double *out, int iters, double seed) {
+  double a0 = seed, a1 = seed + 1, a2 = seed + 2, a3 = seed + 3, a4 = seed + 4, a5 = seed + 5, a6 = seed + 6, a7 = seed + 7;
+  const double m = 1.0000001, c = 1e-9;
+  for (int i = 0; i < iters; ++i) {
+    a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+    a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+}
+cudaError_t fp64_peak(int num_sms, double *tflops) {
+  const int blocks = num_sms * 2, threads = 1024, iters = 20000;
+  double *d = nullptr;
+  cudaError_t e = cudaMalloc(&d, (size_t)blocks * threads * sizeof(double));
+  if (e != cudaSuccess) return e;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  fp64_peak_kernel<<<blocks, threads>>>(d, 100, 1.0);
+  double best = 0.0;
+  for (int rep = 0; rep < 3; ++rep) {
+    cudaEventRecord(e0);
+    fp64_peak_kernel<<<blocks, threads>>>(d, iters, 1.0);
+    cudaEventRecord(e1);
+    e = cudaEventSynchronize(e1);
+    if (e != cudaSuccess) break;
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    const double t = 2.0 * 8.0 * iters * (double)blocks * threads / (ms * 1e-3) / 1e12;
+    if (t > best) best = t;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(d);
+  *tflops = best;
+  return e;
+}
+}  // namespace b200qp

@@ -101,7 +101,7 @@ __device__ __forceinline__ int foot_nullspace(unsigned actl, unsigned actu, doub
 }
 
 // Least squares on <= 3 columns (normal equations, Gaussian elimination with partial pivoting).
-__device__ bool ls_small(const double (*M)[3], const int *idx, int k, const double (&b)[3], double *s) {
+__device__ __noinline__ bool ls_small(const double (*M)[3], const int *idx, int k, const double (&b)[3], double *s) {
   double G[3][4];
   for (int i = 0; i < k; ++i) {
     for (int j = 0; j < k; ++j)
@@ -131,7 +131,7 @@ __device__ bool ls_small(const double (*M)[3], const int *idx, int k, const doub
 }
 
 // Lawson-Hanson NNLS for min || M c - b ||, c >= 0, M = [3 x m] given as m columns.  Returns residual b - M c.
-__device__ void nnls3(const double (*M)[3], int m, const double (&b)[3], double *coef, double (&res)[3]) {
+__device__ __noinline__ void nnls3(const double (*M)[3], int m, const double (&b)[3], double *coef, double (&res)[3]) {
   bool P[14], excl[14];
   for (int j = 0; j < m; ++j) {
     coef[j] = 0.0;
@@ -219,7 +219,7 @@ __device__ void nnls3(const double (*M)[3], int m, const double (&b)[3], double 
 // pivot rows are produced column-wise (thread j writes A[P, j]) so that no thread runs a long divergent branch.
 // The last n mod 4 pivots use the scalar step.
 template <int LD>
-__device__ __forceinline__ void gj_invert(double *K, int n, double *prow4) {
+__device__ __noinline__ void gj_invert(double *K, int n, double *prow4) {
   const int i = threadIdx.x;
   double *Ki = K + i;
   int p0 = 0;

@@ -188,6 +188,9 @@ void *b200qp_wbc_stream(b200qp_wbc *h);
 const char *b200qp_version(void);
 int32_t b200qp_device_count(void);
 const char *b200qp_last_error(void);
+/* Measured dense FP64 FMA throughput of the device (TFLOP/s, DFMA microbenchmark): the roofline denominator of the
+ * on-chip solve kernels (MEASURED_PEAKS.json carries HBM and bf16 only). */
+int32_t b200qp_fp64_peak_tflops(int32_t device, double *tflops);
 
 #ifdef __cplusplus
 }
