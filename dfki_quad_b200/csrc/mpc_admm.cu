@@ -282,19 +282,23 @@ __device__ __noinline__ void gj_invert(double *K, int n, double *prow4) {
         const double w2 = c0 * E[0][2] + c1 * E[1][2] + c2 * E[2][2] + c3 * E[3][2];
         const double w3 = c0 * E[0][3] + c1 * E[1][3] + c2 * E[2][3] + c3 * E[3][3];
         int j = 0;
-        for (; j + 1 < n; j += 2) {
-          const double2 a0 = *reinterpret_cast<const double2 *>(prow4 + 4 * j);
-          const double2 b0 = *reinterpret_cast<const double2 *>(prow4 + 4 * j + 2);
-          const double2 a1 = *reinterpret_cast<const double2 *>(prow4 + 4 * j + 4);
-          const double2 b1 = *reinterpret_cast<const double2 *>(prow4 + 4 * j + 6);
-          const double k0 = Ki[j * LD], k1 = Ki[(j + 1) * LD];
-          Ki[j * LD] = k0 - (w0 * a0.x + w1 * a0.y + w2 * b0.x + w3 * b0.y);
-          Ki[(j + 1) * LD] = k1 - (w0 * a1.x + w1 * a1.y + w2 * b1.x + w3 * b1.y);
+        for (; j + 3 < n; j += 4) {  // 4 elements per trip: 8 broadcast LDS.128 + 4 LDS in flight, two half-sums per element
+          double2 pa[4], pb[4];
+          double kk[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            pa[u] = *reinterpret_cast<const double2 *>(prow4 + 4 * (j + u));
+            pb[u] = *reinterpret_cast<const double2 *>(prow4 + 4 * (j + u) + 2);
+            kk[u] = Ki[(j + u) * LD];
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u)  // four independent chains of four FMAs
+            Ki[(j + u) * LD] = fma(-w3, pb[u].y, fma(-w2, pb[u].x, fma(-w1, pa[u].y, fma(-w0, pa[u].x, kk[u]))));
         }
-        if (j < n) {
+        for (; j < n; ++j) {
           const double2 a0 = *reinterpret_cast<const double2 *>(prow4 + 4 * j);
           const double2 b0 = *reinterpret_cast<const double2 *>(prow4 + 4 * j + 2);
-          Ki[j * LD] -= (w0 * a0.x + w1 * a0.y + w2 * b0.x + w3 * b0.y);
+          Ki[j * LD] = fma(-w3, b0.y, fma(-w2, b0.x, fma(-w1, a0.y, fma(-w0, a0.x, Ki[j * LD]))));
         }
         Ki[p0 * LD] = -w0;
         Ki[(p0 + 1) * LD] = -w1;
@@ -342,20 +346,34 @@ __device__ __forceinline__ double matvec_smem(const double *K, int n, const doub
   return (a0 + a1) + (a2 + a3);
 }
 
-// y_i = sum_j Hs(i,j) v_j with Hs in global memory (column-major, leading dimension BS; coalesced over i)
+// y_i = sum_j Hs(i,j) v_j with Hs in global memory (column-major, leading dimension BS; coalesced over i).  The scratch is
+// L2-resident, so the loop is latency bound: 12 independent loads are issued before the first FMA.
 template <int BS>
 __device__ __forceinline__ double matvec_glob(const double *__restrict__ Hs, int n, const double *v) {
-  const int i = threadIdx.x;
+  const double *Hi = Hs + threadIdx.x;
   double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
   int j = 0;
+  for (; j + 11 < n; j += 12) {
+    double h[12];
+#pragma unroll
+    for (int u = 0; u < 12; ++u) h[u] = __ldcg(Hi + (size_t)(j + u) * BS);
+#pragma unroll
+    for (int u = 0; u < 12; u += 4) {
+      a0 = fma(h[u], v[j + u], a0);
+      a1 = fma(h[u + 1], v[j + u + 1], a1);
+      a2 = fma(h[u + 2], v[j + u + 2], a2);
+      a3 = fma(h[u + 3], v[j + u + 3], a3);
+    }
+  }
   for (; j + 3 < n; j += 4) {
-    const double h0 = Hs[j * BS + i], h1 = Hs[(j + 1) * BS + i], h2 = Hs[(j + 2) * BS + i], h3 = Hs[(j + 3) * BS + i];
+    const double h0 = __ldcg(Hi + (size_t)j * BS), h1 = __ldcg(Hi + (size_t)(j + 1) * BS), h2 = __ldcg(Hi + (size_t)(j + 2) * BS),
+                 h3 = __ldcg(Hi + (size_t)(j + 3) * BS);
     a0 = fma(h0, v[j], a0);
     a1 = fma(h1, v[j + 1], a1);
     a2 = fma(h2, v[j + 2], a2);
     a3 = fma(h3, v[j + 3], a3);
   }
-  for (; j < n; ++j) a0 = fma(Hs[j * BS + i], v[j], a0);
+  for (; j < n; ++j) a0 = fma(__ldcg(Hi + (size_t)j * BS), v[j], a0);
   return (a0 + a1) + (a2 + a3);
 }
 
@@ -670,12 +688,18 @@ __global__ void __launch_bounds__(BS) mpc_admm_kernel(const MpcParams P, const M
       while (!admm_done) {
         if (need_factor) {
           __syncthreads();
-          if (act)
-            for (int jx = 0; jx < n; ++jx) {
-              double h = Hs[jx * BS + tid];
-              if (jx == tid) h += sigma + rho * Ei;
-              K[jx * LD + tid] = h;
+          if (act) {
+            int jx = 0;
+            for (; jx + 7 < n; jx += 8) {
+              double h[8];
+#pragma unroll
+              for (int u = 0; u < 8; ++u) h[u] = __ldcg(Hs + (size_t)(jx + u) * BS + tid);
+#pragma unroll
+              for (int u = 0; u < 8; ++u) K[(jx + u) * LD + tid] = h[u];
             }
+            for (; jx < n; ++jx) K[jx * LD + tid] = __ldcg(Hs + (size_t)jx * BS + tid);
+            K[tid * LD + tid] += sigma + rho * Ei;
+          }
           __syncthreads();
           gj_invert<LD>(K, n, prow);
           need_factor = false;
@@ -803,16 +827,27 @@ __global__ void __launch_bounds__(BS) mpc_admm_kernel(const MpcParams P, const M
           vp[0] = s_fZ[9 * ap + 3 * kq];
           vp[1] = s_fZ[9 * ap + 3 * kq + 1];
           vp[2] = s_fZ[9 * ap + 3 * kq + 2];
-          for (int q = 0; q < nr; ++q) {
-            const int bq = s_rfoot[q];
-            const double *vq = s_fZ + 9 * bq + 3 * s_rk[q];
-            double acc = 0.0;
+          // u_c = sum_r vp[r] H(3 ap + r, c) for every column c is shared by the reduced columns of one foot: walk the feet,
+          // 9 L2 loads per foot issued together, then up to 3 reduced entries
+          for (int bq = 0; bq < nf; ++bq) {
+            const int nzb = s_fnz[bq];
+            if (nzb == 0) continue;
+            double hh[9];
 #pragma unroll
             for (int c2 = 0; c2 < 3; ++c2) {
               const double *col = Hs + (size_t)(3 * bq + c2) * BS + 3 * ap;
-              acc += vq[c2] * (vp[0] * col[0] + vp[1] * col[1] + vp[2] * col[2]);
+              hh[3 * c2] = __ldcg(col);
+              hh[3 * c2 + 1] = __ldcg(col + 1);
+              hh[3 * c2 + 2] = __ldcg(col + 2);
             }
-            K[q * LD + tid] = acc;
+            const double u0 = vp[0] * hh[0] + vp[1] * hh[1] + vp[2] * hh[2];
+            const double u1 = vp[0] * hh[3] + vp[1] * hh[4] + vp[2] * hh[5];
+            const double u2 = vp[0] * hh[6] + vp[1] * hh[7] + vp[2] * hh[8];
+            const int q0 = s_foff[bq];
+            for (int kq = 0; kq < nzb; ++kq) {
+              const double *vq = s_fZ + 9 * bq + 3 * kq;
+              K[(q0 + kq) * LD + tid] = vq[0] * u0 + vq[1] * u1 + vq[2] * u2;
+            }
           }
         }
         __syncthreads();
