@@ -29,6 +29,8 @@ WORKLOADS = {
                     seed=20261019 + 2, kernel="mpc_admm_kernel<64,64>"),
     "config3": dict(name="go2_mixed_sparse_mpc_h16_riccati", horizon=16, batch=16384, gaits=("TROT", "PACE", "BOUND"),
                     solver="SPARSE_RICCATI", seed=20261019 + 3, kernel="mpc_riccati_kernel<64>"),
+    "config5": dict(name="go2_1M_mixed_sweep_sharded", horizon=0, batch=1048576, gaits=(), solver="ADMM(N=10 trot) + RICCATI(N=16 mixed)",
+                    seed=20261019 + 5, kernel="mpc_admm_kernel<64,64> + mpc_riccati_kernel<64>"),
     "config4": dict(name="go2_wbc_reduced_tsid_qp", horizon=10, batch=16384, gaits=("TROT",), solver="WBC_DENSE_IPM",
                     seed=20261019 + 4, kernel="wbc_qp_kernel"),
 }
@@ -410,6 +412,102 @@ def run_b200_wbc(args):
         dist.destroy_process_group()
 
 
+def run_b200_sweep(args):
+    """BASELINE.json configs[4]: 1 048 576 problems = config-2 union config-3 distributions, cut into contiguous slices over
+    the GPUs (STRONG scaling: the total is fixed), no collective on the solve path.  Each rank generates one 32 768-problem
+    chunk per distribution and re-solves it for every chunk of its slice (input generation is host-side numpy and is not
+    part of the metric); timing = CUDA events around every chunk solve, summed, max over ranks."""
+    import torch
+
+    from dfki_quad_b200 import BatchedMPC, sequencer
+    from dfki_quad_b200.shard import shard_range
+
+    rank, local, world = dist_env()
+    if world > 1:
+        import torch.distributed as dist
+
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = local
+    torch.cuda.set_device(dev)
+    wl = WORKLOADS["config5"]
+    total = args.batch or wl["batch"]
+    lo, hi = shard_range(total, rank, world)
+    mine = hi - lo
+    chunk = 32768
+    cfg = sequencer.GO2_MPC
+    parts = []
+    for tag, N, gaits, solver, seed in (("admm", 10, ("TROT",), "CONDENSED_ADMM", wl["seed"]), ("riccati", 16, ("TROT", "PACE", "BOUND"), "SPARSE_RICCATI", wl["seed"] + 1)):
+        b = sequencer.random_batch(chunk, N, seed=seed + 1000 * rank, gaits=gaits, device=dev)
+        mpc = BatchedMPC(cfg["alpha"], cfg["state_weights_move"], cfg["mu"], cfg["fmin"], cfg["fmax"], solver, horizon=N, dt=cfg["dt"],
+                         max_batch=chunk, device=dev)
+        ext = torch.cuda.ExternalStream(mpc.stream(), device=dev)
+        with torch.cuda.stream(ext):
+            d = dict(inp=torch.from_numpy(b["rec"]).to(dev), ct=torch.from_numpy(b["contact"]).to(dev),
+                     f=torch.zeros((chunk, N, 12), dtype=torch.float64, device=dev), x=torch.zeros((chunk, N + 1, 13), dtype=torch.float64, device=dev),
+                     info=torch.zeros((chunk, 48), dtype=torch.uint8, device=dev))
+        ext.synchronize()
+        parts.append((tag, N, mpc, ext, d))
+    half = mine // 2
+    plan = [(parts[0], half), (parts[1], mine - half)]  # first half of the slice: config-2 problems, second half: config-3
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def one_pass(timed):
+        evs, conv = [], 0
+        for (tag, N, mpc, ext, d), count in plan:
+            done = 0
+            while done < count:
+                nb = min(chunk, count - done)
+                with torch.cuda.stream(ext):
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record(ext)
+                    mpc.solve_device(nb, d["inp"].data_ptr(), d["ct"].data_ptr(), d["f"].data_ptr(), d["x"].data_ptr(), d["info"].data_ptr(), sync=False)
+                    e1.record(ext)
+                evs.append((e0, e1))
+                if timed:
+                    ext.synchronize()
+                    info = np.frombuffer(d["info"][:nb].cpu().numpy().tobytes(), dtype=np.dtype(
+                        [("status", "i4"), ("iterations", "i4"), ("polish_rounds", "i4"), ("n_free", "i4"), ("kkt", "f8", (4,))]))
+                    conv += int(((info["status"] == 0) & (info["kkt"].max(axis=1) <= KKT_TOL)).sum())
+                done += nb
+        torch.cuda.synchronize(dev)
+        return float(sum(a.elapsed_time(b) for a, b in evs)), conv
+
+    for _ in range(max(1, args.warmup - 2)):
+        one_pass(False)
+    barrier()
+    tot_ms, conv = 0.0, 0
+    with ClockSampler(dev) as clocks:
+        barrier()
+        for _ in range(args.steps):
+            ms, c = one_pass(True)
+            tot_ms += ms
+            conv += c
+        barrier()
+    stats = torch.tensor([tot_ms], dtype=torch.float64, device=dev)
+    counts = torch.tensor([conv, mine * args.steps], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(stats, op=dist.ReduceOp.MAX)
+        dist.all_reduce(counts, op=dist.ReduceOp.SUM)
+    if rank == 0:
+        line = {"metric": "MPC QP solves/sec (Go2, 1M-problem mixed sweep: horizon 10 condensed ADMM + horizon 16 sparse Riccati)",
+                "value": counts[0].item() / (stats[0].item() * 1e-3), "unit": "solves/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": stats[0].item() / args.steps, "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": wl["name"], "total_problems": total, "chunk": chunk, "chunk_reuse": True, "solver": wl["solver"],
+                           "l2": "inputs of one chunk (75-115 MB) plus outputs exceed nothing; no flush (chunks stream back to back)",
+                           "converged_fraction": counts[0].item() / counts[1].item(), "parallelism": f"shard{world}"},
+                "gpu_launches": None, "clocks": clocks.summary()}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -428,6 +526,8 @@ def main():
         run_reference(args)
     elif args.workload == "config4":
         run_b200_wbc(args)
+    elif args.workload == "config5":
+        run_b200_sweep(args)
     else:
         run_b200(args)
 

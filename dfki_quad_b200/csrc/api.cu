@@ -74,6 +74,7 @@ struct b200qp_mpc {
   int last_n = 0;
   int last_launches = 0;
   bool want_duals = false;
+  bool have_timing = false;
   long long *d_dbg_cycles = nullptr;  // optional per-phase cycle accounting (B200QP_PHASE_CYCLES=1)
 };
 
@@ -290,6 +291,7 @@ static int32_t solve_device_impl(b200qp_mpc *h, int32_t n, const double *d_in, c
     ++launches;
   }
   CK(cudaEventRecord(h->ev1, h->stream));
+  h->have_timing = true;
   h->last_launches = launches;
   h->last_in = d_in;
   h->last_contact = d_contact;
@@ -449,6 +451,11 @@ int32_t b200qp_mpc_get_condensed(b200qp_mpc *h, int32_t index, double *H, int32_
 
 int32_t b200qp_mpc_last_timing(b200qp_mpc *h, float *kernel_ms, int32_t *kernel_launches) {
   if (!h) return B200QP_ERR_ARG;
+  if (!h->have_timing) {  // nothing has been launched on this handle yet
+    if (kernel_ms) *kernel_ms = 0.f;
+    if (kernel_launches) *kernel_launches = 0;
+    return B200QP_OK;
+  }
   CK(cudaSetDevice(h->cfg.device));
   CK(cudaEventSynchronize(h->ev1));
   float ms = 0.f;

@@ -348,3 +348,53 @@ def test_config3_full_batch_riccati(go2_params):
     F = forces.reshape(n, N, 4, 3)[info.success]
     assert np.all(F[batch["contact"][info.success] == 0] == 0.0)
     assert np.all(np.abs(F[..., 0]) <= 0.6 * F[..., 2] + 1e-6) and np.all(F[..., 2] >= -1e-6)
+
+
+# ---------------------------------------------------------------------------------------------------- edge cases
+def test_edge_cases_sizes_and_arguments(go2_params):
+    from dfki_quad_b200 import BatchedMPC, _lib, sequencer
+
+    cfg = sequencer.GO2_MPC
+    # empty batch is a no-op
+    mpc = _mpc(10, 4)
+    f, x, info = mpc.solve_records(np.zeros((0, 289)), np.zeros((0, 10, 4), dtype=np.uint8))
+    assert f.shape == (0, 10, 12) and len(info.success) == 0
+    # more problems than max_batch is an argument error, not a crash
+    b = sequencer.random_batch(6, 10, seed=1)
+    with pytest.raises(_lib.B200QPError):
+        mpc.solve_records(b["rec"], b["contact"])
+    # horizon limits: 1 and B200QP_MAX_HORIZON = 20 (the reference's compile-time value), both kernels
+    for N in (1, 20):
+        bb = sequencer.random_batch(5, N, seed=40 + N, gaits=("TROT", "STAND"))
+        for solver in ("CONDENSED_ADMM", "SPARSE_RICCATI"):
+            m = _mpc(N, 5, solver=solver)
+            ff, xx, ii = m.solve_records(bb["rec"], bb["contact"])
+            for p in range(5):
+                if solver == "CONDENSED_ADMM" and ii.n_free[p] > 156:
+                    assert ii.return_code[p] == 4
+                    continue
+                assert ii.return_code[p] == 0, (N, solver, p, ii.return_code[p])
+                U, X, qp, _ = mo.solve_reference_qp(N, bb["rec"][p], bb["contact"][p], go2_params)
+                assert np.abs(ff[p].reshape(N, 12) - U).max() <= 1e-5 * max(1.0, np.abs(U).max())
+    with pytest.raises(_lib.B200QPError):
+        BatchedMPC(cfg["alpha"], cfg["state_weights_move"], cfg["mu"], cfg["fmin"], cfg["fmax"], horizon=21, max_batch=4)
+
+
+def test_mixed_sizes_in_one_call_and_determinism(go2_params):
+    """One call with problems of all three size bins (and one too large for the condensed kernel); results do not
+    depend on the batch composition or on the run."""
+    from dfki_quad_b200 import sequencer
+
+    N, n = 12, 40
+    b = sequencer.random_batch(n, N, seed=8, gaits=("TROT", "STAND", "STATIC_WALK", "BOUND"))
+    mpc = _mpc(N, n)
+    f1, x1, i1 = mpc.solve_records(b["rec"], b["contact"])
+    f2, x2, i2 = mpc.solve_records(b["rec"], b["contact"])
+    assert np.array_equal(f1, f2) and np.array_equal(i1.return_code, i2.return_code)
+    assert set(np.unique(np.digitize(i1.n_free, [65, 129, 157]))) >= {0, 1, 2}
+    perm = np.random.default_rng(0).permutation(n)
+    f3, _, i3 = mpc.solve_records(b["rec"][perm], b["contact"][perm])
+    assert np.array_equal(f3, f1[perm])
+    ok = i1.return_code == 0
+    assert ok.sum() >= n - 12 and np.all(i1.return_code[~ok] == 4)
+    _check_against_oracle(N, b, f1, x1, i1, go2_params, np.nonzero(ok)[0][:8])

@@ -203,3 +203,30 @@ def test_tsid_scene_against_oracle():
         f = x2[18:].reshape(4, 3)
         assert np.abs(f[~b["contacts"][p]]).max() <= 1e-9
         assert np.abs(wbc.joint_torques({k: v[p:p + 1] for k, v in b["dyn"].items()}, x2[None])).max() <= gm.TAU_MAX.max() + 1e-6
+
+
+def test_cpp_header_compiles_and_links(tmp_path):
+    """include/b200qp_mpc.hpp (header-only C++ mirror of the MPC plugin) compiles with g++ -std=c++17 and links against
+    libb200qp.so; without a GPU construction throws with the library's error string (no CPU fallback)."""
+    import __graft_entry__ as ge
+
+    ge.build()
+    src = tmp_path / "t.cpp"
+    src.write_text(
+        '#include "b200qp_mpc.hpp"\n#include <cstdio>\n'
+        "int main() {\n"
+        "  std::array<double, 12> w{}; w.fill(1.0);\n"
+        "  try { b200qp::BatchedMPC mpc(1e-5, w, 0.6, 0.0, 400.0, B200QP_SOLVER_CONDENSED_ADMM, 10, 0.05, 2);\n"
+        "        std::printf(\"created\\n\"); }\n"
+        "  catch (const std::exception &e) { std::printf(\"error: %s\\n\", e.what()); return b200qp_device_count() > 0 ? 1 : 0; }\n"
+        "  return 0; }\n")
+    libdir = os.path.join(ROOT, "dfki_quad_b200")
+    exe = tmp_path / "t"
+    gxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    r = subprocess.run([gxx, "-std=c++17", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe), "-L", libdir, "-lb200qp",
+                        "-L/usr/local/cuda/lib64", "-lcudart", f"-Wl,-rpath,{libdir}", "-Wl,-rpath,/usr/local/cuda/lib64"],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "created" in out.stdout or "no CPU fallback" in out.stdout or "error" in out.stdout
