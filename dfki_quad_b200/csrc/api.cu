@@ -20,7 +20,7 @@ cudaError_t fp64_peak(int num_sms, double *tflops);
 int admm_occupancy(int bin);
 cudaError_t launch_mpc_riccati(const MpcParams &P, int n, const double *in, const uint8_t *contact, double *forces,
                                double *xpred, b200qp_solver_info *info, double *lam_box, double *lam_g, double *scratch,
-                               int *next, int grid, cudaStream_t st);
+                               int *next, int grid, cudaStream_t st, long long *dbg_cycles);
 int riccati_grid(int num_sms, int horizon);
 struct WbcParams {
   int nq, neq, nin;
@@ -287,7 +287,7 @@ static int32_t solve_device_impl(b200qp_mpc *h, int32_t n, const double *d_in, c
     CK(cudaMemsetAsync(h->d_bin_count, 0, 8 * sizeof(int), h->stream));
     CK(launch_mpc_riccati(h->P, n, d_in, d_contact, d_forces, d_xpred, d_info,
                           h->want_duals ? h->d_lam_box : nullptr, h->want_duals ? h->d_lam_g : nullptr,
-                          h->d_ric_scratch, h->d_bin_count + 7, h->ric_grid, h->stream));
+                          h->d_ric_scratch, h->d_bin_count + 7, h->ric_grid, h->stream, h->d_dbg_cycles));
     ++launches;
   }
   CK(cudaEventRecord(h->ev1, h->stream));

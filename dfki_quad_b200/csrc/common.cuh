@@ -103,6 +103,15 @@ __device__ __forceinline__ void block_max(double (&v)[V], double *red) {
   }
 }
 
+// 1/sqrt(x) for x > 0: FP32 seed + two Newton steps in FP64 (relative error ~1e-15); ~10 instructions instead of the
+// library rsqrt()/sqrt()+division sequences, which sit on the serial critical path of the small Cholesky factorisations.
+__device__ __forceinline__ double fast_rsqrt(double x) {
+  double r = (double)rsqrtf((float)x);
+  r = r * fma(-0.5 * x, r * r, 1.5);
+  r = r * fma(-0.5 * x, r * r, 1.5);
+  return r;
+}
+
 // NaN-propagating abs-max helper: fmax drops NaNs, so NaN detection is done separately.
 __device__ __forceinline__ double absmax(double a, double b) { return fmax(fabs(a), fabs(b)); }
 

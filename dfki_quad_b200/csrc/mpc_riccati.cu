@@ -56,30 +56,34 @@ __device__ __forceinline__ void GT_apply(const double (&v)[10], double mu, doubl
 }
 }  // namespace
 
-template <int BS>
-__global__ void __launch_bounds__(BS) mpc_riccati_kernel(const MpcParams P, int nprob, const double *__restrict__ in,
+// NH = horizon capacity of the instantiation (shared-memory stage arrays are sized by it), MINB = resident blocks per SM
+// the register allocation is tuned for: the kernel is a chain of dependent FP64 instructions, so resident warps are what
+// hides its latency.
+template <int BS, int NH, int MINB>
+__global__ void __launch_bounds__(BS, MINB) mpc_riccati_kernel(const MpcParams P, int nprob, const double *__restrict__ in,
                                                          const uint8_t *__restrict__ contact, double *__restrict__ forces,
                                                          double *__restrict__ xpred, b200qp_solver_info *__restrict__ info,
                                                          double *__restrict__ lam_box, double *__restrict__ lam_g,
-                                                         double *__restrict__ scratch, int *next) {
+                                                         double *__restrict__ scratch, int *next, long long *dbg_cycles) {
   constexpr int NS = 12;  // controllable state dimension (the 13th state is the constant g, mpc.cpp:396)
   __shared__ double sP[144], sPn[144], sT[144], sPB[144], sHuu[144], sHux[144];
   __shared__ double sKbuf[288], sLi[144];
-  __shared__ double sBw[MAXH * 36];
-  __shared__ double sU[MAXH * 12], sDU[MAXH * 12], sRt12[MAXH * 12], sKK[MAXH * 12], sUb[MAXH * 12];
-  __shared__ double sX[(MAXH + 1) * 12], sXref[(MAXH + 1) * 12], sQe[(MAXH + 1) * 12];
-  __shared__ double sLw[(MAXH + 2) * 3], sLv[(MAXH + 2) * 3];
-  __shared__ double sRb[MAXH * 4 * 6];  // R~ blocks per foot: xx yy zz xz yz (xy = 0) + pad
-  __shared__ double sBwsum[MAXH * 6];
-  __shared__ double sYaw[MAXH + 1], sX0[13], sRot[9], sVec[64], red[4 * 8];
-  __shared__ unsigned char sOn[MAXH * 4], sAct[MAXH * 12];
-  __shared__ int sNu[MAXH];
+  __shared__ double sBw[NH * 36];
+  __shared__ double sU[NH * 12], sDU[NH * 12], sRt12[NH * 12], sKK[NH * 12], sUb[NH * 12];
+  __shared__ double sX[(NH + 1) * 12], sXref[(NH + 1) * 12], sQe[(NH + 1) * 12];
+  __shared__ double sLw[(NH + 2) * 3], sLv[(NH + 2) * 3];
+  __shared__ double sRb[NH * 4 * 6];  // R~ blocks per foot: xx yy zz xz yz (xy = 0) + pad
+  __shared__ double sBwsum[NH * 6];
+  __shared__ double sYaw[NH + 1], sX0[13], sRot[9], sVec[64], red[4 * 8];
+  __shared__ unsigned char sOn[NH * 4], sAct[NH * 12];
+  __shared__ int sNu[NH];
   __shared__ int sSlot;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int N = P.N;
   const double dt = P.dt, mu_f = P.mu;
   double *Ks = scratch + (size_t)blockIdx.x * MAXH * 288;
+  static_assert(4 * NH <= BS, "one thread per (stage, foot)");
 
   for (;;) {
     __syncthreads();
@@ -90,6 +94,10 @@ __global__ void __launch_bounds__(BS) mpc_riccati_kernel(const MpcParams P, int 
     const double *rec = in + (size_t)prob * P.in_stride;
     const uint8_t *ct = contact + (size_t)prob * N * 4;
     const double mass = rec[13], dm = dt / mass;
+    const bool timing = dbg_cycles != nullptr;
+    long long cyc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    long long tlast = timing ? clock64() : 0;
+#define RPH(idx) do { if (timing && tid == 0) { const long long t__ = clock64(); cyc[idx] += t__ - tlast; tlast = t__; } } while (0)
 
     // ---- setup (same data as mpc.cpp:332-398) ---------------------------------------------------------------------
     if (tid <= N) {
@@ -220,6 +228,7 @@ __global__ void __launch_bounds__(BS) mpc_riccati_kernel(const MpcParams P, int 
     int stall = 0;
     bool final_pass = false;
 
+    RPH(0);
     for (iter = 0; iter <= P.ipm_max_iter + 1; ++iter) {
       // (A) roll-out x(u) and exact adjoint -----------------------------------------------------------------------
       if (tid < N) {
@@ -287,6 +296,7 @@ __global__ void __launch_bounds__(BS) mpc_riccati_kernel(const MpcParams P, int 
       }
       __syncthreads();
 
+      RPH(1);
       // (B) residuals ------------------------------------------------------------------------------------------------
       double rd[3] = {0, 0, 0}, rp[10], Gu[10];
       double rs[3] = {0.0, 0.0, 0.0};  // max |rd|,|rp| ; max s*z ; max violation
@@ -356,6 +366,7 @@ __global__ void __launch_bounds__(BS) mpc_riccati_kernel(const MpcParams P, int 
       }
       const double mu_c = gap[0] / mtot;
 
+      RPH(2);
       // (C) R~ blocks ---------------------------------------------------------------------------------------------------
       if (tid < 4 * N) {
         double *Rb = sRb + 6 * tid;
@@ -418,34 +429,56 @@ __global__ void __launch_bounds__(BS) mpc_riccati_kernel(const MpcParams P, int 
           sHux[e] = x;
         }
         __syncthreads();
+        RPH(3);
         if (warp == 0) {  // Cholesky Huu = L L' and L^-1 inside one warp (explicit Huu^-1 loses the IPM endgame accuracy)
           const double od = (lane < nu) ? sHuu[13 * lane] : 1.0;  // original diagonal, for the round-off pivot floor
+          // Everything in this branch is one serial dependency chain (the other warp waits at the barrier), so the
+          // instruction count per pivot is what matters: the (row, column) of the trailing-update entries a lane owns
+          // is computed once per stage instead of with an integer division per pivot, and there is one rsqrt per pivot.
+          int ei[5], ej[5];
+          const float rnu = 1.0f / (float)(nu > 0 ? nu : 1);
+#pragma unroll
+          for (int m = 0; m < 5; ++m) {
+            const int e = lane + 32 * m;
+            int qi = (int)((float)e * rnu);
+            if (qi * nu > e) --qi;
+            if ((qi + 1) * nu <= e) ++qi;
+            ei[m] = (e < nu * nu) ? qi : -1;
+            ej[m] = e - qi * nu;
+          }
+          const int nm = (nu * nu + 31) >> 5;
           for (int p = 0; p < nu; ++p) {
             const double flo = 1e-13 * __shfl_sync(0xffffffffu, od, p);
-            const double piv = sHuu[13 * p];
-            const double d = sqrt((piv > flo) ? piv : flo);
+            const double piv0 = sHuu[13 * p];
+            const double piv = (piv0 > flo) ? piv0 : flo;
+            const double rd = fast_rsqrt(piv);
             __syncwarp();
             if (lane < nu) {
-              if (lane == p) sHuu[13 * p] = d;
-              else if (lane > p) sHuu[12 * lane + p] /= d;
+              if (lane == p) {
+                sHuu[13 * p] = piv * rd;
+                sVec[48 + p] = rd;  // 1 / L[p][p]
+              } else if (lane > p) {
+                sHuu[12 * lane + p] *= rd;
+              }
             }
             __syncwarp();
-            const int rem = nu - p - 1;
-            for (int e = lane; e < rem * rem; e += 32) {
-              const int i = p + 1 + e / rem, j = p + 1 + e % rem;
-              if (j <= i) sHuu[12 * i + j] -= sHuu[12 * i + p] * sHuu[12 * j + p];
-            }
+#pragma unroll
+            for (int m = 0; m < 5; ++m)
+              if (m < nm && ei[m] > p && ej[m] > p && ej[m] <= ei[m])
+                sHuu[12 * ei[m] + ej[m]] -= sHuu[12 * ei[m] + p] * sHuu[12 * ej[m] + p];
             __syncwarp();
           }
+          RPH(8);
           if (lane < nu) {  // column `lane` of X = L^-1 by forward substitution
             const int j = lane;
             for (int i = 0; i < j; ++i) sLi[12 * i + j] = 0.0;
             for (int i = j; i < nu; ++i) {
               double acc = (i == j) ? 1.0 : 0.0;
               for (int kk2 = j; kk2 < i; ++kk2) acc -= sHuu[12 * i + kk2] * sLi[12 * kk2 + j];
-              sLi[12 * i + j] = acc / sHuu[13 * i];
+              sLi[12 * i + j] = acc * sVec[48 + i];
             }
           }
+          RPH(9);
         } else {  // Pn = Q + A' T
           for (int e = tid - 32; e < 144; e += BS - 32) {
             const int i = e / 12, j = e - 12 * i;
@@ -457,6 +490,7 @@ __global__ void __launch_bounds__(BS) mpc_riccati_kernel(const MpcParams P, int 
           }
         }
         __syncthreads();
+        RPH(4);
         for (int e = tid; e < 12 * nu; e += BS) {  // Y = L^-1 Hux   (nu x 12)
           const int j = e / 12, col = e - 12 * j;
           double acc = 0.0;
@@ -480,6 +514,7 @@ __global__ void __launch_bounds__(BS) mpc_riccati_kernel(const MpcParams P, int 
         double *tmp = Pc;
         Pc = Pnx;
         Pnx = tmp;
+        RPH(5);
       }
 
       // (E)/(F) predictor and corrector ---------------------------------------------------------------------------------
@@ -502,6 +537,7 @@ __global__ void __launch_bounds__(BS) mpc_riccati_kernel(const MpcParams P, int 
           sRt12[3 * tid] = rt[0]; sRt12[3 * tid + 1] = rt[1]; sRt12[3 * tid + 2] = rt[2];
         }
         __syncthreads();
+        RPH(6);
         if (warp == 0) {
           // vector backward sweep: lanes 0..11 hold p; compact input quantities live in lanes < nu
           double pv = 0.0;  // p[lane]
@@ -586,6 +622,7 @@ __global__ void __launch_bounds__(BS) mpc_riccati_kernel(const MpcParams P, int 
           }
         }
         __syncthreads();
+        RPH(7);
         // step in (s, z)
         double st[1] = {1.0};
         double dsn[10], dzn[10];
@@ -634,6 +671,9 @@ __global__ void __launch_bounds__(BS) mpc_riccati_kernel(const MpcParams P, int 
       }
     }
 
+    RPH(8);
+    if (timing && tid == 0)
+      for (int q = 0; q < 10; ++q) dbg_cycles[(size_t)prob * 10 + q] = cyc[q];
     // ---- outputs ------------------------------------------------------------------------------------------------------
     __syncthreads();
     if (status == B200QP_ACADOS_SUCCESS) {
@@ -676,25 +716,31 @@ __global__ void __launch_bounds__(BS) mpc_riccati_kernel(const MpcParams P, int 
   (void)NS;
 }
 
-int riccati_grid(int num_sms, int horizon) {
+template <int BS, int NH, int MINB>
+static int ric_occ() {
   int occ = 0;
-  const cudaError_t e = (4 * horizon <= 64) ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, mpc_riccati_kernel<64>, 64, 0)
-                                            : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, mpc_riccati_kernel<96>, 96, 0);
-  if (e != cudaSuccess) {
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, mpc_riccati_kernel<BS, NH, MINB>, BS, 0) != cudaSuccess) {
     cudaGetLastError();
     occ = 1;
   }
-  return num_sms * (occ < 1 ? 1 : occ);
+  return occ < 1 ? 1 : occ;
+}
+
+int riccati_grid(int num_sms, int horizon) {
+  const int occ = horizon <= 10 ? ric_occ<64, 10, 8>() : horizon <= 16 ? ric_occ<64, 16, 6>() : ric_occ<96, 20, 3>();
+  return num_sms * occ;
 }
 
 cudaError_t launch_mpc_riccati(const MpcParams &P, int n, const double *in, const uint8_t *contact, double *forces,
                                double *xpred, b200qp_solver_info *info, double *lam_box, double *lam_g, double *scratch,
-                               int *next, int grid, cudaStream_t st) {
+                               int *next, int grid, cudaStream_t st, long long *dbg_cycles) {
   if (grid > n) grid = n;
-  if (4 * P.N <= 64)
-    mpc_riccati_kernel<64><<<grid, 64, 0, st>>>(P, n, in, contact, forces, xpred, info, lam_box, lam_g, scratch, next);
+  if (P.N <= 10)
+    mpc_riccati_kernel<64, 10, 8><<<grid, 64, 0, st>>>(P, n, in, contact, forces, xpred, info, lam_box, lam_g, scratch, next, dbg_cycles);
+  else if (P.N <= 16)
+    mpc_riccati_kernel<64, 16, 6><<<grid, 64, 0, st>>>(P, n, in, contact, forces, xpred, info, lam_box, lam_g, scratch, next, dbg_cycles);
   else
-    mpc_riccati_kernel<96><<<grid, 96, 0, st>>>(P, n, in, contact, forces, xpred, info, lam_box, lam_g, scratch, next);
+    mpc_riccati_kernel<96, 20, 3><<<grid, 96, 0, st>>>(P, n, in, contact, forces, xpred, info, lam_box, lam_g, scratch, next, dbg_cycles);
   return cudaGetLastError();
 }
 

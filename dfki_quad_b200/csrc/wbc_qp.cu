@@ -45,10 +45,12 @@ __device__ void chol_and_inverse(double *A, double *Li, int n, double *diag0) {
   __syncthreads();
   for (int p = 0; p < n; ++p) {
     const double flo = 1e-13 * diag0[p];
-    const double piv = A[p * n + p];
-    const double d = sqrt(piv > flo ? piv : flo);
+    const double piv0 = A[p * n + p];
+    const double piv = piv0 > flo ? piv0 : flo;
+    const double rd = fast_rsqrt(piv);  // reciprocal square root once per pivot: no FP64 divisions in the column scaling / L^-1
     __syncthreads();
-    for (int i = p + tid; i < n; i += BS) A[i * n + p] = (i == p) ? d : A[i * n + p] / d;
+    for (int i = p + tid; i < n; i += BS) A[i * n + p] = (i == p) ? piv * rd : A[i * n + p] * rd;
+    if (tid == 0) diag0[p] = rd;  // from here on diag0[p] = 1 / L[p][p]
     __syncthreads();
     const int rem = n - p - 1;
     for (int e = tid; e < rem * rem; e += BS) {
@@ -63,7 +65,7 @@ __device__ void chol_and_inverse(double *A, double *Li, int n, double *diag0) {
     for (int i = j; i < n; ++i) {
       double acc = (i == j) ? 1.0 : 0.0;
       for (int k = j; k < i; ++k) acc -= A[i * n + k] * Li[k * n + j];
-      Li[i * n + j] = acc / A[i * n + i];
+      Li[i * n + j] = acc * diag0[i];
     }
   }
   __syncthreads();
