@@ -40,11 +40,17 @@ class WbcConfig(C.Structure):
                 ("max_iter", C.c_int32), ("kkt_tol", C.c_double)]
 
 
+class SeqModel(C.Structure):
+    _fields_ = [("mass", C.c_double), ("inertia", C.c_double * 9), ("com", C.c_double * 3), ("shoulders", C.c_double * 12),
+                ("raibert_k", C.c_double), ("raibert_g", C.c_double), ("max_leg_length", C.c_double)]
+
+
 EXPORTS = [
     "b200qp_version", "b200qp_device_count", "b200qp_last_error", "b200qp_fp64_peak_tflops", "b200qp_mpc_create", "b200qp_mpc_destroy",
     "b200qp_mpc_set_state_weights", "b200qp_mpc_set_input_weights", "b200qp_mpc_set_fmax", "b200qp_mpc_set_mu",
     "b200qp_mpc_solve_batch", "b200qp_mpc_solve_batch_device", "b200qp_mpc_get_duals", "b200qp_mpc_get_condensed",
-    "b200qp_mpc_last_timing", "b200qp_mpc_stream", "b200qp_gait_schedule", "b200qp_gait_schedule_device",
+    "b200qp_mpc_last_timing", "b200qp_mpc_stream", "b200qp_mpc_set_model", "b200qp_mpc_sequence_batch",
+    "b200qp_mpc_sequence_solve_batch", "b200qp_mpc_sequence_solve_batch_device", "b200qp_gait_schedule", "b200qp_gait_schedule_device",
     "b200qp_wbc_create", "b200qp_wbc_destroy", "b200qp_wbc_solve_batch", "b200qp_wbc_solve_batch_device", "b200qp_wbc_stream",
 ]
 
@@ -79,6 +85,10 @@ def load() -> C.CDLL:
     lib.b200qp_mpc_get_condensed.argtypes = [vp, i32, vp, i32, vp]
     lib.b200qp_mpc_last_timing.argtypes = [vp, p(C.c_float), p(i32)]
     lib.b200qp_mpc_stream.argtypes = [vp]
+    lib.b200qp_mpc_set_model.argtypes = [vp, p(SeqModel)]
+    lib.b200qp_mpc_sequence_batch.argtypes = [vp, i32, vp, vp, vp, vp]
+    lib.b200qp_mpc_sequence_solve_batch.argtypes = [vp, i32, vp, vp, vp, vp, vp]
+    lib.b200qp_mpc_sequence_solve_batch_device.argtypes = [vp, i32, vp, vp, vp, vp, vp, i32]
     lib.b200qp_mpc_stream.restype = vp
     lib.b200qp_gait_schedule.argtypes = [i32, i32, i32, dbl, vp, vp, vp, vp, vp, dbl, dbl, vp, vp, vp, vp]
     lib.b200qp_gait_schedule_device.argtypes = [i32, i32, dbl, vp, vp, vp, vp, vp, dbl, dbl, vp, vp, vp, vp, vp]

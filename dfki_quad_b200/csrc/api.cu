@@ -22,6 +22,12 @@ cudaError_t launch_mpc_riccati(const MpcParams &P, int n, const double *in, cons
                                double *xpred, b200qp_solver_info *info, double *lam_box, double *lam_g, double *scratch,
                                int *next, int grid, cudaStream_t st, long long *dbg_cycles);
 int riccati_grid(int num_sms, int horizon);
+struct SeqModel {
+  double mass, inertia[9], com[3], shoulders[12], raibert_k, raibert_g, max_leg_length, dt;
+  int N;
+};
+cudaError_t launch_sequencer(int n, const SeqModel &M, const double *seq_in, const uint8_t *measured, double *rec_out,
+                             uint8_t *contact_out, int in_stride, cudaStream_t st);
 struct WbcParams {
   int nq, neq, nin;
   double kkt_tol;
@@ -76,6 +82,12 @@ struct b200qp_mpc {
   bool want_duals = false;
   bool have_timing = false;
   long long *d_dbg_cycles = nullptr;  // optional per-phase cycle accounting (B200QP_PHASE_CYCLES=1)
+  // on-device gait sequencer (b200qp_mpc_sequence_*)
+  SeqModel model;
+  bool have_model = false;
+  bool no_zero_copy = false;  // B200QP_NO_ZERO_COPY=1: always stage outputs through device buffers + DMA
+  double *d_seq = nullptr, *h_seq = nullptr;
+  uint8_t *d_measured = nullptr;
 };
 
 static bool is_pinned(const void *p) {
@@ -188,6 +200,7 @@ int32_t b200qp_mpc_create(const b200qp_mpc_config *cfg, b200qp_mpc **out) {
     h->ric_grid = g;
     CK(cudaMalloc(&h->d_ric_scratch, (size_t)g * B200QP_MAX_HORIZON * 288 * sizeof(double)));
   }
+  h->no_zero_copy = getenv("B200QP_NO_ZERO_COPY") != nullptr;
   if (getenv("B200QP_PHASE_CYCLES")) {
     CK(cudaMalloc(&h->d_dbg_cycles, nb * 10 * sizeof(long long)));
     CK(cudaMemset(h->d_dbg_cycles, 0, nb * 10 * sizeof(long long)));
@@ -197,6 +210,9 @@ int32_t b200qp_mpc_create(const b200qp_mpc_config *cfg, b200qp_mpc **out) {
   CK(cudaMallocHost(&h->h_forces, nb * N * 12 * sizeof(double)));
   CK(cudaMallocHost(&h->h_xpred, nb * (N + 1) * 13 * sizeof(double)));
   CK(cudaMallocHost(&h->h_info, nb * sizeof(b200qp_solver_info)));
+  CK(cudaMalloc(&h->d_seq, nb * B200QP_SEQ_IN_DOUBLES * sizeof(double)));
+  CK(cudaMalloc(&h->d_measured, nb * 4));
+  CK(cudaMallocHost(&h->h_seq, nb * B200QP_SEQ_IN_DOUBLES * sizeof(double) + nb * 4));
   *out = h;
   return B200QP_OK;
 }
@@ -220,6 +236,9 @@ void b200qp_mpc_destroy(b200qp_mpc *h) {
   cudaFreeHost(h->h_forces);
   cudaFreeHost(h->h_xpred);
   cudaFreeHost(h->h_info);
+  cudaFree(h->d_seq);
+  cudaFree(h->d_measured);
+  cudaFreeHost(h->h_seq);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -313,32 +332,10 @@ int32_t b200qp_mpc_solve_batch_device(b200qp_mpc *h, int32_t n, const double *d_
   return B200QP_OK;
 }
 
-int32_t b200qp_mpc_solve_batch(b200qp_mpc *h, int32_t n, const double *in, const uint8_t *contact, double *forces,
-                               double *xpred, b200qp_solver_info *info) {
-  if (!h || n < 0 || n > h->cfg.max_batch || (n > 0 && (!in || !contact || !forces || !xpred || !info))) {
-    g_err = "b200qp_mpc_solve_batch: bad arguments";
-    return B200QP_ERR_ARG;
-  }
-  if (n == 0) return B200QP_OK;
-  CK(cudaSetDevice(h->cfg.device));
+// Device results -> caller buffers through DMA copies (pageable or unmappable caller buffers).
+static int32_t fetch_outputs(b200qp_mpc *h, int32_t n, double *forces, double *xpred, b200qp_solver_info *info) {
   const int N = h->cfg.horizon;
-  const size_t in_b = (size_t)n * b200qp_mpc_in_doubles(N) * sizeof(double);
   const size_t f_b = (size_t)n * N * 12 * sizeof(double), x_b = (size_t)n * (N + 1) * 13 * sizeof(double);
-  // Inputs: DMA straight from the caller's buffers when they are page-locked (cudaHostAlloc / cudaHostRegister /
-  // torch pin_memory), else stage through the handle's pinned buffers.
-  const bool in_pinned = is_pinned(in) && is_pinned(contact);
-  const double *src_in = in;
-  const uint8_t *src_ct = contact;
-  if (!in_pinned) {
-    memcpy(h->h_in, in, in_b);
-    memcpy(h->h_contact, contact, (size_t)n * N * 4);
-    src_in = h->h_in;
-    src_ct = h->h_contact;
-  }
-  CK(cudaMemcpyAsync(h->d_in, src_in, in_b, cudaMemcpyHostToDevice, h->stream));
-  CK(cudaMemcpyAsync(h->d_contact, src_ct, (size_t)n * N * 4, cudaMemcpyHostToDevice, h->stream));
-  int32_t rc = solve_device_impl(h, n, h->d_in, h->d_contact, h->d_forces, h->d_xpred, h->d_info, -1, nullptr, nullptr);
-  if (rc != B200QP_OK) return rc;
   // The per-problem status comes back first: failed problems must leave the caller's output slots untouched
   // (mpc.cpp:447-455), so the outputs can only be written in place when every problem succeeded.
   CK(cudaMemcpyAsync(h->h_info, h->d_info, (size_t)n * sizeof(b200qp_solver_info), cudaMemcpyDeviceToHost, h->stream));
@@ -373,6 +370,154 @@ int32_t b200qp_mpc_solve_batch(b200qp_mpc *h, int32_t n, const double *in, const
     }
   }
   memcpy(info, h->h_info, (size_t)n * sizeof(b200qp_solver_info));
+  return B200QP_OK;
+}
+
+// Solve the records resident in h->d_in / h->d_contact and deliver the results to HOST buffers.  Page-locked caller
+// buffers are mapped into the device address space and written by the kernels themselves as each problem finishes
+// (posted PCIe writes overlap the remaining solves; a failed problem's slots are never touched by the kernels, which
+// is the reference's failure semantics, mpc.cpp:447-455), so the call ends with one stream synchronisation and no
+// device->host copy.  Pageable buffers go through the handle's pinned staging copies.
+static int32_t solve_and_fetch(b200qp_mpc *h, int32_t n, double *forces, double *xpred, b200qp_solver_info *info) {
+  void *mf = nullptr, *mx = nullptr, *mi = nullptr;
+  const bool direct = !h->no_zero_copy && is_pinned(forces) && is_pinned(xpred) &&
+                      cudaHostGetDevicePointer(&mf, forces, 0) == cudaSuccess &&
+                      cudaHostGetDevicePointer(&mx, xpred, 0) == cudaSuccess &&
+                      cudaHostGetDevicePointer(&mi, h->h_info, 0) == cudaSuccess;
+  if (!direct) {
+    cudaGetLastError();
+    int32_t rc = solve_device_impl(h, n, h->d_in, h->d_contact, h->d_forces, h->d_xpred, h->d_info, -1, nullptr, nullptr);
+    if (rc != B200QP_OK) return rc;
+    return fetch_outputs(h, n, forces, xpred, info);
+  }
+  int32_t rc = solve_device_impl(h, n, h->d_in, h->d_contact, static_cast<double *>(mf), static_cast<double *>(mx),
+                                 static_cast<b200qp_solver_info *>(mi), -1, nullptr, nullptr);
+  if (rc != B200QP_OK) return rc;
+  CK(cudaStreamSynchronize(h->stream));
+  memcpy(info, h->h_info, (size_t)n * sizeof(b200qp_solver_info));
+  return B200QP_OK;
+}
+
+int32_t b200qp_mpc_solve_batch(b200qp_mpc *h, int32_t n, const double *in, const uint8_t *contact, double *forces,
+                               double *xpred, b200qp_solver_info *info) {
+  if (!h || n < 0 || n > h->cfg.max_batch || (n > 0 && (!in || !contact || !forces || !xpred || !info))) {
+    g_err = "b200qp_mpc_solve_batch: bad arguments";
+    return B200QP_ERR_ARG;
+  }
+  if (n == 0) return B200QP_OK;
+  CK(cudaSetDevice(h->cfg.device));
+  const int N = h->cfg.horizon;
+  const size_t in_b = (size_t)n * b200qp_mpc_in_doubles(N) * sizeof(double);
+  // Inputs: DMA straight from the caller's buffers when they are page-locked (cudaHostAlloc / cudaHostRegister /
+  // torch pin_memory), else stage through the handle's pinned buffers.
+  const bool in_pinned = is_pinned(in) && is_pinned(contact);
+  const double *src_in = in;
+  const uint8_t *src_ct = contact;
+  if (!in_pinned) {
+    memcpy(h->h_in, in, in_b);
+    memcpy(h->h_contact, contact, (size_t)n * N * 4);
+    src_in = h->h_in;
+    src_ct = h->h_contact;
+  }
+  CK(cudaMemcpyAsync(h->d_in, src_in, in_b, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->d_contact, src_ct, (size_t)n * N * 4, cudaMemcpyHostToDevice, h->stream));
+  return solve_and_fetch(h, n, forces, xpred, info);
+}
+
+int32_t b200qp_mpc_set_model(b200qp_mpc *h, const b200qp_seq_model *m) {
+  if (!h || !m || !(m->mass > 0) || !(m->raibert_g > 0) || !(m->max_leg_length > 0)) return B200QP_ERR_ARG;
+  SeqModel &M = h->model;
+  M.mass = m->mass;
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c) M.inertia[c * 3 + r] = m->inertia[r * 3 + c];  // record layout is column-major
+  for (int c = 0; c < 3; ++c) M.com[c] = m->com[c];
+  for (int c = 0; c < 12; ++c) M.shoulders[c] = m->shoulders[c];
+  M.raibert_k = m->raibert_k;
+  M.raibert_g = m->raibert_g;
+  M.max_leg_length = m->max_leg_length;
+  h->have_model = true;
+  return B200QP_OK;
+}
+
+// seq_in (+ optional measured contacts) host -> device, then the sequencer kernel into the handle's record buffers.
+static int32_t sequence_impl(b200qp_mpc *h, int32_t n, const double *seq_in, const uint8_t *measured, bool on_device) {
+  if (!h->have_model) {
+    g_err = "b200qp_mpc_sequence: call b200qp_mpc_set_model first";
+    return B200QP_ERR_ARG;
+  }
+  h->model.dt = h->cfg.dt;
+  h->model.N = h->cfg.horizon;
+  const double *d_seq = seq_in;
+  const uint8_t *d_meas = measured;
+  if (!on_device) {
+    const size_t sb = (size_t)n * B200QP_SEQ_IN_DOUBLES * sizeof(double);
+    const double *src = seq_in;
+    if (!is_pinned(seq_in)) {
+      memcpy(h->h_seq, seq_in, sb);
+      src = h->h_seq;
+    }
+    CK(cudaMemcpyAsync(h->d_seq, src, sb, cudaMemcpyHostToDevice, h->stream));
+    d_seq = h->d_seq;
+    if (measured) {
+      uint8_t *stage = reinterpret_cast<uint8_t *>(h->h_seq + (size_t)h->cfg.max_batch * B200QP_SEQ_IN_DOUBLES);
+      memcpy(stage, measured, (size_t)n * 4);
+      CK(cudaMemcpyAsync(h->d_measured, stage, (size_t)n * 4, cudaMemcpyHostToDevice, h->stream));
+      d_meas = h->d_measured;
+    }
+  }
+  CK(launch_sequencer(n, h->model, d_seq, d_meas, h->d_in, h->d_contact, h->P.in_stride, h->stream));
+  return B200QP_OK;
+}
+
+int32_t b200qp_mpc_sequence_batch(b200qp_mpc *h, int32_t n, const double *seq_in, const uint8_t *measured_contact,
+                                  double *records, uint8_t *contact) {
+  if (!h || n < 0 || n > h->cfg.max_batch || (n > 0 && (!seq_in || !records || !contact))) {
+    g_err = "b200qp_mpc_sequence_batch: bad arguments";
+    return B200QP_ERR_ARG;
+  }
+  if (n == 0) return B200QP_OK;
+  CK(cudaSetDevice(h->cfg.device));
+  int32_t rc = sequence_impl(h, n, seq_in, measured_contact, false);
+  if (rc != B200QP_OK) return rc;
+  const int N = h->cfg.horizon;
+  CK(cudaMemcpyAsync(h->h_in, h->d_in, (size_t)n * h->P.in_stride * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(h->h_contact, h->d_contact, (size_t)n * N * 4, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  memcpy(records, h->h_in, (size_t)n * h->P.in_stride * sizeof(double));
+  memcpy(contact, h->h_contact, (size_t)n * N * 4);
+  return B200QP_OK;
+}
+
+int32_t b200qp_mpc_sequence_solve_batch(b200qp_mpc *h, int32_t n, const double *seq_in, const uint8_t *measured_contact,
+                                        double *forces, double *xpred, b200qp_solver_info *info) {
+  if (!h || n < 0 || n > h->cfg.max_batch || (n > 0 && (!seq_in || !forces || !xpred || !info))) {
+    g_err = "b200qp_mpc_sequence_solve_batch: bad arguments";
+    return B200QP_ERR_ARG;
+  }
+  if (n == 0) return B200QP_OK;
+  CK(cudaSetDevice(h->cfg.device));
+  int32_t rc = sequence_impl(h, n, seq_in, measured_contact, false);
+  if (rc != B200QP_OK) return rc;
+  rc = solve_and_fetch(h, n, forces, xpred, info);
+  h->last_launches += 1;
+  return rc;
+}
+
+int32_t b200qp_mpc_sequence_solve_batch_device(b200qp_mpc *h, int32_t n, const double *d_seq_in,
+                                               const uint8_t *d_measured_contact, double *d_forces, double *d_xpred,
+                                               b200qp_solver_info *d_info, int32_t sync) {
+  if (!h || n < 0 || n > h->cfg.max_batch || (n > 0 && (!d_seq_in || !d_forces || !d_xpred || !d_info))) {
+    g_err = "b200qp_mpc_sequence_solve_batch_device: bad arguments";
+    return B200QP_ERR_ARG;
+  }
+  if (n == 0) return B200QP_OK;
+  CK(cudaSetDevice(h->cfg.device));
+  int32_t rc = sequence_impl(h, n, d_seq_in, d_measured_contact, true);
+  if (rc != B200QP_OK) return rc;
+  rc = solve_device_impl(h, n, h->d_in, h->d_contact, d_forces, d_xpred, d_info, -1, nullptr, nullptr);
+  if (rc != B200QP_OK) return rc;
+  h->last_launches += 1;
+  if (sync) CK(cudaStreamSynchronize(h->stream));
   return B200QP_OK;
 }
 

@@ -100,3 +100,197 @@ cudaError_t fp64_peak(int num_sms, double *tflops) {
   return e;
 }
 }  // namespace b200qp
+
+// ---- on-device gait sequencer: one thread per robot turns (state, Target, gait, phase) into
+// the MPC input record + contact mask, so the host->device boundary shrinks from 2.3 KB to 0.4 KB per robot.
+//   SimpleGaitSequencer::GetGaitSequence            simple_gait_sequencer.cpp:43-60
+//   MPCTrajectoryPlanner::plan_trajectory            mpc_trajectory_planner.cpp:28-140  (Target activation of the node,
+//       mit_controller_node.cpp:145-165: hybrid_x_dot, hybrid_y_dot, wz, wx, wy, roll, pitch, z active)
+//   MPCTrajectoryPlanner::plan_desired_trajectory    mpc_trajectory_planner.cpp:142-264 (first call, no latching)
+//   Gait::update_sequence                            gait.cpp:67-112
+//   RaibertFootStepPlanner::get_foot_position_sequence / get_foothold   raibert_foot_step_planner.cpp:43-169
+namespace b200qp {
+
+struct SeqModel {
+  double mass, inertia[9], com[3], shoulders[12], raibert_k, raibert_g, max_leg_length, dt;
+  int N;
+};
+
+namespace {
+__device__ inline double q_yaw(const double *q) {
+  double R[3][3];
+  quat_to_rot(q, R);
+  return atan2(R[1][0], R[0][0]);
+}
+__device__ inline void e_to_q(const double *e, double *q) {  // euler_to_quaternion, quaternion_operations.hpp:19-25
+  const double r = 0.5 * e[0], p = 0.5 * e[1], y = 0.5 * e[2];
+  const double cr = cos(r), sr = sin(r), cp = cos(p), sp = sin(p), cy = cos(y), sy = sin(y);
+  q[3] = cy * cp * cr + sy * sp * sr;
+  q[0] = cy * cp * sr - sy * sp * cr;
+  q[1] = cy * sp * cr + sy * cp * sr;
+  q[2] = sy * cp * cr - cy * sp * sr;
+}
+__device__ inline void yaw_q(double yaw, double *q) {
+  q[0] = 0.0; q[1] = 0.0; q[2] = sin(0.5 * yaw); q[3] = cos(0.5 * yaw);
+}
+__device__ inline void slerp_half(const double *a, const double *b, double *o) {  // Eigen slerp(0.5, b)
+  const double d = a[0] * b[0] + a[1] * b[1] + a[2] * b[2] + a[3] * b[3];
+  const double ad = fabs(d);
+  double s0 = 0.5, s1 = 0.5;
+  if (ad < 1.0 - 2.220446049250313e-16) {
+    const double th = acos(ad), st = sin(th);
+    s0 = sin(0.5 * th) / st;
+    s1 = s0;
+  }
+  if (d < 0) s1 = -s1;
+  for (int c = 0; c < 4; ++c) o[c] = s0 * a[c] + s1 * b[c];
+}
+__device__ inline void rot_v(const double *q, const double *v, double *o) {
+  double R[3][3];
+  quat_to_rot(q, R);
+  for (int r = 0; r < 3; ++r) o[r] = R[r][0] * v[0] + R[r][1] * v[1] + R[r][2] * v[2];
+}
+}  // namespace
+
+// seq_in per robot (50 doubles): quat 0-3, pos 4-6, omega 7-9, vel 10-12, feet 13-24, v_filtered 25-27, last foot heights 28-31,
+// target 32-39 (hybrid_x_dot, hybrid_y_dot, wz, wx, wy, roll, pitch, z), phase 40, period 41, duty 42-45, offset 46-49
+__global__ void sequencer_kernel(int n, SeqModel M, const double *__restrict__ seq_in, const uint8_t *__restrict__ measured,
+                                 double *__restrict__ rec_out, uint8_t *__restrict__ contact_out, int in_stride) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  const double *S = seq_in + (size_t)p * 50;
+  const int N = M.N, steps = N + 1;
+  const double dt = M.dt;
+  double *rec = rec_out + (size_t)p * in_stride;
+  uint8_t *ct = contact_out + (size_t)p * N * 4;
+  // ---- contact schedule, rows 0..N (row N is only needed by the foot-step logic)
+  unsigned cmask[MAXH + 1];
+  {
+    bool early[4] = {false, false, false, false};
+    for (int i = 0; i < steps; ++i) {
+      unsigned m = 0;
+      for (int leg = 0; leg < 4; ++leg) {
+        const double T = S[41], d = S[42 + leg], off = S[46 + leg];
+        const double leg_phase = fmod(((S[40] + 1.0) - off) + ((double)(unsigned)i * dt) / T, 1.0);
+        bool c = leg_phase < d;
+        if (i == 0 && measured != nullptr) {
+          if (measured[4 * p + leg] != 0 && !c && (leg_phase > ((d + 1.0) / 2.0))) early[leg] = true;
+        }
+        if (c) early[leg] = false;
+        else if (early[leg]) c = true;
+        if (c) m |= 1u << leg;
+      }
+      cmask[i] = m;
+      if (i < N)
+        for (int leg = 0; leg < 4; ++leg) ct[4 * i + leg] = (m >> leg) & 1u;
+    }
+  }
+  // ---- header: state + model
+  for (int c = 0; c < 13; ++c) rec[c] = S[c];
+  rec[13] = M.mass;
+  for (int c = 0; c < 9; ++c) rec[14 + c] = M.inertia[c];
+  for (int c = 0; c < 3; ++c) rec[23 + c] = M.com[c];
+  const double hx = S[32], hy = S[33];
+  const double twc[3] = {S[35], S[36], S[34]};
+  const double troll = S[37], tpitch = S[38], tz = S[39];
+  double min_h = fmin(fmin(S[13 + 2], S[16 + 2]), fmin(S[19 + 2], S[22 + 2]));
+  // ---- reference ("ref") and desired ("des") trajectories; both recursions coincide on the first call except that the
+  // reference twist of row 0 is the measured one.  Per row we also need ref position / yaw-quaternion / velocity / twist for
+  // the foot-step planner, kept in small per-row arrays.
+  double ref_pos[MAXH + 1][3], ref_yawq[MAXH + 1][4], ref_vel[MAXH + 1][3];
+  {
+    double R0[3][3], eul[3], position[3], quat_prev[4];
+    quat_to_rot(S, R0);
+    rot_to_euler(R0, eul);
+    for (int c = 0; c < 3; ++c) position[c] = S[4 + c];
+    for (int c = 0; c < 4; ++c) quat_prev[c] = S[c];
+    // row 0
+    double *st0 = rec + 26;
+    for (int c = 0; c < 4; ++c) st0[c] = S[c];
+    for (int c = 0; c < 3; ++c) { st0[4 + c] = S[4 + c]; st0[7 + c] = S[7 + c]; st0[10 + c] = S[10 + c]; }
+    for (int c = 0; c < 3; ++c) { ref_pos[0][c] = S[4 + c]; ref_vel[0][c] = S[10 + c]; }
+    yaw_q(q_yaw(S), ref_yawq[0]);
+    for (int i = 1; i < steps; ++i) {
+      for (int c = 0; c < 3; ++c) eul[c] = eul[c] + dt * twc[c];
+      eul[1] = tpitch;
+      eul[0] = troll;
+      double q[4], yq_prev[4], yq[4], mid[4], step[3], dv[3] = {dt * hx, dt * hy, 0.0};
+      e_to_q(eul, q);
+      yaw_q(q_yaw(quat_prev), yq_prev);
+      yaw_q(q_yaw(q), yq);
+      slerp_half(yq_prev, yq, mid);
+      rot_v(mid, dv, step);
+      for (int c = 0; c < 3; ++c) position[c] = position[c] + step[c];
+      position[2] = tz + min_h;
+      double hv[3] = {hx, hy, 0.0}, vel[3];
+      rot_v(q, hv, vel);
+      double *st = rec + 26 + 13 * i;
+      for (int c = 0; c < 4; ++c) st[c] = q[c];
+      for (int c = 0; c < 3; ++c) { st[4 + c] = position[c]; st[7 + c] = twc[c]; st[10 + c] = vel[c]; }
+      for (int c = 0; c < 3; ++c) { ref_pos[i][c] = position[c]; ref_vel[i][c] = vel[c]; }
+      for (int c = 0; c < 4; ++c) { ref_yawq[i][c] = yq[c]; quat_prev[c] = q[c]; }
+    }
+  }
+  // ---- Raibert foot positions (z_on_plane = false)
+  double *fp = rec + 26 + 13 * steps;
+  double heights[4] = {S[28], S[29], S[30], S[31]};
+  bool resume[4] = {true, true, true, true};
+  double prevfp[4][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+  const double L = M.max_leg_length;
+  for (int i = 0; i < steps; ++i) {
+    for (int leg = 0; leg < 4; ++leg) {
+      double out[3] = {0.0, 0.0, 0.0};
+      if ((cmask[i] >> leg) & 1u) {
+        if (i == 0) {
+          for (int c = 0; c < 3; ++c) out[c] = S[13 + 3 * leg + c];
+          heights[leg] = out[2];
+        } else if (resume[leg]) {
+          for (int c = 0; c < 3; ++c) out[c] = prevfp[leg][c];
+        } else {
+          double psh[3], sh[3] = {M.shoulders[3 * leg], M.shoulders[3 * leg + 1], M.shoulders[3 * leg + 2]};
+          rot_v(ref_yawq[i], sh, psh);
+          for (int c = 0; c < 3; ++c) psh[c] = ref_pos[i][c] + psh[c];
+          double h = ref_pos[i][2] - fmin(fmin(heights[0], heights[1]), fmin(heights[2], heights[3]));
+          h = fmin(fmax(h, 0.0), L);
+          const double *v = S + 25;
+          const double wcx = (i == 0) ? S[7] : twc[0], wcy = (i == 0) ? S[8] : twc[1], wcz = (i == 0) ? S[9] : twc[2];
+          const double cr[3] = {v[1] * wcz - v[2] * wcy, v[2] * wcx - v[0] * wcz, v[0] * wcy - v[1] * wcx};
+          const double kc = 0.5 * sqrt(h / M.raibert_g);
+          const double tst = S[42 + leg] * S[41];
+          double pp[3];
+          for (int c = 0; c < 3; ++c) pp[c] = psh[c] + kc * cr[c] + ((tst / 2.0) * v[c] + M.raibert_k * (v[c] - ref_vel[i][c]));
+          pp[2] = heights[leg];
+          double dif[3] = {pp[0] - psh[0], pp[1] - psh[1], pp[2] - psh[2]};
+          const double nrm = sqrt(dif[0] * dif[0] + dif[1] * dif[1] + dif[2] * dif[2]);
+          if (nrm > L && fabs(dif[2]) <= L) {  // clip to the reachable sphere keeping dx/dy (raibert_foot_step_planner.cpp:97-113)
+            double nd[3];
+            if (fabs(dif[0]) > fabs(dif[1])) {
+              nd[0] = -sqrt(-(dif[2] - L) * (dif[2] + L) / ((dif[1] / dif[0]) * (dif[1] / dif[0]) + 1));
+              nd[1] = (dif[1] / dif[0]) * nd[0];
+            } else {
+              nd[1] = -sqrt(-(dif[2] - L) * (dif[2] + L) / ((dif[0] / dif[1]) * (dif[0] / dif[1]) + 1));
+              nd[0] = (dif[0] / dif[1]) * nd[1];
+            }
+            nd[2] = dif[2];
+            for (int c = 0; c < 3; ++c) pp[c] = psh[c] + nd[c];
+          }
+          for (int c = 0; c < 3; ++c) out[c] = pp[c];
+        }
+        resume[leg] = true;
+      } else {
+        resume[leg] = false;
+      }
+      for (int c = 0; c < 3; ++c) prevfp[leg][c] = out[c];
+      if (i < N)
+        for (int c = 0; c < 3; ++c) fp[12 * i + 3 * leg + c] = out[c];
+    }
+  }
+}
+
+cudaError_t launch_sequencer(int n, const SeqModel &M, const double *seq_in, const uint8_t *measured, double *rec_out,
+                             uint8_t *contact_out, int in_stride, cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  sequencer_kernel<<<(n + 63) / 64, 64, 0, st>>>(n, M, seq_in, measured, rec_out, contact_out, in_stride);
+  return cudaGetLastError();
+}
+}  // namespace b200qp

@@ -444,8 +444,20 @@ __global__ void __launch_bounds__(BS) mpc_admm_kernel(const MpcParams P, const M
     const int slot = s_slot;
     if (slot >= *B.bin_count) break;
     const int prob = B.bin_list[slot];
-    const double *rec = B.in + (size_t)prob * P.in_stride;
-    const uint8_t *ct = B.contact + (size_t)prob * N * 4;
+    // Stage the record (2.3 KB at N = 10) and its contact bytes in shared memory with one coalesced pass: the scattered
+    // per-thread reads of the assembly then never leave the SM, and B.in may be the caller's page-locked host buffer
+    // (read once over PCIe).  The copy aliases the ADMM work vectors, which are idle until the first factorisation.
+    static_assert(9 * BS >= 26 + 13 * (MAXH + 1) + 12 * MAXH + (4 * MAXH + 7) / 8, "record staging area");
+    {
+      const double *grec = B.in + (size_t)prob * P.in_stride;
+      const uint8_t *gct = B.contact + (size_t)prob * N * 4;
+      for (int e = tid; e < P.in_stride; e += BS) s_v[e] = grec[e];
+      uint8_t *sct = reinterpret_cast<uint8_t *>(s_v + P.in_stride);
+      for (int e = tid; e < 4 * N; e += BS) sct[e] = gct[e];
+    }
+    __syncthreads();
+    const double *rec = s_v;
+    const uint8_t *ct = reinterpret_cast<const uint8_t *>(s_v + P.in_stride);
     const double mass = rec[13];
 
     const bool timing = B.dbg_cycles != nullptr;
@@ -998,12 +1010,6 @@ __global__ void __launch_bounds__(BS) mpc_admm_kernel(const MpcParams P, const M
       if (act) s_xt[tid] = xsol;
       for (int e = tid; e < N * 36; e += BS) s_Bw[e] = Bw_park[e];
       __syncthreads();
-      double *fo = B.forces + (size_t)prob * N * 12;
-      for (int e = tid; e < N * 12; e += BS) {
-        const int kf = e / 3, c = e - 3 * kf;
-        const int fi = s_fidx[kf];
-        fo[e] = (fi >= 0) ? s_xt[3 * fi + c] : 0.0;
-      }
       if (B.lam_box != nullptr) {
         double *lb = B.lam_box + (size_t)prob * N * 12;
         double *lg = B.lam_g + (size_t)prob * N * 16;
@@ -1071,7 +1077,13 @@ __global__ void __launch_bounds__(BS) mpc_admm_kernel(const MpcParams P, const M
       if (act) nanout |= !(fabs(xsol) < BIG);
       if (__syncthreads_or(nanout ? 1 : 0)) {
         status = B200QP_NAN_AFTER_SUCCESS;  // mpc.cpp:447-455
-      } else {
+      } else {  // outputs are only touched for a solved, finite problem (the buffers may be the caller's own host memory)
+        double *fo = B.forces + (size_t)prob * N * 12;
+        for (int e = tid; e < N * 12; e += BS) {
+          const int kf = e / 3, c = e - 3 * kf;
+          const int fi = s_fidx[kf];
+          fo[e] = (fi >= 0) ? s_xt[3 * fi + c] : 0.0;
+        }
         for (int e = tid; e < (N + 1) * 13; e += BS) xo[e] = s_X[e];
       }
     }

@@ -190,6 +190,58 @@ class BatchedMPC:
         _lib.check(rc, "b200qp_mpc_solve_batch")
         return forces, xpred, self._info(info, n)
 
+    # -- on-device gait sequencer (b200qp_mpc_sequence_*) ---------------------------------------------------------------
+    def set_model(self, mass, inertia, com, shoulders, raibert_k, raibert_g, max_leg_length):
+        """MPC::UpdateModel + the planner constants for the sequencer entry points (b200qp_mpc_set_model)."""
+        m = _lib.SeqModel()
+        m.mass = float(mass)
+        m.inertia[:] = [float(v) for v in np.asarray(inertia, float).reshape(9)]
+        m.com[:] = [float(v) for v in np.asarray(com, float).reshape(3)]
+        m.shoulders[:] = [float(v) for v in np.asarray(shoulders, float).reshape(12)]
+        m.raibert_k, m.raibert_g, m.max_leg_length = float(raibert_k), float(raibert_g), float(max_leg_length)
+        _lib.check(self._lib.b200qp_mpc_set_model(self._h, C.byref(m)), "b200qp_mpc_set_model")
+
+    def _seq_args(self, seq_in, measured_contact):
+        seq_in = np.ascontiguousarray(seq_in, dtype=np.float64)
+        n = seq_in.shape[0]
+        if seq_in.shape != (n, 50):
+            raise ValueError("seq_in must be [n, 50]")
+        mc = None
+        if measured_contact is not None:
+            mc = np.ascontiguousarray(measured_contact, dtype=np.uint8)
+            if mc.shape != (n, 4):
+                raise ValueError("measured_contact must be [n, 4]")
+        return seq_in, mc, n
+
+    def sequence_records(self, seq_in, measured_contact=None):
+        """b200qp_mpc_sequence_batch: (state, feet, Target, gait, phase) -> (records, contact) as solve_records takes."""
+        seq_in, mc, n = self._seq_args(seq_in, measured_contact)
+        rec = np.zeros((n, in_doubles(self.N)))
+        contact = np.zeros((n, self.N, 4), dtype=np.uint8)
+        rc = self._lib.b200qp_mpc_sequence_batch(self._h, n, seq_in.ctypes.data, mc.ctypes.data if mc is not None else None,
+                                                 rec.ctypes.data, contact.ctypes.data)
+        _lib.check(rc, "b200qp_mpc_sequence_batch")
+        return rec, contact
+
+    def sequence_and_solve(self, seq_in, measured_contact=None, forces=None, xpred=None):
+        """b200qp_mpc_sequence_solve_batch: sequencer + QP assembly + solve in one call."""
+        seq_in, mc, n = self._seq_args(seq_in, measured_contact)
+        if forces is None:
+            forces = np.zeros((n, self.N, 12))
+        if xpred is None:
+            xpred = np.zeros((n, self.N + 1, 13))
+        info = (_lib.SolverInfo * max(n, 1))()
+        rc = self._lib.b200qp_mpc_sequence_solve_batch(self._h, n, seq_in.ctypes.data,
+                                                       mc.ctypes.data if mc is not None else None, forces.ctypes.data,
+                                                       xpred.ctypes.data, C.addressof(info))
+        _lib.check(rc, "b200qp_mpc_sequence_solve_batch")
+        return forces, xpred, self._info(info, n)
+
+    def sequence_and_solve_device(self, n, d_seq_in, d_measured, d_forces, d_xpred, d_info, sync=True):
+        rc = self._lib.b200qp_mpc_sequence_solve_batch_device(self._h, n, d_seq_in, d_measured, d_forces, d_xpred, d_info,
+                                                              1 if sync else 0)
+        _lib.check(rc, "b200qp_mpc_sequence_solve_batch_device")
+
     def solve_device(self, n, d_in, d_contact, d_forces, d_xpred, d_info, sync=True):
         """b200qp_mpc_solve_batch_device on raw device pointers (ints)."""
         rc = self._lib.b200qp_mpc_solve_batch_device(self._h, n, d_in, d_contact, d_forces, d_xpred, d_info, 1 if sync else 0)

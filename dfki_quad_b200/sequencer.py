@@ -209,6 +209,39 @@ def random_batch(n, horizon, seed, gaits=("TROT",), dt=0.05, device=0, schedule_
     fp = raibert_foot_positions(steps, contact, traj, feet, vel, t_stance, np.repeat(min_h[:, None], 4, axis=1))
     rec = pack_records(N, quat, pos, omega, vel, np.full(n, GO2_MASS), GO2_INERTIA, np.broadcast_to(GO2_COM, (n, 3)),
                        traj["des_quat"], traj["des_pos"], traj["ref_twist"], traj["ref_vel"], fp)
+    seq_in = pack_sequencer_inputs(quat, pos, omega, vel, feet, vel, np.repeat(min_h[:, None], 4, axis=1), target, phase,
+                                   period, duty, offset)
     return dict(rec=rec, contact=np.ascontiguousarray(contact[:, :N]), quat=quat, pos=pos, omega=omega, vel=vel,
                 target=target, phase=phase, gait_ids=gait_ids, period=period, duty=duty, offset=offset, feet=feet,
-                traj=traj, foot_pos=fp, swing_time=swing)
+                traj=traj, foot_pos=fp, swing_time=swing, seq_in=seq_in)
+
+
+SEQ_IN_DOUBLES = 50  # B200QP_SEQ_IN_DOUBLES
+TARGET_FIELDS = ("hybrid_x_dot", "hybrid_y_dot", "wz", "wx", "wy", "roll", "pitch", "z")
+
+
+def pack_sequencer_inputs(quat, pos, omega, vel, feet, v_filtered, last_foot_heights, target, phase, period, duty, offset):
+    """Per-robot input of the on-device sequencer (include/b200qp.h, B200QP_SEQ_IN_DOUBLES layout) -> [n, 50]."""
+    n = len(phase)
+    s = np.zeros((n, SEQ_IN_DOUBLES))
+    s[:, 0:4] = quat
+    s[:, 4:7] = pos
+    s[:, 7:10] = omega
+    s[:, 10:13] = vel
+    s[:, 13:25] = np.asarray(feet).reshape(n, 12)
+    s[:, 25:28] = v_filtered
+    s[:, 28:32] = last_foot_heights
+    for j, f in enumerate(TARGET_FIELDS):
+        s[:, 32 + j] = target[f]
+    s[:, 40] = phase
+    s[:, 41] = period
+    s[:, 42:46] = duty
+    s[:, 46:50] = offset
+    return s
+
+
+def go2_seq_model():
+    """b200qp_seq_model constants of the Go2 configuration (mit_controller_sim_go2.yaml / quad_model_symbolic.cpp)."""
+    return dict(mass=GO2_MASS, inertia=np.asarray(GO2_INERTIA, float).reshape(3, 3), com=np.asarray(GO2_COM, float),
+                shoulders=np.asarray(GO2_SHOULDERS, float), raibert_k=RAIBERT_K, raibert_g=RAIBERT_G,
+                max_leg_length=MAX_LEG_LENGTH)

@@ -137,6 +137,46 @@ int32_t b200qp_mpc_last_timing(b200qp_mpc *h, float *kernel_ms, int32_t *kernel_
 /* CUDA stream of the handle as a void* (cudaStream_t), for callers that time with their own events. */
 void *b200qp_mpc_stream(b200qp_mpc *h);
 
+/* ---- on-device gait sequencer -----------------------------------------------------
+ * Replaces, for n robots at once, the caller side of MPC::UpdateGaitSequence: one SimpleGaitSequencer pass
+ *   SimpleGaitSequencer::GetGaitSequence            simple_gait_sequencer.cpp:43-60
+ *   Gait::update_sequence                           gait.cpp:67-112
+ *   MPCTrajectoryPlanner::plan_trajectory           mpc_trajectory_planner.cpp:28-140 (+ plan_desired_trajectory,
+ *       :142-264, first call; Target activation of the controller node, mit_controller_node.cpp:145-165)
+ *   RaibertFootStepPlanner::get_foot_position_sequence  raibert_foot_step_planner.cpp:43-169 (z_on_plane = false)
+ * so the host->device boundary is (state, feet, Target, gait, phase) = 400 B per robot instead of the 2.3 KB record.
+ * Sequencer input per robot, B200QP_SEQ_IN_DOUBLES doubles:
+ *   [0:4) quat xyzw  [4:7) position  [7:10) angular velocity (world)  [10:13) linear velocity   StateInterface
+ *   [13:25) current foot positions, world, leg-major                  StateInterface::GetFeetPositions
+ *   [25:28) filtered velocity (RaibertFootStepPlanner's moving average, kept by the caller)
+ *   [28:32) last stance height per foot                               RaibertFootStepPlanner::last_foot_heights_
+ *   [32:40) Target: hybrid_x_dot, hybrid_y_dot, wz, wx, wy, roll, pitch, z   interfaces::msg::QuadControlTarget
+ *   [40] gait phase  [41] period  [42:46) duty factor per leg  [46:50) phase offset per leg      Gait members */
+#define B200QP_SEQ_IN_DOUBLES 50
+typedef struct b200qp_seq_model {
+  double mass;            /* QuadModel mass                                   quad_model_symbolic.cpp        */
+  double inertia[9];      /* body inertia, row-major                                                          */
+  double com[3];          /* body-frame COM offset                                                            */
+  double shoulders[12];   /* shoulder offsets in the body frame, leg-major    raibert_foot_step_planner.cpp:28-34 */
+  double raibert_k;       /* raibert.k                                        mit_controller_sim_go2.yaml    */
+  double raibert_g;       /* RaibertFootStepPlanner g                         raibert_foot_step_planner.hpp  */
+  double max_leg_length;  /* FK(0) leg length - 0.02                          raibert_foot_step_planner.cpp:36-40 */
+} b200qp_seq_model;
+/* Model constants used by the sequencer entry points (MPC::UpdateModel + planner constructor arguments). */
+int32_t b200qp_mpc_set_model(b200qp_mpc *h, const b200qp_seq_model *model);
+/* Sequencer only: HOST seq_in[n][50], measured_contact[n][4] or NULL -> HOST records[n][b200qp_mpc_in_doubles(N)] and
+ * contact[n][N][4] in exactly the layout b200qp_mpc_solve_batch consumes (parity hook for the sequencer kernel). */
+int32_t b200qp_mpc_sequence_batch(b200qp_mpc *h, int32_t n, const double *seq_in, const uint8_t *measured_contact,
+                                  double *records, uint8_t *contact);
+/* Sequencer + QP assembly + solve in one call; outputs and failure semantics as b200qp_mpc_solve_batch. */
+int32_t b200qp_mpc_sequence_solve_batch(b200qp_mpc *h, int32_t n, const double *seq_in,
+                                        const uint8_t *measured_contact, double *forces, double *xpred,
+                                        b200qp_solver_info *info);
+/* Same with DEVICE pointers on the handle's stream (d_measured_contact may be NULL). */
+int32_t b200qp_mpc_sequence_solve_batch_device(b200qp_mpc *h, int32_t n, const double *d_seq_in,
+                                               const uint8_t *d_measured_contact, double *d_forces, double *d_xpred,
+                                               b200qp_solver_info *d_info, int32_t sync);
+
 /* ---- gait schedule -> contact mask -> bound indexing (kernel K4, bit-exact) -------------------------------------
  * Gait::update_sequence (gait.cpp:67-112) for n robots with per-robot gait parameters and phase, followed by
  * MPC::GetUBounds (mpc.cpp:94-115).

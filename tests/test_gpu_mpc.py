@@ -229,6 +229,31 @@ def test_setters_and_failure_semantics(go2_params):
     assert np.array_equal(forces[0], f1[0])
 
 
+@pytest.mark.parametrize("solver", ["CONDENSED_ADMM", "SPARSE_RICCATI"])
+def test_page_locked_outputs_are_written_in_place_with_failure_semantics(solver):
+    """Pinned caller buffers are written by the kernels directly (no staging copy): results identical to the staged
+    path, failed problems leave their slots untouched."""
+    import torch
+    from dfki_quad_b200 import sequencer
+
+    N, n = 10, 512
+    batch = sequencer.random_batch(n, N, seed=31, gaits=("TROT", "PACE", "STAND"))
+    mpc = _mpc(N, n, solver=solver)
+    f_ref, x_ref, info_ref = mpc.solve_records(batch["rec"], batch["contact"])  # pageable numpy -> staged path
+    rec = torch.from_numpy(batch["rec"].copy()).pin_memory()
+    ct = torch.from_numpy(batch["contact"]).pin_memory()
+    rec[7, 5] = float("nan")
+    rec[300, 30] = float("nan")
+    f_p = torch.full((n, N, 12), 123.0, dtype=torch.float64).pin_memory()
+    x_p = torch.full((n, N + 1, 13), 321.0, dtype=torch.float64).pin_memory()
+    _, _, info = mpc.solve_records(rec.numpy(), ct.numpy(), f_p.numpy(), x_p.numpy())
+    bad = np.zeros(n, bool)
+    bad[[7, 300]] = True
+    assert not info.success[bad].any() and info.success[~bad].all()
+    assert (f_p.numpy()[bad] == 123.0).all() and (x_p.numpy()[bad] == 321.0).all()
+    assert np.array_equal(f_p.numpy()[~bad], f_ref[~bad]) and np.array_equal(x_p.numpy()[~bad], x_ref[~bad])
+
+
 def test_duals_reported_in_reference_row_order(go2_params):
     from dfki_quad_b200 import sequencer
 
@@ -398,3 +423,91 @@ def test_mixed_sizes_in_one_call_and_determinism(go2_params):
     ok = i1.return_code == 0
     assert ok.sum() >= n - 12 and np.all(i1.return_code[~ok] == 4)
     _check_against_oracle(N, b, f1, x1, i1, go2_params, np.nonzero(ok)[0][:8])
+
+
+# ------------------------------------------------------------------ on-device gait sequencer
+def _seq_case(rng, N, gait, early=False):
+    from oracle import sequencer_oracle as so
+    (rec, contact), raw = so.random_problem(rng, N, gait)
+    return rec, contact, raw
+
+
+@pytest.mark.parametrize("N", [10, 20])
+def test_sequencer_kernel_matches_scalar_oracle(N):
+    """Sequencer kernel vs the scalar restatement of SimpleGaitSequencer / MPCTrajectoryPlanner / Raibert planner:
+    contact masks bit-exact, records to 1e-12 (libm vs CUDA trig differ in the last ulp)."""
+    from oracle import mpc_oracle as mo
+    from dfki_quad_b200 import sequencer as sq
+    rng = np.random.Generator(np.random.PCG64(77 + N))
+    gaits = list(mo.GAITS)
+    recs, cts, seqs = [], [], []
+    for i in range(96):
+        g = gaits[i % len(gaits)]
+        rec, contact, raw = _seq_case(rng, N, g)
+        T, duty, off = mo.GAITS[g]
+        st = raw["state"]
+        min_h = raw["feet"][:, 2].min()
+        tgt = {k: np.array([v]) for k, v in raw["tgt"].items()}
+        seqs.append(sq.pack_sequencer_inputs(st["quat"][None], st["pos"][None], st["omega"][None], st["vel"][None],
+                                             raw["feet"][None], st["vel"][None], np.full((1, 4), min_h), tgt,
+                                             np.array([raw["phase"]]), np.array([T]), np.full((1, 4), duty),
+                                             np.asarray(off, float)[None])[0])
+        recs.append(rec)
+        cts.append(contact)
+    mpc = _mpc(N, 128)
+    mpc.set_model(**sq.go2_seq_model())
+    rec_g, ct_g = mpc.sequence_records(np.array(seqs))
+    assert np.array_equal(ct_g, np.array(cts).astype(np.uint8))
+    np.testing.assert_allclose(rec_g, np.array(recs), rtol=0, atol=1e-12)
+
+
+def test_sequencer_early_contact_rule():
+    """Measured contact late in a planned swing phase latches the leg into stance (gait.cpp:78-90)."""
+    from oracle import mpc_oracle as mo
+    from oracle import sequencer_oracle as so
+    from dfki_quad_b200 import sequencer as sq
+    N = 10
+    rng = np.random.Generator(np.random.PCG64(5))
+    T, duty, off = mo.GAITS["TROT"]
+    seqs, cts, meas = [], [], []
+    for i in range(64):
+        (_, _), raw = so.random_problem(rng, N, "TROT")
+        st = raw["state"]
+        m = rng.integers(0, 2, 4).astype(np.uint8)
+        rec, contact = so.make_problem(N, "TROT", raw["phase"], st, raw["tgt"], raw["feet"], mo.GO2_PARAMS, measured_contacts=list(m))
+        min_h = raw["feet"][:, 2].min()
+        tgt = {k: np.array([v]) for k, v in raw["tgt"].items()}
+        seqs.append(sq.pack_sequencer_inputs(st["quat"][None], st["pos"][None], st["omega"][None], st["vel"][None],
+                                             raw["feet"][None], st["vel"][None], np.full((1, 4), min_h), tgt,
+                                             np.array([raw["phase"]]), np.array([T]), np.full((1, 4), duty),
+                                             np.asarray(off, float)[None])[0])
+        cts.append(contact)
+        meas.append(m)
+    mpc = _mpc(N, 64)
+    mpc.set_model(**sq.go2_seq_model())
+    _, ct_g = mpc.sequence_records(np.array(seqs), np.array(meas))
+    ref = np.array(cts).astype(np.uint8)
+    assert np.array_equal(ct_g, ref)
+    # the rule must actually have fired somewhere in the sample
+    _, ct_plain = mpc.sequence_records(np.array(seqs))
+    assert (ct_g != ct_plain).any()
+
+
+def test_sequence_and_solve_equals_two_step_path():
+    """Fused sequencer+solve call gives the same forces as host sequencer -> solve_records (records agree to 1e-12,
+    so the QP solutions agree to the solver tolerance)."""
+    from dfki_quad_b200 import sequencer as sq
+    N, n = 10, 2048
+    batch = sq.random_batch(n, N, seed=11, gaits=("TROT", "WALKING_TROT", "STAND"))
+    mpc = _mpc(N, n)
+    mpc.set_model(**sq.go2_seq_model())
+    rec_g, ct_g = mpc.sequence_records(batch["seq_in"])
+    assert np.array_equal(ct_g, batch["contact"])
+    np.testing.assert_allclose(rec_g, batch["rec"], rtol=0, atol=1e-12)
+    f1, x1, i1 = mpc.solve_records(batch["rec"], batch["contact"])
+    f2, x2, i2 = mpc.sequence_and_solve(batch["seq_in"])
+    assert i1.success.all() and i2.success.all()
+    scale = np.abs(f1).max(axis=(1, 2), keepdims=True)
+    assert (np.abs(f1 - f2) / scale).max() < 1e-5
+    with pytest.raises(Exception):
+        _mpc(N, 4).sequence_and_solve(batch["seq_in"][:4])  # no model set
