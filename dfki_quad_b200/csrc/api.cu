@@ -110,13 +110,13 @@ static void fill_params(b200qp_mpc *h) {
   P.mu = c.mu;
   P.fmin = c.fmin;
   P.fmax = c.fmax;
-  P.rho0 = c.admm_rho > 0 ? c.admm_rho : 1e-3;
+  P.rho0 = c.admm_rho > 0 ? c.admm_rho : 5e-5;
   P.sigma = c.admm_sigma > 0 ? c.admm_sigma : 1e-6;
   P.relax = c.admm_alpha > 0 ? c.admm_alpha : 1.6;
   P.eps = c.admm_eps > 0 ? c.admm_eps : 1e-3;
   P.kkt_tol = c.kkt_tol > 0 ? c.kkt_tol : 1e-7;
   P.max_iter = c.admm_max_iter > 0 ? c.admm_max_iter : 2000;
-  P.check_every = c.admm_check_every > 0 ? c.admm_check_every : 10;
+  P.check_every = c.admm_check_every > 0 ? c.admm_check_every : 15;
   P.polish_rounds = c.polish_max_rounds > 0 ? c.polish_max_rounds : 8;
   P.ipm_max_iter = c.ipm_max_iter > 0 ? c.ipm_max_iter : 40;
 }
@@ -189,6 +189,7 @@ int32_t b200qp_mpc_create(const b200qp_mpc_config *cfg, b200qp_mpc **out) {
     for (int b = 0; b < 3; ++b) {
       const int bs = admm_block_size(b);
       int g = h->num_sms * admm_occupancy(b);
+      if (const char *e = getenv("B200QP_BLOCKS_PER_SM")) g = h->num_sms * (atoi(e) > 0 ? atoi(e) : 1);  // development
       if ((size_t)g > nb) g = (int)nb;
       h->grid[b] = g;
       CK(cudaMalloc(&h->d_hscratch[b], (size_t)g * ((size_t)bs * bs + B200QP_MAX_HORIZON * 36) * sizeof(double)));

@@ -13,6 +13,12 @@
 // lbu = ubu = 0, mpc.cpp:110-113) are eliminated, which leaves the optimum unchanged.
 #include "common.cuh"
 
+#ifndef B200QP_TC_GJ
+#define B200QP_TC_GJ 0
+#endif
+#ifndef B200QP_CHOL_POLISH
+#define B200QP_CHOL_POLISH 0
+#endif
 namespace b200qp {
 
 // optional per-phase cycle accounting (B.dbg_cycles != nullptr): thread 0 accumulates clock64() deltas per phase
@@ -329,6 +335,330 @@ __device__ __noinline__ void gj_invert(double *K, int n, double *prow4) {
   }
 }
 
+// One m8n8k4 FP64 tensor-core MMA: C[8x8] += A[8x4] B[4x8].  Fragments (lane = 4 g + t): A[g][t], B[t][g], C[g][2t], C[g][2t+1].
+// DMMA runs at the full FP64 rate of the SM (measured 37 TFLOP/s on B200, the DFMA rate) for 1/8 of the issue slots.
+__device__ __forceinline__ void dmma_8x8x4(double &c0, double &c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+// Register-resident blocked Gauss-Jordan inverse on the FP64 tensor cores, 64 threads, matrices up to 64 x 64.
+// The shared-memory version is bound by shared-memory bandwidth (every element is read and written once per four pivots;
+// the LSU pipe was the busiest unit of the kernel).  Here the matrix lives in the MMA accumulator fragments of the two
+// warps for the whole inversion - warp w owns row blocks w, w+2, w+4, w+6 (8 rows each) and all eight column tiles, 32
+// tiles x 2 doubles per thread - and a 4-pivot step is
+//   [A] the owners publish the 4 pivot rows (prow4[j][q] = A[p0+q][j]) and the 4 pivot columns (cw[i][q] = A[i][p0+q]);
+//   [B] thread i inverts the 4x4 pivot block E = D^-1, forms its multipliers w[i][.] = A[i,P] E (published negated; zero
+//       for pivot rows) and the new pivot-row entries of column i, np[i][.] = E A[P,i];
+//   [C] trailing update C -= w Pr as one DMMA per tile, then the pivot columns take -w and the pivot rows take np.
+// Shared memory is touched only by the O(n) staging of [A]/[B] and the 12 fragment loads per thread of [C].
+// Tile geometry: tile rows are contiguous, the 8 columns of tile ct = 2 s + t are {16 s + 2 t + 4 u + e : u < 4, e < 2}
+// (two interleaved tiles per 16-column span) so that fragment <-> memory moves with the odd leading dimension are
+// bank-conflict free.  Rows / columns >= n are padded with the identity, so n needs no alignment.
+// src: symmetric source, element (r, c), r >= c, at src[c * lds + r] (global Hessian scratch or the shared matrix
+// itself); dg: added to the diagonal (may be nullptr).  The inverse is written to K[c * LD + r] (full matrix).
+// K doubles as staging space while the matrix is in registers.
+template <int LD>
+__device__ __noinline__ void gj_invert_tc(const double *src, int lds, const double *dg, double *K, int n) {
+  const int i = threadIdx.x, lane = i & 31, warp = i >> 5, gid = lane >> 2, tig = lane & 3;
+  double *prow4 = K, *cw = K + 256, *nps = K + 512;
+  double C[4][8][2];
+  const int nrb = (n + 7) >> 3;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int r = (warp + 2 * k) * 8 + gid;
+#pragma unroll
+    for (int ct = 0; ct < 8; ++ct) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int c = (ct >> 1) * 16 + 2 * (ct & 1) + 4 * tig + e;
+        double v = (r == c) ? 1.0 : 0.0;
+        if (r < n && c < n) {
+          v = (r >= c) ? src[c * lds + r] : src[r * lds + c];
+          if (r == c && dg != nullptr) v += dg[r];
+        }
+        C[k][ct][e] = v;
+      }
+    }
+  }
+  __syncthreads();  // the source may be K itself
+  for (int p0 = 0; p0 < n; p0 += 4) {
+    const int rbp = p0 >> 3, kp = rbp >> 1, sp = p0 >> 4, up = (p0 >> 2) & 3;
+    const bool rowOwner = (warp == (rbp & 1)) && ((gid >> 2) == ((p0 >> 2) & 1));
+    const int qrow = gid & 3;
+    // [A] publish pivot rows and pivot columns
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (k == kp && rowOwner) {
+#pragma unroll
+        for (int ct = 0; ct < 8; ++ct) {
+          const int c = (ct >> 1) * 16 + 2 * (ct & 1) + 4 * tig;
+          prow4[c * 4 + qrow] = C[k][ct][0];
+          prow4[(c + 1) * 4 + qrow] = C[k][ct][1];
+        }
+      }
+    }
+    if (tig == up) {
+#pragma unroll
+      for (int s2 = 0; s2 < 4; ++s2) {
+        if (s2 == sp) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int r = (warp + 2 * k) * 8 + gid;
+            *reinterpret_cast<double2 *>(cw + 4 * r) = make_double2(C[k][2 * s2][0], C[k][2 * s2][1]);
+            *reinterpret_cast<double2 *>(cw + 4 * r + 2) = make_double2(C[k][2 * s2 + 1][0], C[k][2 * s2 + 1][1]);
+          }
+        }
+      }
+    }
+    __syncthreads();
+    // [B] E = D^-1 by an in-place scalar Gauss-Jordan on the 4x4 block, then multipliers and new pivot-row entries
+    {
+      double E[4][4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const double2 a = *reinterpret_cast<const double2 *>(prow4 + 4 * (p0 + c));
+        const double2 b = *reinterpret_cast<const double2 *>(prow4 + 4 * (p0 + c) + 2);
+        E[0][c] = a.x; E[1][c] = a.y; E[2][c] = b.x; E[3][c] = b.y;
+      }
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        const double d = 1.0 / E[p][p];
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          if (c != p) E[p][c] *= d;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          if (r == p) continue;
+          const double f = E[r][p];
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            if (c != p) E[r][c] = fma(-f, E[p][c], E[r][c]);
+          E[r][p] = -f * d;
+        }
+        E[p][p] = d;
+      }
+      const double2 pa = *reinterpret_cast<const double2 *>(prow4 + 4 * i);
+      const double2 pb = *reinterpret_cast<const double2 *>(prow4 + 4 * i + 2);
+      const double2 ca = *reinterpret_cast<const double2 *>(cw + 4 * i);
+      const double2 cb = *reinterpret_cast<const double2 *>(cw + 4 * i + 2);
+      const bool inP = (i >= p0) && (i < p0 + 4);
+      const int rp = i - p0;
+      double np[4], w[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const double epick = (rp == 0) ? E[q][0] : (rp == 1) ? E[q][1] : (rp == 2) ? E[q][2] : E[q][3];
+        np[q] = inP ? epick : (E[q][0] * pa.x + E[q][1] * pa.y + E[q][2] * pb.x + E[q][3] * pb.y);
+        w[q] = inP ? 0.0 : -(ca.x * E[0][q] + ca.y * E[1][q] + cb.x * E[2][q] + cb.y * E[3][q]);
+      }
+      *reinterpret_cast<double2 *>(nps + 4 * i) = make_double2(np[0], np[1]);
+      *reinterpret_cast<double2 *>(nps + 4 * i + 2) = make_double2(np[2], np[3]);
+      *reinterpret_cast<double2 *>(cw + 4 * i) = make_double2(w[0], w[1]);
+      *reinterpret_cast<double2 *>(cw + 4 * i + 2) = make_double2(w[2], w[3]);
+    }
+    __syncthreads();
+    // [C] trailing update on the tensor cores, then pivot columns and pivot rows
+    {
+      double af[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) af[k] = cw[((warp + 2 * k) * 8 + gid) * 4 + tig];
+#pragma unroll
+      for (int ct = 0; ct < 8; ++ct) {
+        const int J0 = (ct >> 1) * 16 + 2 * (ct & 1);
+        if (J0 < n) {
+          const double b = prow4[(J0 + 4 * (gid >> 1) + (gid & 1)) * 4 + tig];
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            if (warp + 2 * k < nrb) dmma_8x8x4(C[k][ct][0], C[k][ct][1], af[k], b);
+        }
+      }
+      if (tig == up) {
+#pragma unroll
+        for (int s2 = 0; s2 < 4; ++s2) {
+          if (s2 == sp) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int r = (warp + 2 * k) * 8 + gid;
+              const double2 wa = *reinterpret_cast<const double2 *>(cw + 4 * r);
+              const double2 wb = *reinterpret_cast<const double2 *>(cw + 4 * r + 2);
+              C[k][2 * s2][0] = wa.x; C[k][2 * s2][1] = wa.y;
+              C[k][2 * s2 + 1][0] = wb.x; C[k][2 * s2 + 1][1] = wb.y;
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (k == kp && rowOwner) {
+#pragma unroll
+          for (int ct = 0; ct < 8; ++ct) {
+            const int c = (ct >> 1) * 16 + 2 * (ct & 1) + 4 * tig;
+            C[k][ct][0] = nps[c * 4 + qrow];
+            C[k][ct][1] = nps[(c + 1) * 4 + qrow];
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int r = (warp + 2 * k) * 8 + gid;
+#pragma unroll
+    for (int ct = 0; ct < 8; ++ct) {
+      const int c = (ct >> 1) * 16 + 2 * (ct & 1) + 4 * tig;
+      K[c * LD + r] = C[k][ct][0];
+      K[(c + 1) * LD + r] = C[k][ct][1];
+    }
+  }
+  __syncthreads();
+}
+
+// In-place blocked (4 columns per step) right-looking Cholesky factorisation of the SPD matrix held in the lower triangle
+// of K (element (i, j) at K[j * LD + i], thread i owns row i).  On return the strict lower triangle holds L and the
+// diagonal holds 1 / L_ii.  n is padded to a multiple of 4 with identity rows, so there is no scalar tail.  A third of
+// the flops of the explicit Gauss-Jordan inverse spent only on the triangle that is used: the polish needs two solves
+// per round, not an inverse.   lst: [4 * blockDim] staging of the current block column, dst: [16] diagonal block.
+template <int LD>
+__device__ __noinline__ void chol_factor(double *K, int n, double *lst, double *dst) {
+  const int i = threadIdx.x;
+  const int n4 = (n + 3) & ~3;
+  if (i >= n && i < n4) {
+    for (int j = 0; j < i; ++j) K[j * LD + i] = 0.0;
+    K[i * LD + i] = 1.0;
+  }
+  for (int p0 = 0; p0 < n4; p0 += 4) {
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    const bool mine = (i >= p0) && (i < n4);
+    if (mine) {
+      a0 = K[p0 * LD + i];
+      a1 = K[(p0 + 1) * LD + i];
+      a2 = K[(p0 + 2) * LD + i];
+      a3 = K[(p0 + 3) * LD + i];
+      if (i < p0 + 4) {
+        double *d = dst + 4 * (i - p0);
+        d[0] = a0; d[1] = a1; d[2] = a2; d[3] = a3;
+      }
+    }
+    __syncthreads();
+    double x0 = 0.0, x1 = 0.0, x2 = 0.0, x3 = 0.0;
+    if (mine) {
+      const double r00 = fast_rsqrt(dst[0]);
+      const double l10 = dst[4] * r00, l20 = dst[8] * r00, l30 = dst[12] * r00;
+      const double r11 = fast_rsqrt(dst[5] - l10 * l10);
+      const double l21 = (dst[9] - l20 * l10) * r11, l31 = (dst[13] - l30 * l10) * r11;
+      const double r22 = fast_rsqrt(dst[10] - l20 * l20 - l21 * l21);
+      const double l32 = (dst[14] - l30 * l20 - l31 * l21) * r22;
+      const double r33 = fast_rsqrt(dst[15] - l30 * l30 - l31 * l31 - l32 * l32);
+      if (i >= p0 + 4) {
+        x0 = a0 * r00;
+        x1 = (a1 - x0 * l10) * r11;
+        x2 = (a2 - x0 * l20 - x1 * l21) * r22;
+        x3 = (a3 - x0 * l30 - x1 * l31 - x2 * l32) * r33;
+        K[p0 * LD + i] = x0;
+        K[(p0 + 1) * LD + i] = x1;
+        K[(p0 + 2) * LD + i] = x2;
+        K[(p0 + 3) * LD + i] = x3;
+        *reinterpret_cast<double2 *>(lst + 4 * i) = make_double2(x0, x1);
+        *reinterpret_cast<double2 *>(lst + 4 * i + 2) = make_double2(x2, x3);
+      } else {
+        const int r = i - p0;
+        if (r == 0) {
+          K[p0 * LD + i] = r00;
+        } else if (r == 1) {
+          K[p0 * LD + i] = l10;
+          K[(p0 + 1) * LD + i] = r11;
+        } else if (r == 2) {
+          K[p0 * LD + i] = l20;
+          K[(p0 + 1) * LD + i] = l21;
+          K[(p0 + 2) * LD + i] = r22;
+        } else {
+          K[p0 * LD + i] = l30;
+          K[(p0 + 1) * LD + i] = l31;
+          K[(p0 + 2) * LD + i] = l32;
+          K[(p0 + 3) * LD + i] = r33;
+        }
+      }
+    }
+    __syncthreads();
+    if (i >= p0 + 4 && i < n4) {  // trailing update of the own row, columns p0+4 .. i
+      double *Ki = K + i;
+      int j = p0 + 4;
+      for (; j + 3 <= i; j += 4) {
+        double2 la[4], lb[4];
+        double kk[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          la[u] = *reinterpret_cast<const double2 *>(lst + 4 * (j + u));
+          lb[u] = *reinterpret_cast<const double2 *>(lst + 4 * (j + u) + 2);
+          kk[u] = Ki[(j + u) * LD];
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          Ki[(j + u) * LD] = fma(-x3, lb[u].y, fma(-x2, lb[u].x, fma(-x1, la[u].y, fma(-x0, la[u].x, kk[u]))));
+      }
+      for (; j <= i; ++j) {
+        const double2 la = *reinterpret_cast<const double2 *>(lst + 4 * j);
+        const double2 lb = *reinterpret_cast<const double2 *>(lst + 4 * j + 2);
+        Ki[j * LD] = fma(-x3, lb.y, fma(-x2, lb.x, fma(-x1, la.y, fma(-x0, la.x, Ki[j * LD]))));
+      }
+    }
+  }
+  __syncthreads();
+}
+
+// x = (L L^T)^-1 b with the factor of chol_factor: blocked forward and backward substitution, 4 unknowns and one barrier
+// per step (the 4x4 diagonal solve is repeated by every thread from broadcast loads).  b and the result are per thread
+// (i < n).  yst: [8] double-buffered staging of the block right-hand side.
+template <int LD>
+__device__ __noinline__ double chol_solve(const double *K, int n, double b, double *yst) {
+  const int i = threadIdx.x;
+  const int n4 = (n + 3) & ~3;
+  double acc = (i < n) ? b : 0.0;
+  double yi = 0.0;
+  int buf = 0;
+  for (int p0 = 0; p0 < n4; p0 += 4, buf ^= 4) {
+    if (i >= p0 && i < p0 + 4) yst[buf + (i - p0)] = acc;
+    __syncthreads();
+    if (i >= p0 && i < n4) {
+      const double *c0 = K + p0 * LD + p0, *c1 = c0 + LD + 1, *c2 = c1 + LD + 1, *c3 = c2 + LD + 1;
+      const double y0 = yst[buf] * c0[0];
+      const double y1 = (yst[buf + 1] - c0[1] * y0) * c1[0];
+      const double y2 = (yst[buf + 2] - c0[2] * y0 - c1[1] * y1) * c2[0];
+      const double y3 = (yst[buf + 3] - c0[3] * y0 - c1[2] * y1 - c2[1] * y2) * c3[0];
+      if (i >= p0 + 4) {
+        acc -= K[p0 * LD + i] * y0 + K[(p0 + 1) * LD + i] * y1 + K[(p0 + 2) * LD + i] * y2 + K[(p0 + 3) * LD + i] * y3;
+      } else {
+        const int r = i - p0;
+        yi = (r == 0) ? y0 : (r == 1) ? y1 : (r == 2) ? y2 : y3;
+      }
+    }
+  }
+  acc = yi;
+  double xi = 0.0;
+  for (int p0 = n4 - 4; p0 >= 0; p0 -= 4, buf ^= 4) {
+    if (i >= p0 && i < p0 + 4) yst[buf + (i - p0)] = acc;
+    __syncthreads();
+    if (i < p0 + 4) {
+      const double *c0 = K + p0 * LD + p0, *c1 = c0 + LD + 1, *c2 = c1 + LD + 1, *c3 = c2 + LD + 1;
+      const double x3 = yst[buf + 3] * c3[0];
+      const double x2 = (yst[buf + 2] - c2[1] * x3) * c2[0];
+      const double x1 = (yst[buf + 1] - c1[1] * x2 - c1[2] * x3) * c1[0];
+      const double x0 = (yst[buf] - c0[1] * x1 - c0[2] * x2 - c0[3] * x3) * c0[0];
+      if (i < p0) {  // L[p0 + q][i] = K[i * LD + p0 + q]
+        const double *col = K + i * LD + p0;
+        acc -= col[0] * x0 + col[1] * x1 + col[2] * x2 + col[3] * x3;
+      } else {
+        const int r = i - p0;
+        xi = (r == 0) ? x0 : (r == 1) ? x1 : (r == 2) ? x2 : x3;
+      }
+    }
+  }
+  __syncthreads();
+  return xi;
+}
+
 template <int LD>
 __device__ __forceinline__ double matvec_smem(const double *K, int n, const double *v) {
   const int i = threadIdx.x;
@@ -392,7 +722,7 @@ __device__ __forceinline__ void horizon_sums(int N, int j, int l, double &cnt, d
 // ---------------------------------------------------------------------------------------------------------------
 // BS = threads per block (multiple of 32), NV = largest reduced problem the instantiation accepts (even, <= BS)
 template <int BS, int NV>
-__global__ void __launch_bounds__(BS) mpc_admm_kernel(const MpcParams P, const MpcBuffers B) {
+__global__ void __launch_bounds__(BS, (BS == 64 && !B200QP_TC_GJ) ? 5 : 1) mpc_admm_kernel(const MpcParams P, const MpcBuffers B) {
   constexpr int LD = NV + 1;
   constexpr int MAXF = NV / 3 + 1;
   extern __shared__ __align__(16) double smem[];
@@ -694,31 +1024,41 @@ __global__ void __launch_bounds__(BS) mpc_admm_kernel(const MpcParams P, const M
     bool need_factor = true;
 
     if (n == 0) status = B200QP_ACADOS_SUCCESS;
+#pragma unroll 1
     for (int attempt = 0; attempt < 5 && status != B200QP_ACADOS_SUCCESS && n > 0; ++attempt) {
       // (re)build K^-1 from the Hessian scratch when needed
       bool admm_done = false;
+#pragma unroll 1
       while (!admm_done) {
         if (need_factor) {
           __syncthreads();
-          if (act) {
-            int jx = 0;
-            for (; jx + 7 < n; jx += 8) {
-              double h[8];
+          if constexpr (BS == 64 && NV == 64 && B200QP_TC_GJ) {
+            // K = H + sigma I + rho A^T A inverted in the tensor-core accumulators straight from the Hessian scratch
+            s_xt[tid] = sigma + rho * Ei;
+            __syncthreads();
+            gj_invert_tc<LD>(Hs, BS, s_xt, K, n);
+          } else {
+            if (act) {
+              int jx = 0;
+              for (; jx + 7 < n; jx += 8) {
+                double h[8];
 #pragma unroll
-              for (int u = 0; u < 8; ++u) h[u] = __ldcg(Hs + (size_t)(jx + u) * BS + tid);
+                for (int u = 0; u < 8; ++u) h[u] = __ldcg(Hs + (size_t)(jx + u) * BS + tid);
 #pragma unroll
-              for (int u = 0; u < 8; ++u) K[(jx + u) * LD + tid] = h[u];
+                for (int u = 0; u < 8; ++u) K[(jx + u) * LD + tid] = h[u];
+              }
+              for (; jx < n; ++jx) K[jx * LD + tid] = __ldcg(Hs + (size_t)jx * BS + tid);
+              K[tid * LD + tid] += sigma + rho * Ei;
             }
-            for (; jx < n; ++jx) K[jx * LD + tid] = __ldcg(Hs + (size_t)jx * BS + tid);
-            K[tid * LD + tid] += sigma + rho * Ei;
+            __syncthreads();
+            gj_invert<LD>(K, n, prow);
           }
-          __syncthreads();
-          gj_invert<LD>(K, n, prow);
           need_factor = false;
           PH(2);
         }
         const double rinv = 1.0 / rho;
         int it_block = 0;
+#pragma unroll 1
         for (; it_block < P.check_every && iters < P.max_iter; ++it_block, ++iters) {
           if (act) {
             double w[7];
@@ -804,6 +1144,7 @@ __global__ void __launch_bounds__(BS) mpc_admm_kernel(const MpcParams P, const M
         s_actu[fa] = (unsigned short)au;
       }
       bool accepted = false;
+#pragma unroll 1
       for (int round = 0; round < P.polish_rounds && !accepted; ++round) {
         ++rounds_total;
         __syncthreads();
@@ -828,6 +1169,7 @@ __global__ void __launch_bounds__(BS) mpc_admm_kernel(const MpcParams P, const M
         __syncthreads();
         const int nr = s_foff[nf];
         PH(5);
+        constexpr bool TCP = (BS == 64 && NV == 64 && B200QP_TC_GJ);
         // hc = H c + g
         if (act) s_r[tid] = matvec_glob<BS>(Hs, n, s_c) + gi;
         // reduced Hessian Hr = Z^T H Z into K
@@ -843,6 +1185,7 @@ __global__ void __launch_bounds__(BS) mpc_admm_kernel(const MpcParams P, const M
           // 9 L2 loads per foot issued together, then up to 3 reduced entries
           for (int bq = 0; bq < nf; ++bq) {
             const int nzb = s_fnz[bq];
+            if (B200QP_CHOL_POLISH && !TCP && s_foff[bq] > tid) break;  // Cholesky only needs the lower triangle
             if (nzb == 0) continue;
             double hh[9];
 #pragma unroll
@@ -866,13 +1209,27 @@ __global__ void __launch_bounds__(BS) mpc_admm_kernel(const MpcParams P, const M
         double grp = 0.0;
         if (tid < nr) grp = vp[0] * s_r[3 * ap] + vp[1] * s_r[3 * ap + 1] + vp[2] * s_r[3 * ap + 2];
         PH(6);
-        gj_invert<LD>(K, nr, prow);
-        PH(7);
-        if (tid < nr) s_v[tid] = -grp;
-        __syncthreads();
+        constexpr bool TC = (BS == 64 && NV == 64 && B200QP_TC_GJ);
         double wred = 0.0;
-        if (tid < nr) wred = matvec_smem<LD>(K, nr, s_v);
+        if constexpr (TC) {
+          gj_invert_tc<LD>(K, LD, nullptr, K, nr);
+          PH(7);
+          if (tid < nr) s_v[tid] = -grp;
+          __syncthreads();
+          if (tid < nr) wred = matvec_smem<LD>(K, nr, s_v);
+        } else if constexpr (B200QP_CHOL_POLISH) {
+          chol_factor<LD>(K, nr, prow, red + 16);
+          PH(7);
+          wred = chol_solve<LD>(K, nr, -grp, red);
+        } else {
+          gj_invert<LD>(K, nr, prow);
+          PH(7);
+          if (tid < nr) s_v[tid] = -grp;
+          __syncthreads();
+          if (tid < nr) wred = matvec_smem<LD>(K, nr, s_v);
+        }
         double xn = 0.0;
+#pragma unroll 1
         for (int refine = 0; refine < 2; ++refine) {
           __syncthreads();
           if (tid < nr) s_w[tid] = wred;
@@ -887,9 +1244,14 @@ __global__ void __launch_bounds__(BS) mpc_admm_kernel(const MpcParams P, const M
           if (act) s_r[tid] = matvec_glob<BS>(Hs, n, s_xt) + gi;  // r = H x + g
           __syncthreads();
           if (refine == 0) {  // one step of iterative refinement on the reduced system
-            if (tid < nr) s_v[tid] = -(vp[0] * s_r[3 * ap] + vp[1] * s_r[3 * ap + 1] + vp[2] * s_r[3 * ap + 2]);
-            __syncthreads();
-            if (tid < nr) wred += matvec_smem<LD>(K, nr, s_v);
+            const double rr = (tid < nr) ? -(vp[0] * s_r[3 * ap] + vp[1] * s_r[3 * ap + 1] + vp[2] * s_r[3 * ap + 2]) : 0.0;
+            if constexpr (TC || !B200QP_CHOL_POLISH) {
+              if (tid < nr) s_v[tid] = rr;
+              __syncthreads();
+              if (tid < nr) wred += matvec_smem<LD>(K, nr, s_v);
+            } else {
+              wred += chol_solve<LD>(K, nr, rr, red);
+            }
           }
         }
         PH(8);

@@ -61,13 +61,13 @@ typedef struct b200qp_mpc_config {
   double fmin;                /* (mpc.cpp:94-115)                                                                */
   double fmax;
   /* solver options (0 => library default) */
-  double admm_rho;            /* initial ADMM penalty                                     default 1e-3          */
+  double admm_rho;            /* initial ADMM penalty                                     default 5e-5          */
   double admm_sigma;          /* ADMM proximal weight                                     default 1e-6          */
   double admm_alpha;          /* ADMM over-relaxation                                     default 1.6           */
   double admm_eps;            /* relative tolerance at which ADMM hands over to polish    default 1e-3          */
   double kkt_tol;             /* accept when all four KKT inf-norms <= kkt_tol            default 1e-7          */
   int32_t admm_max_iter;      /* total ADMM iteration cap per problem                     default 2000          */
-  int32_t admm_check_every;   /* residual check / rho adaptation interval                 default 10            */
+  int32_t admm_check_every;   /* residual check / rho adaptation interval                 default 15            */
   int32_t polish_max_rounds;  /* active-set repair sweeps per polish                      default 8             */
   int32_t ipm_max_iter;       /* Riccati IPM iteration cap                                default 40            */
 } b200qp_mpc_config;
