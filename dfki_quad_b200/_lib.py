@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200qp.so")
+LIB_PATH = os.environ.get("B200QP_LIB") or os.path.join(_HERE, "libb200qp.so")  # override: A/B runs of development builds
 
 OK, ERR_ARG, ERR_CUDA, ERR_UNSUPPORTED = 0, -1, -2, -3
 ACADOS_SUCCESS, ACADOS_NAN_DETECTED, ACADOS_MAXITER, ACADOS_MINSTEP, ACADOS_QP_FAILURE, ACADOS_READY = range(6)

@@ -43,8 +43,10 @@ def load():
     return _lib
 
 
-def make_params(N, params, eps=1e-3, polish=True, rho=0.1, max_iter=4000, kkt_tol=1e-7):
-    """OSQP 0.6.3 defaults (rho 0.1, sigma 1e-6, alpha 1.6, eps 1e-3, max_iter 4000, check every 25), polish on."""
+def make_params(N, params, eps=1e-3, polish=True, rho=3e-4, max_iter=4000, kkt_tol=1e-7):
+    """OSQP 0.6.3 defaults (sigma 1e-6, alpha 1.6, eps 1e-3, max_iter 4000, check every 25, polish on) except the initial
+    penalty: rho = 3e-4 instead of OSQP's 0.1, which on this problem family halves the iterations and saves the
+    adaptive-rho refactorisation (measured ~1.8x faster) - the CPU baseline gets the same tuning as the GPU kernel."""
     P = RefParams()
     P.N, P.dt, P.alpha, P.mu, P.fmin, P.fmax = N, params["dt"], params["alpha"], params["mu"], params["fmin"], params["fmax"]
     for i in range(12):
@@ -102,5 +104,5 @@ def time_sample(N, rec, contact, budget_s, threads=None):
         done = hi
     dt = time.perf_counter() - t0
     return dict(solved=solved, seconds=dt, cores=cores, kind="port",
-                solver="C port: full condensing + OSQP-style ADMM (eps 1e-3) + polish to KKT<=1e-7, OpenMP",
+                solver="C port: full condensing + OSQP-style ADMM (eps 1e-3, rho0 3e-4) + polish to KKT<=1e-7, OpenMP",
                 sample=f"first {done} of {n} problems of the same batch, {cores} threads")
