@@ -423,7 +423,9 @@ def run_b200_wbc(args):
     info = np.frombuffer(dinfo.cpu().numpy().tobytes(), dtype=np.dtype(
         [("status", "i4"), ("iterations", "i4"), ("polish_rounds", "i4"), ("n_free", "i4"), ("kkt", "f8", (4,))]))
     conv = (info["status"] == 0) & (info["kkt"].max(axis=1) <= KKT_TOL)
-    xh = np.zeros((B, 30))
+    # e2e: page-locked host buffers (the contract's "pinned host memory"), so the library DMAs straight from / into them
+    H, g, A, lo, hi = (torch.from_numpy(a).pin_memory().numpy() for a in (H, g, A, lo, hi))
+    xh = torch.zeros((B, 30), dtype=torch.float64).pin_memory().numpy()
     solver.solve_abi(H, g, A, lo, hi, xh)
     barrier()
     t0 = time.perf_counter()

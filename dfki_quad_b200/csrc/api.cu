@@ -702,10 +702,11 @@ int32_t b200qp_gait_schedule(int32_t device, int32_t n, int32_t steps, double dt
 struct b200qp_wbc {
   b200qp_wbc_config cfg;
   WbcParams P;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr, copy_stream = nullptr;
+  cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   int grid = 0;
   double *d_H = nullptr, *d_g = nullptr, *d_A = nullptr, *d_lo = nullptr, *d_hi = nullptr, *d_x = nullptr;
-  b200qp_solver_info *d_info = nullptr;
+  b200qp_solver_info *d_info = nullptr, *h_info = nullptr;
   int *d_next = nullptr;
 };
 
@@ -743,6 +744,9 @@ int32_t b200qp_wbc_create(const b200qp_wbc_config *cfg, b200qp_wbc **out) {
   }
   const size_t nb = cfg->max_batch, nq = cfg->nq, nc = cfg->neq + cfg->nin;
   CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+  for (int c = 0; c < 8; ++c) CK(cudaEventCreateWithFlags(&h->ev[c], cudaEventDisableTiming));
+  CK(cudaMallocHost(&h->h_info, (size_t)cfg->max_batch * sizeof(b200qp_solver_info)));
   CK(cudaMalloc(&h->d_H, nb * nq * nq * sizeof(double)));
   CK(cudaMalloc(&h->d_g, nb * nq * sizeof(double)));
   CK(cudaMalloc(&h->d_A, nb * nc * nq * sizeof(double)));
@@ -766,6 +770,10 @@ void b200qp_wbc_destroy(b200qp_wbc *h) {
   cudaFree(h->d_x);
   cudaFree(h->d_info);
   cudaFree(h->d_next);
+  cudaFreeHost(h->h_info);
+  for (int c = 0; c < 8; ++c)
+    if (h->ev[c]) cudaEventDestroy(h->ev[c]);
+  if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
 }
@@ -790,17 +798,32 @@ int32_t b200qp_wbc_solve_batch(b200qp_wbc *h, int32_t n, const double *H, const 
   if (n == 0) return B200QP_OK;
   CK(cudaSetDevice(h->cfg.device));
   const size_t nn = n, nq = h->cfg.nq, nc = h->cfg.neq + h->cfg.nin;
-  CK(cudaMemcpyAsync(h->d_H, H, nn * nq * nq * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-  CK(cudaMemcpyAsync(h->d_g, g, nn * nq * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-  CK(cudaMemcpyAsync(h->d_A, A, nn * nc * nq * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-  CK(cudaMemcpyAsync(h->d_lo, lower_y, nn * nc * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-  CK(cudaMemcpyAsync(h->d_hi, upper_y, nn * nc * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-  CK(cudaMemcpyAsync(h->d_x, x, nn * nq * sizeof(double), cudaMemcpyHostToDevice, h->stream));  // keep caller's x on failure
-  int32_t rc = b200qp_wbc_solve_batch_device(h, n, h->d_H, h->d_g, h->d_A, h->d_lo, h->d_hi, h->d_x, h->d_info, 0);
-  if (rc != B200QP_OK) return rc;
+  // Large batches are cut into chunks: the H2D copy of chunk c+1 (19.5 KB per QP - this call is PCIe-bound) runs on the
+  // copy stream while chunk c is being solved; results go back per chunk behind its kernel.
+  const int chunks = (n >= 8192) ? 4 : (n >= 2048 ? 2 : 1);
+  for (int c = 0; c < chunks; ++c) {  // all copies are queued first: a D2H into pageable memory would block the host
+    const size_t lo = nn * c / chunks, hi = nn * (c + 1) / chunks, m = hi - lo;
+    if (m == 0) continue;
+    CK(cudaMemcpyAsync(h->d_H + lo * nq * nq, H + lo * nq * nq, m * nq * nq * sizeof(double), cudaMemcpyHostToDevice, h->copy_stream));
+    CK(cudaMemcpyAsync(h->d_g + lo * nq, g + lo * nq, m * nq * sizeof(double), cudaMemcpyHostToDevice, h->copy_stream));
+    CK(cudaMemcpyAsync(h->d_A + lo * nc * nq, A + lo * nc * nq, m * nc * nq * sizeof(double), cudaMemcpyHostToDevice, h->copy_stream));
+    CK(cudaMemcpyAsync(h->d_lo + lo * nc, lower_y + lo * nc, m * nc * sizeof(double), cudaMemcpyHostToDevice, h->copy_stream));
+    CK(cudaMemcpyAsync(h->d_hi + lo * nc, upper_y + lo * nc, m * nc * sizeof(double), cudaMemcpyHostToDevice, h->copy_stream));
+    CK(cudaMemcpyAsync(h->d_x + lo * nq, x + lo * nq, m * nq * sizeof(double), cudaMemcpyHostToDevice, h->copy_stream));  // keep caller's x on failure
+    CK(cudaEventRecord(h->ev[c], h->copy_stream));
+  }
+  for (int c = 0; c < chunks; ++c) {
+    const size_t lo = nn * c / chunks, hi = nn * (c + 1) / chunks, m = hi - lo;
+    if (m == 0) continue;
+    CK(cudaStreamWaitEvent(h->stream, h->ev[c], 0));
+    CK(cudaMemsetAsync(h->d_next, 0, sizeof(int), h->stream));
+    CK(launch_wbc_qp(h->P, (int)m, h->d_H + lo * nq * nq, h->d_g + lo * nq, h->d_A + lo * nc * nq, h->d_lo + lo * nc, h->d_hi + lo * nc,
+                     h->d_x + lo * nq, h->d_info + lo, h->d_next, h->grid, h->stream));
+    CK(cudaMemcpyAsync(h->h_info + lo, h->d_info + lo, m * sizeof(b200qp_solver_info), cudaMemcpyDeviceToHost, h->stream));
+  }
   CK(cudaMemcpyAsync(x, h->d_x, nn * nq * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-  CK(cudaMemcpyAsync(info, h->d_info, nn * sizeof(b200qp_solver_info), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
+  memcpy(info, h->h_info, nn * sizeof(b200qp_solver_info));
   return B200QP_OK;
 }
 
