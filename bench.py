@@ -29,7 +29,7 @@ WORKLOADS = {
                     seed=20261019 + 2, kernel="mpc_admm_kernel<64,64>"),
     "config3": dict(name="go2_mixed_sparse_mpc_h16_riccati", horizon=16, batch=16384, gaits=("TROT", "PACE", "BOUND"),
                     solver="SPARSE_RICCATI", seed=20261019 + 3, kernel="mpc_riccati_kernel<64>"),
-    "config5": dict(name="go2_1M_mixed_sweep_sharded", horizon=0, batch=1048576, gaits=(), solver="ADMM(N=10 trot) + RICCATI(N=16 mixed)",
+    "config5": dict(name="go2_1M_mixed_sweep_sharded", horizon=0, batch=1048576, gaits=(), solver="ADMM(N=10 trot) + AUTO(N=16 mixed: condensed kernel where n <= 156, Riccati otherwise)",
                     seed=20261019 + 5, kernel="mpc_admm_kernel<64,64> + mpc_riccati_kernel<64>"),
     "config4": dict(name="go2_wbc_reduced_tsid_qp", horizon=10, batch=16384, gaits=("TROT",), solver="WBC_DENSE_IPM",
                     seed=20261019 + 4, kernel="wbc_qp_kernel"),
@@ -498,7 +498,7 @@ def run_b200_sweep(args):
     chunk = 32768
     cfg = sequencer.GO2_MPC
     parts = []
-    for tag, N, gaits, solver, seed in (("admm", 10, ("TROT",), "CONDENSED_ADMM", wl["seed"]), ("riccati", 16, ("TROT", "PACE", "BOUND"), "SPARSE_RICCATI", wl["seed"] + 1)):
+    for tag, N, gaits, solver, seed in (("admm", 10, ("TROT",), "CONDENSED_ADMM", wl["seed"]), ("auto16", 16, ("TROT", "PACE", "BOUND"), "AUTO", wl["seed"] + 1)):
         b = sequencer.random_batch(chunk, N, seed=seed + 1000 * rank, gaits=gaits, device=dev)
         mpc = BatchedMPC(cfg["alpha"], cfg["state_weights_move"], cfg["mu"], cfg["fmin"], cfg["fmax"], solver, horizon=N, dt=cfg["dt"],
                          max_batch=chunk, device=dev)
@@ -555,7 +555,7 @@ def run_b200_sweep(args):
         dist.all_reduce(stats, op=dist.ReduceOp.MAX)
         dist.all_reduce(counts, op=dist.ReduceOp.SUM)
     if rank == 0:
-        line = {"metric": "MPC QP solves/sec (Go2, 1M-problem mixed sweep: horizon 10 condensed ADMM + horizon 16 sparse Riccati)",
+        line = {"metric": "MPC QP solves/sec (Go2, 1M-problem mixed sweep: horizon 10 trot + horizon 16 mixed gaits, solver AUTO)",
                 "value": counts[0].item() / (stats[0].item() * 1e-3), "unit": "solves/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": stats[0].item() / args.steps, "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",

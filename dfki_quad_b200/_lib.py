@@ -11,8 +11,8 @@ LIB_PATH = os.environ.get("B200QP_LIB") or os.path.join(_HERE, "libb200qp.so")  
 OK, ERR_ARG, ERR_CUDA, ERR_UNSUPPORTED = 0, -1, -2, -3
 ACADOS_SUCCESS, ACADOS_NAN_DETECTED, ACADOS_MAXITER, ACADOS_MINSTEP, ACADOS_QP_FAILURE, ACADOS_READY = range(6)
 NAN_AFTER_SUCCESS = -7777
-SOLVER_CONDENSED_ADMM, SOLVER_SPARSE_RICCATI = 0, 1
-SOLVERS = {"CONDENSED_ADMM": 0, "SPARSE_RICCATI": 1,
+SOLVER_CONDENSED_ADMM, SOLVER_SPARSE_RICCATI, SOLVER_AUTO = 0, 1, 2
+SOLVERS = {"CONDENSED_ADMM": 0, "SPARSE_RICCATI": 1, "AUTO": 2,
            # the reference's acados plan names (mit_controller_node.cpp:502-519) map onto the two kernels
            "PARTIAL_CONDENSING_OSQP": 0, "FULL_CONDENSING_HPIPM": 0, "FULL_CONDENSING_QPOASES": 0,
            "FULL_CONDENSING_DAQP": 0, "PARTIAL_CONDENSING_HPIPM": 1}

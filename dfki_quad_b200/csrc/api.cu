@@ -13,14 +13,15 @@ cudaError_t launch_gait_schedule(int n, int steps, double dt, const double *peri
                                  double fmax, uint8_t *contact, double *swing_time, double *lbu, double *ubu,
                                  cudaStream_t st);
 cudaError_t launch_mpc_bin(int n, int N, const uint8_t *contact, int *bin_count, int *bin_lists,
-                           b200qp_solver_info *info, cudaStream_t st);
+                           b200qp_solver_info *info, int overflow_bin, cudaStream_t st);
 cudaError_t launch_mpc_admm(int bin, const MpcParams &P, const MpcBuffers &B, int grid, cudaStream_t st);
 int admm_block_size(int bin);
 cudaError_t fp64_peak(int num_sms, double *tflops);
 int admm_occupancy(int bin);
 cudaError_t launch_mpc_riccati(const MpcParams &P, int n, const double *in, const uint8_t *contact, double *forces,
                                double *xpred, b200qp_solver_info *info, double *lam_box, double *lam_g, double *scratch,
-                               int *next, int grid, cudaStream_t st, long long *dbg_cycles);
+                               int *next, int grid, cudaStream_t st, long long *dbg_cycles, const int *list,
+                               const int *list_count);
 int riccati_grid(int num_sms, int horizon);
 struct SeqModel {
   double mass, inertia[9], com[3], shoulders[12], raibert_k, raibert_g, max_leg_length, dt;
@@ -150,7 +151,8 @@ int32_t b200qp_mpc_create(const b200qp_mpc_config *cfg, b200qp_mpc **out) {
     g_err = "b200qp_mpc_create: invalid configuration";
     return B200QP_ERR_ARG;
   }
-  if (cfg->solver != B200QP_SOLVER_CONDENSED_ADMM && cfg->solver != B200QP_SOLVER_SPARSE_RICCATI) {
+  if (cfg->solver != B200QP_SOLVER_CONDENSED_ADMM && cfg->solver != B200QP_SOLVER_SPARSE_RICCATI &&
+      cfg->solver != B200QP_SOLVER_AUTO) {
     g_err = "b200qp_mpc_create: unknown solver";
     return B200QP_ERR_ARG;
   }
@@ -182,10 +184,10 @@ int32_t b200qp_mpc_create(const b200qp_mpc_config *cfg, b200qp_mpc **out) {
   CK(cudaMalloc(&h->d_lam_g, nb * N * 16 * sizeof(double)));
   CK(cudaMalloc(&h->d_info, nb * sizeof(b200qp_solver_info)));
   CK(cudaMalloc(&h->d_bin_count, 8 * sizeof(int)));
-  CK(cudaMalloc(&h->d_bin_lists, 3 * nb * sizeof(int)));
+  CK(cudaMalloc(&h->d_bin_lists, 4 * nb * sizeof(int)));
   CK(cudaMemset(h->d_forces, 0, nb * N * 12 * sizeof(double)));
   CK(cudaMemset(h->d_xpred, 0, nb * (N + 1) * 13 * sizeof(double)));
-  if (cfg->solver == B200QP_SOLVER_CONDENSED_ADMM) {
+  if (cfg->solver != B200QP_SOLVER_SPARSE_RICCATI) {
     for (int b = 0; b < 3; ++b) {
       const int bs = admm_block_size(b);
       int g = h->num_sms * admm_occupancy(b);
@@ -195,7 +197,7 @@ int32_t b200qp_mpc_create(const b200qp_mpc_config *cfg, b200qp_mpc **out) {
       CK(cudaMalloc(&h->d_hscratch[b], (size_t)g * ((size_t)bs * bs + B200QP_MAX_HORIZON * 36) * sizeof(double)));
     }
   }
-  if (cfg->solver == B200QP_SOLVER_SPARSE_RICCATI) {
+  if (cfg->solver != B200QP_SOLVER_CONDENSED_ADMM) {
     int g = riccati_grid(h->num_sms, cfg->horizon);
     if ((size_t)g > nb) g = (int)nb;
     h->ric_grid = g;
@@ -277,9 +279,11 @@ static int32_t solve_device_impl(b200qp_mpc *h, int32_t n, const double *d_in, c
   const int N = h->cfg.horizon;
   int launches = 0;
   CK(cudaEventRecord(h->ev0, h->stream));
-  if (h->cfg.solver == B200QP_SOLVER_CONDENSED_ADMM) {
-    CK(cudaMemsetAsync(h->d_bin_count, 0, 8 * sizeof(int), h->stream));
-    CK(launch_mpc_bin(n, N, d_contact, h->d_bin_count, h->d_bin_lists, d_info, h->stream));
+  CK(cudaMemsetAsync(h->d_bin_count, 0, 8 * sizeof(int), h->stream));
+  const bool use_admm = h->cfg.solver != B200QP_SOLVER_SPARSE_RICCATI;
+  const bool autosel = h->cfg.solver == B200QP_SOLVER_AUTO;
+  if (use_admm) {
+    CK(launch_mpc_bin(n, N, d_contact, h->d_bin_count, h->d_bin_lists, d_info, autosel ? 1 : 0, h->stream));
     ++launches;
     for (int b = 0; b < 3; ++b) {
       MpcBuffers B;
@@ -303,11 +307,12 @@ static int32_t solve_device_impl(b200qp_mpc *h, int32_t n, const double *d_in, c
       CK(launch_mpc_admm(b, h->P, B, g, h->stream));
       ++launches;
     }
-  } else {
-    CK(cudaMemsetAsync(h->d_bin_count, 0, 8 * sizeof(int), h->stream));
+  }
+  if (!use_admm || autosel) {  // whole batch, or (AUTO) the list of problems too large for the condensed kernel
     CK(launch_mpc_riccati(h->P, n, d_in, d_contact, d_forces, d_xpred, d_info,
                           h->want_duals ? h->d_lam_box : nullptr, h->want_duals ? h->d_lam_g : nullptr,
-                          h->d_ric_scratch, h->d_bin_count + 7, h->ric_grid, h->stream, h->d_dbg_cycles));
+                          h->d_ric_scratch, h->d_bin_count + 7, h->ric_grid, h->stream, h->d_dbg_cycles,
+                          autosel ? h->d_bin_lists + (size_t)3 * n : nullptr, autosel ? h->d_bin_count + 3 : nullptr));
     ++launches;
   }
   CK(cudaEventRecord(h->ev1, h->stream));
@@ -554,7 +559,7 @@ int32_t b200qp_mpc_get_duals(b200qp_mpc *h, int32_t n, double *lam_box, double *
 
 int32_t b200qp_mpc_get_condensed(b200qp_mpc *h, int32_t index, double *H, int32_t ldh, double *g) {
   if (!h || !H || !g || index < 0 || index >= h->last_n || !h->last_in) return B200QP_ERR_ARG;
-  if (h->cfg.solver != B200QP_SOLVER_CONDENSED_ADMM) return B200QP_ERR_UNSUPPORTED;
+  if (h->cfg.solver == B200QP_SOLVER_SPARSE_RICCATI) return B200QP_ERR_UNSUPPORTED;
   CK(cudaSetDevice(h->cfg.device));
   const int N = h->cfg.horizon;
   const size_t in_d = (size_t)b200qp_mpc_in_doubles(N);

@@ -1469,7 +1469,7 @@ __global__ void __launch_bounds__(BS, (BS == 64 && !B200QP_TC_GJ) ? 5 : 1) mpc_a
 // ---------------------------------------------------------------------------------------------------------------
 // binning by reduced problem size
 __global__ void mpc_bin_kernel(int n, int N, const uint8_t *__restrict__ contact, int *bin_count, int *bin_lists,
-                               b200qp_solver_info *info) {
+                               b200qp_solver_info *info, int overflow_bin) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n) return;
   const uint8_t *ct = contact + (size_t)p * N * 4;
@@ -1481,7 +1481,7 @@ __global__ void mpc_bin_kernel(int n, int N, const uint8_t *__restrict__ contact
   else if (nv <= 128) bin = 1;
   else if (nv <= 156) bin = 2;
   else bin = 3;
-  if (bin == 3) {
+  if (bin == 3 && !overflow_bin) {
     b200qp_solver_info inf = {B200QP_ACADOS_QP_FAILURE, 0, 0, nv, {0, 0, 0, 0}};
     info[p] = inf;
     return;
@@ -1521,8 +1521,8 @@ int admm_occupancy(int bin) {
 int admm_block_size(int bin) { return bin == 0 ? 64 : bin == 1 ? 128 : 160; }
 
 cudaError_t launch_mpc_bin(int n, int N, const uint8_t *contact, int *bin_count, int *bin_lists,
-                           b200qp_solver_info *info, cudaStream_t st) {
-  mpc_bin_kernel<<<(n + 127) / 128, 128, 0, st>>>(n, N, contact, bin_count, bin_lists, info);
+                           b200qp_solver_info *info, int overflow_bin, cudaStream_t st) {
+  mpc_bin_kernel<<<(n + 127) / 128, 128, 0, st>>>(n, N, contact, bin_count, bin_lists, info, overflow_bin);
   return cudaGetLastError();
 }
 

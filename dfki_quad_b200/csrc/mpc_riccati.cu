@@ -64,7 +64,8 @@ __global__ void __launch_bounds__(BS, MINB) mpc_riccati_kernel(const MpcParams P
                                                          const uint8_t *__restrict__ contact, double *__restrict__ forces,
                                                          double *__restrict__ xpred, b200qp_solver_info *__restrict__ info,
                                                          double *__restrict__ lam_box, double *__restrict__ lam_g,
-                                                         double *__restrict__ scratch, int *next, long long *dbg_cycles) {
+                                                         double *__restrict__ scratch, int *next, long long *dbg_cycles,
+                                                         const int *__restrict__ list, const int *__restrict__ list_count) {
   constexpr int NS = 12;  // controllable state dimension (the 13th state is the constant g, mpc.cpp:396)
   __shared__ double sP[144], sPn[144], sT[144], sPB[144], sHuu[144], sHux[144];
   __shared__ double sKbuf[288], sLi[144];
@@ -89,8 +90,9 @@ __global__ void __launch_bounds__(BS, MINB) mpc_riccati_kernel(const MpcParams P
     __syncthreads();
     if (tid == 0) sSlot = atomicAdd(next, 1);
     __syncthreads();
-    const int prob = sSlot;
-    if (prob >= nprob) break;
+    // work list (solver AUTO: the problems too large for the condensed kernel) or the whole batch
+    if (sSlot >= (list != nullptr ? *list_count : nprob)) break;
+    const int prob = list != nullptr ? list[sSlot] : sSlot;
     const double *rec = in + (size_t)prob * P.in_stride;
     const uint8_t *ct = contact + (size_t)prob * N * 4;
     const double mass = rec[13], dm = dt / mass;
@@ -733,14 +735,14 @@ int riccati_grid(int num_sms, int horizon) {
 
 cudaError_t launch_mpc_riccati(const MpcParams &P, int n, const double *in, const uint8_t *contact, double *forces,
                                double *xpred, b200qp_solver_info *info, double *lam_box, double *lam_g, double *scratch,
-                               int *next, int grid, cudaStream_t st, long long *dbg_cycles) {
+                               int *next, int grid, cudaStream_t st, long long *dbg_cycles, const int *list, const int *list_count) {
   if (grid > n) grid = n;
   if (P.N <= 10)
-    mpc_riccati_kernel<64, 10, 8><<<grid, 64, 0, st>>>(P, n, in, contact, forces, xpred, info, lam_box, lam_g, scratch, next, dbg_cycles);
+    mpc_riccati_kernel<64, 10, 8><<<grid, 64, 0, st>>>(P, n, in, contact, forces, xpred, info, lam_box, lam_g, scratch, next, dbg_cycles, list, list_count);
   else if (P.N <= 16)
-    mpc_riccati_kernel<64, 16, 6><<<grid, 64, 0, st>>>(P, n, in, contact, forces, xpred, info, lam_box, lam_g, scratch, next, dbg_cycles);
+    mpc_riccati_kernel<64, 16, 6><<<grid, 64, 0, st>>>(P, n, in, contact, forces, xpred, info, lam_box, lam_g, scratch, next, dbg_cycles, list, list_count);
   else
-    mpc_riccati_kernel<96, 20, 3><<<grid, 96, 0, st>>>(P, n, in, contact, forces, xpred, info, lam_box, lam_g, scratch, next, dbg_cycles);
+    mpc_riccati_kernel<96, 20, 3><<<grid, 96, 0, st>>>(P, n, in, contact, forces, xpred, info, lam_box, lam_g, scratch, next, dbg_cycles, list, list_count);
   return cudaGetLastError();
 }
 

@@ -4,7 +4,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 from dfki_quad_b200 import BatchedMPC, sequencer
 cfg = sequencer.GO2_MPC
-N, n = 10, 4096
+N, n = int(os.environ.get("HORIZON", "10")), int(os.environ.get("BATCH", "4096"))
 GAITS = tuple(os.environ.get("GAITS", "TROT").split(","))
 b = sequencer.random_batch(n, N, seed=20261021, gaits=GAITS)
 grid = list(itertools.product([1e-3, 3e-4, 1e-4, 3e-5], [5, 10], [1e-3, 3e-3]))

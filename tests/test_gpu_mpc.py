@@ -357,6 +357,37 @@ def test_riccati_matches_admm(go2_params):
     assert np.abs(xa - xr).max() <= 1e-5
 
 
+def test_auto_solver_dispatches_by_reduced_size(go2_params):
+    """Solver AUTO: problems whose reduced size fits go to the condensed kernel, the rest (N = 16 all-stance, n = 192) to the
+    Riccati kernel; every problem is solved and agrees with the single-kernel handles."""
+    from dfki_quad_b200 import sequencer
+
+    N, n = 16, 512
+    batch = sequencer.random_batch(n, N, seed=78, gaits=("TROT", "STAND", "STATIC_WALK", "BOUND"))
+    nfree = 3 * batch["contact"].reshape(n, -1).sum(axis=1)
+    assert (nfree > 156).any() and (nfree <= 128).any()
+    auto = _mpc(N, n, solver="AUTO")
+    fa, xa, ia = auto.solve_records(batch["rec"], batch["contact"])
+    lam_box, lam_g = auto.get_duals(n)
+    assert ia.success.all(), np.unique(ia.return_code, return_counts=True)
+    assert np.all(ia.kkt.max(axis=1) <= 1e-6)
+    fr, xr, ir = _mpc(N, n, solver="SPARSE_RICCATI").solve_records(batch["rec"], batch["contact"])
+    fc, xc, ic = _mpc(N, n).solve_records(batch["rec"], batch["contact"])
+    assert ir.success.all()
+    assert (ic.return_code[nfree > 156] == 4).all() and ic.success[nfree <= 156].all()  # condensed alone cannot take them
+    scale = np.maximum(1.0, np.abs(fr).reshape(n, -1).max(axis=1))
+    assert (np.abs(fa - fr).reshape(n, -1).max(axis=1) / scale).max() <= 1e-5
+    small = nfree <= 156
+    assert np.array_equal(fa[small], fc[small])  # same kernel, same bits
+    # polish rounds are only reported by the condensed kernel: the dispatch is visible in the info records
+    assert (ia.polish_rounds[~small] == 0).all() and (ia.polish_rounds[small & (nfree > 0)] >= 1).all()
+    params = dict(go2_params, weights=go2_params["w_move"])
+    for p in list(np.nonzero(~small)[0][:2]) + list(np.nonzero(small)[0][:2]):
+        U, X, qp, _ = mo.solve_reference_qp(N, batch["rec"][p], batch["contact"][p], params)
+        assert np.abs(fa[p].reshape(N, 12) - U).max() / max(1.0, np.abs(U).max()) <= 1e-5
+        assert max(mo.kkt_residuals(qp, fa[p].reshape(N, 12), lam_box[p], lam_g[p])) <= 1e-6  # with the solver's own duals
+
+
 def test_config3_full_batch_riccati(go2_params):
     """BASELINE.json configs[2]: 16384 mixed trot/pace/bound problems, N = 16, sparse Riccati kernel."""
     from dfki_quad_b200 import sequencer
