@@ -59,16 +59,18 @@ struct b200qp_mpc {
   b200qp_mpc_config cfg;
   MpcParams P;
   cudaStream_t stream = nullptr;
+  cudaStream_t bin_stream[4] = {nullptr, nullptr, nullptr, nullptr};  // bins 1..3 and the Riccati overflow run beside bin 0
+  cudaEvent_t ev_fork = nullptr, ev_join[4] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   int num_sms = 0;
   // device buffers sized for max_batch
   double *d_in = nullptr, *d_forces = nullptr, *d_xpred = nullptr, *d_lam_box = nullptr, *d_lam_g = nullptr;
   uint8_t *d_contact = nullptr;
   b200qp_solver_info *d_info = nullptr;
-  int *d_bin_count = nullptr;  // [4] counts + [4] next
-  int *d_bin_lists = nullptr;  // [3][max_batch]
-  double *d_hscratch[3] = {nullptr, nullptr, nullptr};
-  int grid[3] = {0, 0, 0};
+  int *d_bin_count = nullptr;  // [5] counts (4 condensed bins + overflow), [5..8] condensed work counters, [9] Riccati counter
+  int *d_bin_lists = nullptr;  // [5][max_batch]
+  double *d_hscratch[4] = {nullptr, nullptr, nullptr, nullptr};
+  int grid[4] = {0, 0, 0, 0};
   double *d_ric_scratch = nullptr;
   int ric_grid = 0;
   // pinned staging
@@ -176,6 +178,11 @@ int32_t b200qp_mpc_create(const b200qp_mpc_config *cfg, b200qp_mpc **out) {
   CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   CK(cudaEventCreate(&h->ev0));
   CK(cudaEventCreate(&h->ev1));
+  CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+  for (int b = 0; b < 4; ++b) {
+    CK(cudaStreamCreateWithFlags(&h->bin_stream[b], cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&h->ev_join[b], cudaEventDisableTiming));
+  }
   CK(cudaMalloc(&h->d_in, nb * in_d * sizeof(double)));
   CK(cudaMalloc(&h->d_contact, nb * N * 4));
   CK(cudaMalloc(&h->d_forces, nb * N * 12 * sizeof(double)));
@@ -183,12 +190,12 @@ int32_t b200qp_mpc_create(const b200qp_mpc_config *cfg, b200qp_mpc **out) {
   CK(cudaMalloc(&h->d_lam_box, nb * N * 12 * sizeof(double)));
   CK(cudaMalloc(&h->d_lam_g, nb * N * 16 * sizeof(double)));
   CK(cudaMalloc(&h->d_info, nb * sizeof(b200qp_solver_info)));
-  CK(cudaMalloc(&h->d_bin_count, 8 * sizeof(int)));
-  CK(cudaMalloc(&h->d_bin_lists, 4 * nb * sizeof(int)));
+  CK(cudaMalloc(&h->d_bin_count, 16 * sizeof(int)));
+  CK(cudaMalloc(&h->d_bin_lists, 5 * nb * sizeof(int)));
   CK(cudaMemset(h->d_forces, 0, nb * N * 12 * sizeof(double)));
   CK(cudaMemset(h->d_xpred, 0, nb * (N + 1) * 13 * sizeof(double)));
   if (cfg->solver != B200QP_SOLVER_SPARSE_RICCATI) {
-    for (int b = 0; b < 3; ++b) {
+    for (int b = 0; b < 4; ++b) {
       const int bs = admm_block_size(b);
       int g = h->num_sms * admm_occupancy(b);
       if (const char *e = getenv("B200QP_BLOCKS_PER_SM")) g = h->num_sms * (atoi(e) > 0 ? atoi(e) : 1);  // development
@@ -232,7 +239,7 @@ void b200qp_mpc_destroy(b200qp_mpc *h) {
   cudaFree(h->d_info);
   cudaFree(h->d_bin_count);
   cudaFree(h->d_bin_lists);
-  for (int b = 0; b < 3; ++b) cudaFree(h->d_hscratch[b]);
+  for (int b = 0; b < 4; ++b) cudaFree(h->d_hscratch[b]);
   cudaFree(h->d_ric_scratch);
   cudaFreeHost(h->h_in);
   cudaFreeHost(h->h_contact);
@@ -242,6 +249,11 @@ void b200qp_mpc_destroy(b200qp_mpc *h) {
   cudaFree(h->d_seq);
   cudaFree(h->d_measured);
   cudaFreeHost(h->h_seq);
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  for (int b = 0; b < 4; ++b) {
+    if (h->ev_join[b]) cudaEventDestroy(h->ev_join[b]);
+    if (h->bin_stream[b]) cudaStreamDestroy(h->bin_stream[b]);
+  }
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -279,13 +291,18 @@ static int32_t solve_device_impl(b200qp_mpc *h, int32_t n, const double *d_in, c
   const int N = h->cfg.horizon;
   int launches = 0;
   CK(cudaEventRecord(h->ev0, h->stream));
-  CK(cudaMemsetAsync(h->d_bin_count, 0, 8 * sizeof(int), h->stream));
+  CK(cudaMemsetAsync(h->d_bin_count, 0, 16 * sizeof(int), h->stream));
   const bool use_admm = h->cfg.solver != B200QP_SOLVER_SPARSE_RICCATI;
   const bool autosel = h->cfg.solver == B200QP_SOLVER_AUTO;
+  // The size bins (and the Riccati overflow list) are independent launches: bin 0 stays on the handle's stream, the others
+  // fork onto their own streams after the binning kernel and join before the end event, so their tails overlap instead of
+  // adding up (their persistent grids are sized for a whole GPU each; the hardware interleaves the resident blocks).
+  bool forked[4] = {false, false, false, false};
   if (use_admm) {
     CK(launch_mpc_bin(n, N, d_contact, h->d_bin_count, h->d_bin_lists, d_info, autosel ? 1 : 0, h->stream));
     ++launches;
-    for (int b = 0; b < 3; ++b) {
+    CK(cudaEventRecord(h->ev_fork, h->stream));
+    for (int b = 0; b < 4; ++b) {
       MpcBuffers B;
       B.in = d_in;
       B.contact = d_contact;
@@ -296,7 +313,7 @@ static int32_t solve_device_impl(b200qp_mpc *h, int32_t n, const double *d_in, c
       B.lam_g = h->want_duals ? h->d_lam_g : nullptr;
       B.bin_list = h->d_bin_lists + (size_t)b * n;
       B.bin_count = h->d_bin_count + b;
-      B.bin_next = h->d_bin_count + 4 + b;
+      B.bin_next = h->d_bin_count + 5 + b;
       B.hscratch = h->d_hscratch[b];
       B.dbg_index = dbg_index;
       B.dbg_H = dbg_H;
@@ -304,17 +321,34 @@ static int32_t solve_device_impl(b200qp_mpc *h, int32_t n, const double *d_in, c
       B.dbg_cycles = h->d_dbg_cycles;
       int g = h->grid[b];
       if (g > n) g = n;
-      CK(launch_mpc_admm(b, h->P, B, g, h->stream));
+      cudaStream_t st = h->stream;
+      if (b > 0) {
+        st = h->bin_stream[b - 1];
+        CK(cudaStreamWaitEvent(st, h->ev_fork, 0));
+        forked[b - 1] = true;
+      }
+      CK(launch_mpc_admm(b, h->P, B, g, st));
       ++launches;
     }
   }
   if (!use_admm || autosel) {  // whole batch, or (AUTO) the list of problems too large for the condensed kernel
+    cudaStream_t st = h->stream;
+    if (autosel) {
+      st = h->bin_stream[3];
+      CK(cudaStreamWaitEvent(st, h->ev_fork, 0));
+      forked[3] = true;
+    }
     CK(launch_mpc_riccati(h->P, n, d_in, d_contact, d_forces, d_xpred, d_info,
                           h->want_duals ? h->d_lam_box : nullptr, h->want_duals ? h->d_lam_g : nullptr,
-                          h->d_ric_scratch, h->d_bin_count + 7, h->ric_grid, h->stream, h->d_dbg_cycles,
-                          autosel ? h->d_bin_lists + (size_t)3 * n : nullptr, autosel ? h->d_bin_count + 3 : nullptr));
+                          h->d_ric_scratch, h->d_bin_count + 9, h->ric_grid, st, h->d_dbg_cycles,
+                          autosel ? h->d_bin_lists + (size_t)4 * n : nullptr, autosel ? h->d_bin_count + 4 : nullptr));
     ++launches;
   }
+  for (int b = 0; b < 4; ++b)
+    if (forked[b]) {
+      CK(cudaEventRecord(h->ev_join[b], h->bin_stream[b]));
+      CK(cudaStreamWaitEvent(h->stream, h->ev_join[b], 0));
+    }
   CK(cudaEventRecord(h->ev1, h->stream));
   h->have_timing = true;
   h->last_launches = launches;

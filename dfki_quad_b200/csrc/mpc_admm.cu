@@ -722,19 +722,19 @@ __device__ __forceinline__ void horizon_sums(int N, int j, int l, double &cnt, d
 // ---------------------------------------------------------------------------------------------------------------
 // BS = threads per block (multiple of 32), NV = largest reduced problem the instantiation accepts (even, <= BS)
 template <int BS, int NV>
-__global__ void __launch_bounds__(BS, (BS == 64 && !B200QP_TC_GJ) ? 5 : 1) mpc_admm_kernel(const MpcParams P, const MpcBuffers B) {
+__global__ void __launch_bounds__(BS, (BS == 64 && !B200QP_TC_GJ) ? 6 : 1) mpc_admm_kernel(const MpcParams P, const MpcBuffers B) {
   constexpr int LD = NV + 1;
   constexpr int MAXF = NV / 3 + 1;
   extern __shared__ __align__(16) double smem[];
   double *K = smem;                 // [NV * LD]
   double *s_g = K + NV * LD;        // [BS] gradient
-  double *s_v = s_g + BS;           // [BS] rhs / x broadcast buffer
+  double *s_c = s_g + BS;           // [BS] particular solution of the polish
+  double *s_v = s_c + BS;           // [BS] rhs / x broadcast buffer
   double *s_xt = s_v + BS;          // [BS]
   double *s_r = s_xt + BS;          // [BS] H x + g
-  double *s_c = s_r + BS;           // [BS] particular solution of the polish
-  double *s_w = s_c + BS;           // [BS] reduced solution
-  double *prow = s_w + BS;          // [4 * BS] staged pivot rows (4 per block step)
-  double *red = prow + 4 * BS;      // [4 * 32]
+  double *s_w = s_r + BS;           // [BS] reduced solution
+  double *prow = s_v;               // [4 * BS] staged pivot rows of the Gauss-Jordan sweep: s_v..s_w are idle during an inversion
+  double *red = s_w + BS;           // [4 * 32]
   // Stage quantities are only needed while K is not (assembly before the first factorisation, outputs after the solve), so
   // they alias the K region: one more resident block per SM.  Bw is parked in the per-block global scratch in between.
   double *s_Bw = K;                        // [MAXH * 36] Bw_kf, row-major 3x3 per (k,f); zero for swing feet
@@ -775,19 +775,21 @@ __global__ void __launch_bounds__(BS, (BS == 64 && !B200QP_TC_GJ) ? 5 : 1) mpc_a
     if (slot >= *B.bin_count) break;
     const int prob = B.bin_list[slot];
     // Stage the record (2.3 KB at N = 10) and its contact bytes in shared memory with one coalesced pass: the scattered
-    // per-thread reads of the assembly then never leave the SM, and B.in may be the caller's page-locked host buffer
-    // (read once over PCIe).  The copy aliases the ADMM work vectors, which are idle until the first factorisation.
-    static_assert(9 * BS >= 26 + 13 * (MAXH + 1) + 12 * MAXH + (4 * MAXH + 7) / 8, "record staging area");
+    // per-thread reads of the assembly then never leave the SM.  The copy lives in the K region behind the stage arrays.
+    constexpr int STAGE_DOUBLES = MAXH * 36 + (MAXH + 1) * 12 + 2 * (MAXH + 2) * 3 + MAXH * 6 + (MAXH + 1) * 13;
+    constexpr int REC_DOUBLES = 26 + 13 * (MAXH + 1) + 12 * MAXH + (4 * MAXH + 7) / 8;
+    static_assert(STAGE_DOUBLES + REC_DOUBLES <= NV * LD, "record staging area");
+    double *s_rec = K + STAGE_DOUBLES;  // behind the stage arrays, dead before the first factorisation
     {
       const double *grec = B.in + (size_t)prob * P.in_stride;
       const uint8_t *gct = B.contact + (size_t)prob * N * 4;
-      for (int e = tid; e < P.in_stride; e += BS) s_v[e] = grec[e];
-      uint8_t *sct = reinterpret_cast<uint8_t *>(s_v + P.in_stride);
+      for (int e = tid; e < P.in_stride; e += BS) s_rec[e] = grec[e];
+      uint8_t *sct = reinterpret_cast<uint8_t *>(s_rec + P.in_stride);
       for (int e = tid; e < 4 * N; e += BS) sct[e] = gct[e];
     }
     __syncthreads();
-    const double *rec = s_v;
-    const uint8_t *ct = reinterpret_cast<const uint8_t *>(s_v + P.in_stride);
+    const double *rec = s_rec;
+    const uint8_t *ct = reinterpret_cast<const uint8_t *>(s_rec + P.in_stride);
     const double mass = rec[13];
 
     const bool timing = B.dbg_cycles != nullptr;
@@ -1477,11 +1479,12 @@ __global__ void mpc_bin_kernel(int n, int N, const uint8_t *__restrict__ contact
   for (int e = 0; e < 4 * N; ++e) cnt += ct[e] != 0;
   const int nv = 3 * cnt;
   int bin;
-  if (nv <= 64) bin = 0;
-  else if (nv <= 128) bin = 1;
-  else if (nv <= 156) bin = 2;
-  else bin = 3;
-  if (bin == 3 && !overflow_bin) {
+  if (nv <= 60) bin = 0;
+  else if (nv <= 96) bin = 1;
+  else if (nv <= 128) bin = 2;
+  else if (nv <= 156) bin = 3;
+  else bin = 4;
+  if (bin == 4 && !overflow_bin) {
     b200qp_solver_info inf = {B200QP_ACADOS_QP_FAILURE, 0, 0, nv, {0, 0, 0, 0}};
     info[p] = inf;
     return;
@@ -1492,7 +1495,7 @@ __global__ void mpc_bin_kernel(int n, int N, const uint8_t *__restrict__ contact
 
 template <int BS, int NV>
 static size_t admm_smem_bytes() {
-  return sizeof(double) * ((size_t)NV * (NV + 1) + 10 * BS + 4 * 32);
+  return sizeof(double) * ((size_t)NV * (NV + 1) + 6 * BS + 4 * 32);
 }
 
 template <int BS, int NV>
@@ -1515,10 +1518,13 @@ static int occupancy_one() {
   }
   return occ < 1 ? 1 : occ;
 }
+// Instantiations (threads, max reduced size): trot at N = 10 is exactly n = 60 -> 6 resident blocks per SM; n = 96 is trot / pace /
+// bound at N = 16 and three-leg stance gaits at N = 10.
 int admm_occupancy(int bin) {
-  return bin == 0 ? occupancy_one<64, 64>() : bin == 1 ? occupancy_one<128, 128>() : occupancy_one<160, 156>();
+  return bin == 0 ? occupancy_one<64, 60>() : bin == 1 ? occupancy_one<96, 96>() : bin == 2 ? occupancy_one<128, 128>()
+                                                                                           : occupancy_one<160, 156>();
 }
-int admm_block_size(int bin) { return bin == 0 ? 64 : bin == 1 ? 128 : 160; }
+int admm_block_size(int bin) { return bin == 0 ? 64 : bin == 1 ? 96 : bin == 2 ? 128 : 160; }
 
 cudaError_t launch_mpc_bin(int n, int N, const uint8_t *contact, int *bin_count, int *bin_lists,
                            b200qp_solver_info *info, int overflow_bin, cudaStream_t st) {
@@ -1527,8 +1533,9 @@ cudaError_t launch_mpc_bin(int n, int N, const uint8_t *contact, int *bin_count,
 }
 
 cudaError_t launch_mpc_admm(int bin, const MpcParams &P, const MpcBuffers &B, int grid, cudaStream_t st) {
-  if (bin == 0) return launch_one<64, 64>(P, B, grid, st);
-  if (bin == 1) return launch_one<128, 128>(P, B, grid, st);
+  if (bin == 0) return launch_one<64, 60>(P, B, grid, st);
+  if (bin == 1) return launch_one<96, 96>(P, B, grid, st);
+  if (bin == 2) return launch_one<128, 128>(P, B, grid, st);
   return launch_one<160, 156>(P, B, grid, st);
 }
 
