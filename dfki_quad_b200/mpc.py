@@ -36,6 +36,9 @@ class SolverInformation:
     kernel_launches: int
 
 
+_INFO_DTYPE = np.dtype([("status", "i4"), ("iterations", "i4"), ("polish_rounds", "i4"), ("n_free", "i4"), ("kkt", "f8", (4,))])
+
+
 @dataclass
 class MPCPrediction:
     """Batched analogue of MPCPrediction (mpc_prediction.hpp:7-13)."""
@@ -184,7 +187,7 @@ class BatchedMPC:
             forces = np.zeros((n, self.N, 12))
         if xpred is None:
             xpred = np.zeros((n, self.N + 1, 13))
-        info = (_lib.SolverInfo * max(n, 1))()
+        info = self._info_buf()
         rc = self._lib.b200qp_mpc_solve_batch(self._h, n, rec.ctypes.data, contact.ctypes.data, forces.ctypes.data,
                                               xpred.ctypes.data, C.addressof(info))
         _lib.check(rc, "b200qp_mpc_solve_batch")
@@ -230,7 +233,7 @@ class BatchedMPC:
             forces = np.zeros((n, self.N, 12))
         if xpred is None:
             xpred = np.zeros((n, self.N + 1, 13))
-        info = (_lib.SolverInfo * max(n, 1))()
+        info = self._info_buf()
         rc = self._lib.b200qp_mpc_sequence_solve_batch(self._h, n, seq_in.ctypes.data,
                                                        mc.ctypes.data if mc is not None else None, forces.ctypes.data,
                                                        xpred.ctypes.data, C.addressof(info))
@@ -270,11 +273,15 @@ class BatchedMPC:
             raise _lib.B200QPError(f"b200qp_mpc_get_condensed failed with code {nf}: {_lib.last_error()}")
         return np.array(H[:nf, :nf]), g[:nf].copy()
 
+    def _info_buf(self):
+        if getattr(self, "_ibuf", None) is None:
+            self._ibuf = (_lib.SolverInfo * max(self.max_batch, 1))()  # reused: _info() copies out of it
+        return self._ibuf
+
     def _info(self, info, n):
-        arr = np.frombuffer(info, dtype=np.dtype([("status", "i4"), ("iterations", "i4"), ("polish_rounds", "i4"),
-                                                  ("n_free", "i4"), ("kkt", "f8", (4,))]), count=n)
+        # one bulk copy of the 48-byte records; the fields are views into that private copy
+        arr = np.frombuffer(info, dtype=np.uint8, count=48 * n).copy().view(_INFO_DTYPE)  # (a structured .copy() is 10x slower)
         ms, nl = self.last_timing()
-        return SolverInformation(success=arr["status"] == 0, return_code=arr["status"].copy(),
-                                 acados_num_iter=arr["iterations"].copy(), polish_rounds=arr["polish_rounds"].copy(),
-                                 n_free=arr["n_free"].copy(), kkt=arr["kkt"].copy(), total_solver_time=ms * 1e-3,
-                                 kernel_launches=nl)
+        return SolverInformation(success=arr["status"] == 0, return_code=arr["status"], acados_num_iter=arr["iterations"],
+                                 polish_rounds=arr["polish_rounds"], n_free=arr["n_free"], kkt=arr["kkt"],
+                                 total_solver_time=ms * 1e-3, kernel_launches=nl)
