@@ -60,6 +60,10 @@ struct b200qp_mpc {
   MpcParams P;
   cudaStream_t stream = nullptr;
   cudaStream_t bin_stream[4] = {nullptr, nullptr, nullptr, nullptr};  // bins 1..3 and the Riccati overflow run beside bin 0
+  cudaStream_t copy_stream = nullptr;  // chunked H2D of the records, overlapped with the solve
+  cudaEvent_t ev_copy = nullptr;
+  int *d_ready = nullptr, *h_one = nullptr;  // per-chunk "records have landed" flags, pinned constant 1
+  int stream_chunk = 0;                      // problems per chunk while a streamed solve is being issued, else 0
   cudaEvent_t ev_fork = nullptr, ev_join[4] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   int num_sms = 0;
@@ -179,6 +183,11 @@ int32_t b200qp_mpc_create(const b200qp_mpc_config *cfg, b200qp_mpc **out) {
   CK(cudaEventCreate(&h->ev0));
   CK(cudaEventCreate(&h->ev1));
   CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&h->ev_copy, cudaEventDisableTiming));
+  CK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+  CK(cudaMalloc(&h->d_ready, 16 * sizeof(int)));
+  CK(cudaMallocHost(&h->h_one, sizeof(int)));
+  *h->h_one = 1;
   for (int b = 0; b < 4; ++b) {
     CK(cudaStreamCreateWithFlags(&h->bin_stream[b], cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&h->ev_join[b], cudaEventDisableTiming));
@@ -250,6 +259,10 @@ void b200qp_mpc_destroy(b200qp_mpc *h) {
   cudaFree(h->d_measured);
   cudaFreeHost(h->h_seq);
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->ev_copy) cudaEventDestroy(h->ev_copy);
+  if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+  cudaFree(h->d_ready);
+  cudaFreeHost(h->h_one);
   for (int b = 0; b < 4; ++b) {
     if (h->ev_join[b]) cudaEventDestroy(h->ev_join[b]);
     if (h->bin_stream[b]) cudaStreamDestroy(h->bin_stream[b]);
@@ -315,6 +328,8 @@ static int32_t solve_device_impl(b200qp_mpc *h, int32_t n, const double *d_in, c
       B.bin_count = h->d_bin_count + b;
       B.bin_next = h->d_bin_count + 5 + b;
       B.hscratch = h->d_hscratch[b];
+      B.ready = h->stream_chunk > 0 ? h->d_ready : nullptr;
+      B.ready_chunk = h->stream_chunk;
       B.dbg_index = dbg_index;
       B.dbg_H = dbg_H;
       B.dbg_g = dbg_g;
@@ -459,9 +474,31 @@ int32_t b200qp_mpc_solve_batch(b200qp_mpc *h, int32_t n, const double *in, const
     src_in = h->h_in;
     src_ct = h->h_contact;
   }
-  CK(cudaMemcpyAsync(h->d_in, src_in, in_b, cudaMemcpyHostToDevice, h->stream));
   CK(cudaMemcpyAsync(h->d_contact, src_ct, (size_t)n * N * 4, cudaMemcpyHostToDevice, h->stream));
-  return solve_and_fetch(h, n, forces, xpred, info);
+  // The records (2.3 KB per problem, the bulk of the input) go up in chunks on the copy stream while the condensed kernel is
+  // already solving the chunks that have landed: a per-chunk flag, written by a 4-byte copy queued behind the chunk's data,
+  // is what the kernel polls before it stages a record.  The Riccati kernel has no such wait, so only CONDENSED_ADMM streams.
+  const int chunks = (h->cfg.solver == B200QP_SOLVER_CONDENSED_ADMM && !h->no_zero_copy && n >= 2048) ? 4 : 1;
+  if (chunks == 1) {
+    CK(cudaMemcpyAsync(h->d_in, src_in, in_b, cudaMemcpyHostToDevice, h->stream));
+    return solve_and_fetch(h, n, forces, xpred, info);
+  }
+  const int per = (n + chunks - 1) / chunks;
+  const size_t rec_d = (size_t)b200qp_mpc_in_doubles(N);
+  CK(cudaMemsetAsync(h->d_ready, 0, 16 * sizeof(int), h->stream));
+  CK(cudaEventRecord(h->ev_copy, h->stream));
+  CK(cudaStreamWaitEvent(h->copy_stream, h->ev_copy, 0));
+  for (int c = 0; c < chunks; ++c) {
+    const int lo = c * per, m = (lo + per <= n ? per : n - lo);
+    if (m <= 0) break;
+    CK(cudaMemcpyAsync(h->d_in + lo * rec_d, src_in + lo * rec_d, m * rec_d * sizeof(double), cudaMemcpyHostToDevice, h->copy_stream));
+    CK(cudaMemcpyAsync(h->d_ready + c, h->h_one, sizeof(int), cudaMemcpyHostToDevice, h->copy_stream));
+  }
+  h->stream_chunk = per;
+  const int32_t rc = solve_and_fetch(h, n, forces, xpred, info);
+  h->stream_chunk = 0;
+  CK(cudaStreamSynchronize(h->copy_stream));
+  return rc;
 }
 
 int32_t b200qp_mpc_set_model(b200qp_mpc *h, const b200qp_seq_model *m) {

@@ -780,10 +780,17 @@ __global__ void __launch_bounds__(BS, (BS == 64 && !B200QP_TC_GJ) ? 6 : 1) mpc_a
     constexpr int REC_DOUBLES = 26 + 13 * (MAXH + 1) + 12 * MAXH + (4 * MAXH + 7) / 8;
     static_assert(STAGE_DOUBLES + REC_DOUBLES <= NV * LD, "record staging area");
     double *s_rec = K + STAGE_DOUBLES;  // behind the stage arrays, dead before the first factorisation
+    if (B.ready != nullptr) {  // the H2D copy of this problem's chunk may still be in flight (copy engine, own stream)
+      if (tid == 0) {
+        const volatile int *flag = B.ready + prob / B.ready_chunk;
+        while (*flag == 0) __nanosleep(500);
+      }
+      __syncthreads();
+    }
     {
       const double *grec = B.in + (size_t)prob * P.in_stride;
       const uint8_t *gct = B.contact + (size_t)prob * N * 4;
-      for (int e = tid; e < P.in_stride; e += BS) s_rec[e] = grec[e];
+      for (int e = tid; e < P.in_stride; e += BS) s_rec[e] = __ldcg(grec + e);
       uint8_t *sct = reinterpret_cast<uint8_t *>(s_rec + P.in_stride);
       for (int e = tid; e < 4 * N; e += BS) sct[e] = gct[e];
     }
