@@ -26,11 +26,11 @@ KKT_TOL = 1e-6
 # BASELINE.json configs: [1] is the configuration the metric is quoted on (default); [2] is the Riccati config.
 WORKLOADS = {
     "config2": dict(name="go2_trot_condensed_mpc_h10_admm", horizon=10, batch=4096, gaits=("TROT",), solver="CONDENSED_ADMM",
-                    seed=20261019 + 2, kernel="mpc_admm_kernel<64,64>"),
+                    seed=20261019 + 2, kernel="mpc_admm_kernel<64,60>"),
     "config3": dict(name="go2_mixed_sparse_mpc_h16_riccati", horizon=16, batch=16384, gaits=("TROT", "PACE", "BOUND"),
                     solver="SPARSE_RICCATI", seed=20261019 + 3, kernel="mpc_riccati_kernel<64>"),
     "config5": dict(name="go2_1M_mixed_sweep_sharded", horizon=0, batch=1048576, gaits=(), solver="ADMM(N=10 trot) + AUTO(N=16 mixed: condensed kernel where n <= 156, Riccati otherwise)",
-                    seed=20261019 + 5, kernel="mpc_admm_kernel<64,64> + mpc_riccati_kernel<64>"),
+                    seed=20261019 + 5, kernel="mpc_admm_kernel<64,60> + mpc_riccati_kernel<64>"),
     "config4": dict(name="go2_wbc_reduced_tsid_qp", horizon=10, batch=16384, gaits=("TROT",), solver="WBC_DENSE_IPM",
                     seed=20261019 + 4, kernel="wbc_qp_kernel"),
 }
@@ -317,7 +317,7 @@ def run_b200(args):
             fp64_peak = None
         traffic = profiled_traffic(wl["kernel"])
         ab = algorithmic_bytes(N)
-        # dominant kernel = mpc_admm_kernel<64,64> (all trot problems land in the n<=64 bin); the step's event time
+        # dominant kernel = mpc_admm_kernel<64,60> (all trot problems land in the n<=60 bin); the step's event time
         # also contains the bin kernel and two empty-bin launches (a few microseconds)
         kern_s = (total_ms / args.steps) * 1e-3
         achieved = ab * B / kern_s / 1e9

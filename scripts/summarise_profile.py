@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Summarise an ncu report (run here, no GPU needed): key raw metrics, stall breakdown and the hottest source lines ->
 profiles/<tag>_summary.txt, and DRAM traffic per launch -> profiles/ncu_traffic.json (read by bench.py).
-Usage: scripts/summarise_profile.py gpurun_out/prof_X.ncu-rep <tag> <kernel-key e.g. 'mpc_admm_kernel<64,64>'> <source.cu>"""
+Usage: scripts/summarise_profile.py gpurun_out/prof_X.ncu-rep <tag> <kernel-key e.g. 'mpc_admm_kernel<64,60>'> <source.cu>"""
 import collections
 import csv
 import io
