@@ -26,7 +26,7 @@ class MpcConfig(C.Structure):
         ("admm_rho", C.c_double), ("admm_sigma", C.c_double), ("admm_alpha", C.c_double), ("admm_eps", C.c_double),
         ("kkt_tol", C.c_double),
         ("admm_max_iter", C.c_int32), ("admm_check_every", C.c_int32), ("polish_max_rounds", C.c_int32),
-        ("ipm_max_iter", C.c_int32),
+        ("ipm_max_iter", C.c_int32), ("warm_start", C.c_int32),
     ]
 
 
@@ -47,7 +47,7 @@ class SeqModel(C.Structure):
 
 EXPORTS = [
     "b200qp_version", "b200qp_device_count", "b200qp_last_error", "b200qp_fp64_peak_tflops", "b200qp_mpc_create", "b200qp_mpc_destroy",
-    "b200qp_mpc_set_state_weights", "b200qp_mpc_set_input_weights", "b200qp_mpc_set_fmax", "b200qp_mpc_set_mu",
+    "b200qp_mpc_set_state_weights", "b200qp_mpc_set_input_weights", "b200qp_mpc_set_fmax", "b200qp_mpc_set_mu", "b200qp_mpc_set_warm_start",
     "b200qp_mpc_solve_batch", "b200qp_mpc_solve_batch_device", "b200qp_mpc_get_duals", "b200qp_mpc_get_condensed",
     "b200qp_mpc_last_timing", "b200qp_mpc_stream", "b200qp_mpc_set_model", "b200qp_mpc_sequence_batch",
     "b200qp_mpc_sequence_solve_batch", "b200qp_mpc_sequence_solve_batch_device", "b200qp_gait_schedule", "b200qp_gait_schedule_device",
@@ -79,6 +79,7 @@ def load() -> C.CDLL:
     lib.b200qp_mpc_set_input_weights.argtypes = [vp, dbl]
     lib.b200qp_mpc_set_fmax.argtypes = [vp, dbl]
     lib.b200qp_mpc_set_mu.argtypes = [vp, dbl]
+    lib.b200qp_mpc_set_warm_start.argtypes = [vp, i32]
     lib.b200qp_mpc_solve_batch.argtypes = [vp, i32, vp, vp, vp, vp, vp]
     lib.b200qp_mpc_solve_batch_device.argtypes = [vp, i32, vp, vp, vp, vp, vp, i32]
     lib.b200qp_mpc_get_duals.argtypes = [vp, i32, vp, vp]

@@ -64,6 +64,9 @@ struct b200qp_mpc {
   cudaEvent_t ev_copy = nullptr;
   int *d_ready = nullptr, *h_one = nullptr;  // per-chunk "records have landed" flags, pinned constant 1
   int stream_chunk = 0;                      // problems per chunk while a streamed solve is being issued, else 0
+  // warm / hot start: previous solution per problem slot
+  double *d_warm_x = nullptr, *d_warm_y = nullptr;
+  uint8_t *d_warm_valid = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join[4] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   int num_sms = 0;
@@ -129,6 +132,8 @@ static void fill_params(b200qp_mpc *h) {
 }
 
 extern "C" {
+
+static int32_t ensure_warm_buffers(b200qp_mpc *h);
 
 const char *b200qp_version(void) { return "b200qp 0.1 (sm_100a)"; }
 const char *b200qp_last_error(void) { return g_err.c_str(); }
@@ -229,6 +234,14 @@ int32_t b200qp_mpc_create(const b200qp_mpc_config *cfg, b200qp_mpc **out) {
   CK(cudaMallocHost(&h->h_forces, nb * N * 12 * sizeof(double)));
   CK(cudaMallocHost(&h->h_xpred, nb * (N + 1) * 13 * sizeof(double)));
   CK(cudaMallocHost(&h->h_info, nb * sizeof(b200qp_solver_info)));
+  if (cfg->warm_start < 0 || cfg->warm_start > 2) {
+    g_err = "b200qp_mpc_create: warm_start must be 0, 1 or 2";
+    return B200QP_ERR_ARG;
+  }
+  if (cfg->warm_start > 0) {
+    const int32_t wrc = ensure_warm_buffers(h);
+    if (wrc != B200QP_OK) return wrc;
+  }
   CK(cudaMalloc(&h->d_seq, nb * B200QP_SEQ_IN_DOUBLES * sizeof(double)));
   CK(cudaMalloc(&h->d_measured, nb * 4));
   CK(cudaMallocHost(&h->h_seq, nb * B200QP_SEQ_IN_DOUBLES * sizeof(double) + nb * 4));
@@ -257,6 +270,9 @@ void b200qp_mpc_destroy(b200qp_mpc *h) {
   cudaFreeHost(h->h_info);
   cudaFree(h->d_seq);
   cudaFree(h->d_measured);
+  cudaFree(h->d_warm_x);
+  cudaFree(h->d_warm_y);
+  cudaFree(h->d_warm_valid);
   cudaFreeHost(h->h_seq);
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->ev_copy) cudaEventDestroy(h->ev_copy);
@@ -271,6 +287,25 @@ void b200qp_mpc_destroy(b200qp_mpc *h) {
   if (h->ev1) cudaEventDestroy(h->ev1);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
+}
+
+static int32_t ensure_warm_buffers(b200qp_mpc *h) {
+  const size_t nb = (size_t)h->cfg.max_batch, N = (size_t)h->cfg.horizon;
+  if (h->d_warm_x == nullptr) {
+    CK(cudaMalloc(&h->d_warm_x, nb * N * 12 * sizeof(double)));
+    CK(cudaMalloc(&h->d_warm_y, nb * N * 28 * sizeof(double)));
+    CK(cudaMalloc(&h->d_warm_valid, nb));
+  }
+  CK(cudaMemsetAsync(h->d_warm_valid, 0, nb, h->stream));  // forget every stored solution
+  return B200QP_OK;
+}
+
+int32_t b200qp_mpc_set_warm_start(b200qp_mpc *h, int32_t mode) {
+  if (!h || mode < 0 || mode > 2) return B200QP_ERR_ARG;
+  CK(cudaSetDevice(h->cfg.device));
+  h->cfg.warm_start = mode;
+  if (mode > 0 || h->d_warm_x != nullptr) return ensure_warm_buffers(h);
+  return B200QP_OK;
 }
 
 int32_t b200qp_mpc_set_state_weights(b200qp_mpc *h, const double weights[12]) {
@@ -328,6 +363,10 @@ static int32_t solve_device_impl(b200qp_mpc *h, int32_t n, const double *d_in, c
       B.bin_count = h->d_bin_count + b;
       B.bin_next = h->d_bin_count + 5 + b;
       B.hscratch = h->d_hscratch[b];
+      B.warm_mode = (h->cfg.warm_start > 0 && h->d_warm_x != nullptr && dbg_index < 0 && !h->want_duals) ? h->cfg.warm_start : 0;
+      B.warm_x = h->d_warm_x;
+      B.warm_y = h->d_warm_y;
+      B.warm_valid = h->d_warm_valid;
       B.ready = h->stream_chunk > 0 ? h->d_ready : nullptr;
       B.ready_chunk = h->stream_chunk;
       B.dbg_index = dbg_index;

@@ -38,6 +38,12 @@ struct MpcBuffers {
   // landed in device memory; nullptr = everything is resident
   const int *ready;
   int ready_chunk;
+  // warm / hot start (b200qp_mpc_config.warm_start): previous solution per problem slot, forces layout [n][N][12] and ADMM
+  // duals [n][N][4][7]; warm_mode 0 = off (buffers may be nullptr)
+  double *warm_x;
+  double *warm_y;
+  uint8_t *warm_valid;
+  int warm_mode;
   // debug (parity hook)
   int dbg_index;
   double *dbg_H;

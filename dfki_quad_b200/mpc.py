@@ -99,6 +99,7 @@ class BatchedMPC:
         sw = np.asarray(state_weights, dtype=np.float64).reshape(12)
         for i in range(12):
             cfg.state_weights[i] = sw[i]
+        cfg.warm_start = int(warm_start)  # MPC::MPC warm_start (mpc.hpp:127): 0 cold, 1 warm, 2 hot
         for k, v in opts.items():
             if not hasattr(cfg, k):
                 raise TypeError(f"unknown solver option {k!r}")
@@ -171,6 +172,10 @@ class BatchedMPC:
 
     def SetFmax(self, fmax):
         _lib.check(self._lib.b200qp_mpc_set_fmax(self._h, float(fmax)), "set_fmax")
+
+    def SetWarmStart(self, mode):
+        """0 cold / 1 warm / 2 hot start (b200qp_mpc_set_warm_start); also forgets the stored solutions."""
+        _lib.check(self._lib.b200qp_mpc_set_warm_start(self._h, int(mode)), "set_warm_start")
 
     def SetMu(self, mu):
         _lib.check(self._lib.b200qp_mpc_set_mu(self._h, float(mu)), "set_mu")

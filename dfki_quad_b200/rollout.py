@@ -71,7 +71,7 @@ def closed_loop(mpc, n, steps, target, gait="TROT", seed=0, dt=0.05, v_filter_le
     phase = rng.uniform(0.0, 1.0, n)
     vhist = [vel.copy()]
     prev_contact = None
-    hist = dict(pos=[pos.copy()], vel=[vel.copy()], quat=[quat.copy()], ok=[], fz=[])
+    hist = dict(pos=[pos.copy()], vel=[vel.copy()], quat=[quat.copy()], ok=[], fz=[], iters=[], rounds=[], kernel_ms=[])
     for _ in range(steps):
         vf = np.mean(vhist[-v_filter_len:], axis=0)
         seq_in = sq.pack_sequencer_inputs(quat, pos, omega, vel, feet, vf, heights, tgt, phase, period, duty, offset)
@@ -97,5 +97,6 @@ def closed_loop(mpc, n, steps, target, gait="TROT", seed=0, dt=0.05, v_filter_le
         prev_contact = c0
         vhist.append(vel.copy())
         hist["pos"].append(pos.copy()); hist["vel"].append(vel.copy()); hist["quat"].append(quat.copy())
-        hist["ok"].append(ok.copy()); hist["fz"].append(f0[:, :, 2].sum(axis=1))
+        hist["ok"].append(ok.copy()); hist["fz"].append(f0[:, :, 2].sum(axis=1)); hist["iters"].append(info.acados_num_iter.copy())
+        hist["rounds"].append(info.polish_rounds.copy()); hist["kernel_ms"].append(info.total_solver_time * 1e3)
     return {k: np.array(v) for k, v in hist.items()}

@@ -72,6 +72,11 @@ typedef struct b200qp_mpc_config {
   int32_t admm_check_every;   /* residual check / rho adaptation interval                 default 15            */
   int32_t polish_max_rounds;  /* active-set repair sweeps per polish                      default 8             */
   int32_t ipm_max_iter;       /* Riccati IPM iteration cap                                default 40            */
+  int32_t warm_start;         /* MPC::MPC warm_start (mpc.hpp:127, `mpc_warm_start`, mit_controller_node.cpp:65): 0 cold start;   */
+                              /* 1 warm start - the ADMM iterate of problem slot p starts from the previous solution of slot p    */
+                              /* (primal, duals) of this handle; 2 hot start - the previous active set is tried first (one        */
+                              /* polish round, no factorisation of K) and ADMM only runs, warm-started, if that is not optimal.   */
+                              /* Condensed kernel only; the Riccati IPM always starts cold.                                       */
 } b200qp_mpc_config;
 
 /* Input record of one problem = the subset of {StateInterface, ModelInterface, GaitSequence} that
@@ -111,6 +116,8 @@ int32_t b200qp_mpc_set_state_weights(b200qp_mpc *h, const double weights[12]);
 int32_t b200qp_mpc_set_input_weights(b200qp_mpc *h, double alpha);
 int32_t b200qp_mpc_set_fmax(b200qp_mpc *h, double fmax);
 int32_t b200qp_mpc_set_mu(b200qp_mpc *h, double mu);
+/* Warm-start mode (see b200qp_mpc_config.warm_start); any call also forgets the stored solutions of all slots. */
+int32_t b200qp_mpc_set_warm_start(b200qp_mpc *h, int32_t mode);
 
 /* MPC::GetWrenchSequence for `n` problems, HOST buffers (mpc.cpp:329-470).
  *   in       [n][b200qp_mpc_in_doubles(N)]   input records (see above)

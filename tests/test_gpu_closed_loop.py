@@ -54,3 +54,23 @@ def test_closed_loop_tracks_command(gait, vx, wz, yaw0, plant):
     assert np.abs(rate - wz).max() < 0.12, (rate.min(), rate.max())
     # the stance feet carry the weight on average
     assert abs(h["fz"][-20:].mean() - sequencer.GO2_MASS * 9.8067) < 0.1 * sequencer.GO2_MASS * 9.8067
+
+
+def test_closed_loop_hot_start_follows_the_cold_trajectory():
+    """The reference runs with mpc_warm_start = 1 (mit_controller_sim_go2.yaml:25).  In closed loop consecutive problems are
+    close: hot start must follow the cold-start trajectory and skip most of the ADMM work."""
+    from dfki_quad_b200 import BatchedMPC, rollout, sequencer
+
+    n, steps = 64, 40
+    tgt = dict(hybrid_x_dot=0.3, hybrid_y_dot=0.0, wz=0.0, wx=0.0, wy=0.0, roll=0.0, pitch=0.0, z=0.30)
+    cfg = sequencer.GO2_MPC
+    hist = {}
+    for mode in (0, 2):
+        mpc = BatchedMPC(cfg["alpha"], cfg["state_weights_move"], cfg["mu"], cfg["fmin"], cfg["fmax"], "CONDENSED_ADMM",
+                         warm_start=mode, horizon=10, dt=cfg["dt"], max_batch=n)
+        mpc.set_model(**sequencer.go2_seq_model())
+        hist[mode] = rollout.closed_loop(mpc, n, steps, tgt, gait="TROT", seed=3, yaw0=0.0)
+    assert hist[0]["ok"].all() and hist[2]["ok"].all()
+    assert np.abs(hist[0]["pos"] - hist[2]["pos"]).max() < 1e-4
+    it0, it2 = hist[0]["iters"][5:].mean(), hist[2]["iters"][5:].mean()
+    assert it2 < 0.5 * it0, (it0, it2)

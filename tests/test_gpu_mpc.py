@@ -542,3 +542,44 @@ def test_sequence_and_solve_equals_two_step_path():
     assert (np.abs(f1 - f2) / scale).max() < 1e-5
     with pytest.raises(Exception):
         _mpc(N, 4).sequence_and_solve(batch["seq_in"][:4])  # no model set
+
+
+# ------------------------------------------------------------------ warm / hot start (MPC::MPC warm_start, mpc.hpp:127)
+@pytest.mark.parametrize("mode", [1, 2])
+def test_warm_and_hot_start_reach_the_same_optimum(mode, go2_params):
+    """Second solve of slightly perturbed problems: warm (1) and hot (2) start return the cold-start optimum to 1e-5 with far
+    fewer ADMM iterations; hot start needs none when the active set did not change."""
+    from dfki_quad_b200 import sequencer
+
+    N, n = 10, 1024
+    batch = sequencer.random_batch(n, N, seed=91, gaits=("TROT", "WALKING_TROT", "STAND"))
+    rec2 = batch["rec"].copy()
+    rng = np.random.default_rng(5)
+    rec2[:, 10:13] += rng.uniform(-0.02, 0.02, (n, 3))  # linear velocity
+    rec2[:, 7:10] += rng.uniform(-0.02, 0.02, (n, 3))  # angular velocity
+    cold = _mpc(N, n)
+    fc, xc, ic = cold.solve_records(rec2, batch["contact"])
+    warm = _mpc(N, n, warm_start=mode)
+    f1, _, i1 = warm.solve_records(batch["rec"], batch["contact"])  # nothing stored yet: identical to a cold solve
+    f1c, _, i1c = cold.solve_records(batch["rec"], batch["contact"])
+    assert np.array_equal(f1, f1c) and np.array_equal(i1.acados_num_iter, i1c.acados_num_iter)
+    f2, x2, i2 = warm.solve_records(rec2, batch["contact"])
+    assert ic.success.all() and i2.success.all()
+    assert np.all(i2.kkt.max(axis=1) <= 1e-6)
+    scale = np.maximum(1.0, np.abs(fc).reshape(n, -1).max(axis=1))
+    assert (np.abs(f2 - fc).reshape(n, -1).max(axis=1) / scale).max() <= 1e-5
+    assert i2.acados_num_iter.mean() < (0.75 if mode == 1 else 0.3) * ic.acados_num_iter.mean(), (i2.acados_num_iter.mean(), ic.acados_num_iter.mean())
+    if mode == 2:
+        assert (i2.acados_num_iter == 0).mean() > 0.7, (i2.acados_num_iter == 0).mean()
+    _check_against_oracle(N, dict(batch, rec=rec2), f2, x2, i2, go2_params, range(3))
+    # a different contact pattern in the same slots (another gait phase) must still converge to the right answer
+    other = sequencer.random_batch(n, N, seed=92, gaits=("TROT", "PACE"))
+    f3, x3, i3 = warm.solve_records(other["rec"], other["contact"])
+    f3c, _, i3c = cold.solve_records(other["rec"], other["contact"])
+    assert i3.success.all() and i3c.success.all()
+    scale = np.maximum(1.0, np.abs(f3c).reshape(n, -1).max(axis=1))
+    assert (np.abs(f3 - f3c).reshape(n, -1).max(axis=1) / scale).max() <= 1e-5
+    # switching the mode forgets the stored solutions
+    warm.SetWarmStart(mode)
+    f4, _, i4 = warm.solve_records(other["rec"], other["contact"])
+    assert np.array_equal(i4.acados_num_iter, i3c.acados_num_iter)
