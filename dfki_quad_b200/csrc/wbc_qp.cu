@@ -52,10 +52,10 @@ __device__ void chol_and_inverse(double *A, double *Li, int n, double *diag0) {
     for (int i = p + tid; i < n; i += BS) A[i * n + p] = (i == p) ? piv * rd : A[i * n + p] * rd;
     if (tid == 0) diag0[p] = rd;  // from here on diag0[p] = 1 / L[p][p]
     __syncthreads();
-    const int rem = n - p - 1;
-    for (int e = tid; e < rem * rem; e += BS) {
-      const int i = p + 1 + e / rem, j = p + 1 + e % rem;
-      if (j <= i) A[i * n + j] -= A[i * n + p] * A[j * n + p];
+    // trailing update on an 8 x 8 thread grid (no integer division by the shrinking remainder)
+    for (int i = p + 1 + (tid >> 3); i < n; i += 8) {
+      const double lip = A[i * n + p];
+      for (int j = p + 1 + (tid & 7); j <= i; j += 8) A[i * n + j] -= lip * A[j * n + p];
     }
     __syncthreads();
   }
@@ -114,13 +114,16 @@ __device__ void kkt_solve(int nq, int me, const double *sLi, const double *sY, c
 }
 }  // namespace
 
+// NQ_ / ME_ / MI_ > 0 fix the problem dimensions at compile time (Go2 reduced TSID: 30 / 18 / 28): the element loops divide by
+// them (a runtime integer division is ~25 instructions) and their inner products unroll.  0 = take the dimension from P.
+template <int NQ_, int ME_, int MI_>
 __global__ void __launch_bounds__(64) wbc_qp_kernel(const WbcParams P, int nprob, const double *__restrict__ Hg,
                                                     const double *__restrict__ gg, const double *__restrict__ Ag,
                                                     const double *__restrict__ log, const double *__restrict__ hig,
                                                     double *__restrict__ xout, b200qp_solver_info *__restrict__ info,
                                                     int *next) {
   extern __shared__ __align__(16) double sm[];
-  const int nq = P.nq, me = P.neq, mi = P.nin, nc = me + mi;
+  const int nq = NQ_ > 0 ? NQ_ : P.nq, me = NQ_ > 0 ? ME_ : P.neq, mi = NQ_ > 0 ? MI_ : P.nin, nc = me + mi;
   double *sH = sm;                  // [nq*nq] row-major (symmetric)
   double *sAe = sH + nq * nq;       // [me*nq] row-major
   double *sAi = sAe + me * nq;      // [mi*nq]
@@ -419,21 +422,30 @@ size_t wbc_smem_bytes(const WbcParams &P) {
   return d * sizeof(double) + 64;
 }
 
-int wbc_grid(const WbcParams &P, int num_sms) {
-  const size_t smb = wbc_smem_bytes(P);
+template <int NQ_, int ME_, int MI_>
+static int wbc_occupancy(size_t smb) {
   int occ = 0;
-  if (cudaFuncSetAttribute(wbc_qp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smb) != cudaSuccess ||
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, wbc_qp_kernel, 64, smb) != cudaSuccess) {
+  if (cudaFuncSetAttribute(wbc_qp_kernel<NQ_, ME_, MI_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smb) != cudaSuccess ||
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, wbc_qp_kernel<NQ_, ME_, MI_>, 64, smb) != cudaSuccess) {
     cudaGetLastError();
     return -1;
   }
-  return num_sms * (occ < 1 ? 1 : occ);
+  return occ < 1 ? 1 : occ;
+}
+
+int wbc_grid(const WbcParams &P, int num_sms) {
+  const size_t smb = wbc_smem_bytes(P);
+  const int occ = (P.nq == 30 && P.neq == 18 && P.nin == 28) ? wbc_occupancy<30, 18, 28>(smb) : wbc_occupancy<0, 0, 0>(smb);
+  return occ < 0 ? -1 : num_sms * occ;
 }
 
 cudaError_t launch_wbc_qp(const WbcParams &P, int n, const double *H, const double *g, const double *A, const double *lo,
                           const double *hi, double *x, b200qp_solver_info *info, int *next, int grid, cudaStream_t st) {
   if (grid > n) grid = n;
-  wbc_qp_kernel<<<grid, 64, wbc_smem_bytes(P), st>>>(P, n, H, g, A, lo, hi, x, info, next);
+  if (P.nq == 30 && P.neq == 18 && P.nin == 28)
+    wbc_qp_kernel<30, 18, 28><<<grid, 64, wbc_smem_bytes(P), st>>>(P, n, H, g, A, lo, hi, x, info, next);
+  else
+    wbc_qp_kernel<0, 0, 0><<<grid, 64, wbc_smem_bytes(P), st>>>(P, n, H, g, A, lo, hi, x, info, next);
   return cudaGetLastError();
 }
 
