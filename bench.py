@@ -103,6 +103,20 @@ class ClockSampler:
                 pass
             time.sleep(0.002)
 
+    def sample_now(self):
+        """One synchronous sample (called while the timed launches are queued and the GPU is busy: the polling thread can be
+        starved by the launching thread in a region that only lasts tens of milliseconds)."""
+        n = self.nvml
+        if n is None:
+            return
+        try:
+            sm = n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM)
+            mx = n.nvmlDeviceGetMaxClockInfo(self.h, n.NVML_CLOCK_SM)
+            rs = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+            self.rows.append([str(sm), str(mx), "0"] + ["Active" if rs & b else "Not Active" for b in (0x8, 0x40, 0x20, 0x4)])
+        except Exception:
+            pass
+
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
@@ -279,6 +293,7 @@ def run_b200(args):
                 step_device()
                 e1.record(ext)
             evs.append((e0, e1))
+            clocks.sample_now()
         barrier()
     step_ms = [a.elapsed_time(b) for a, b in evs]
     total_ms = float(sum(step_ms))
@@ -441,6 +456,7 @@ def run_b200_wbc(args):
                 step()
                 e1.record(ext)
             evs.append((e0, e1))
+            clocks.sample_now()
         barrier()
     total_ms = float(sum(a.elapsed_time(c) for a, c in evs))
     info = np.frombuffer(dinfo.cpu().numpy().tobytes(), dtype=np.dtype(
