@@ -230,3 +230,75 @@ def test_cpp_header_compiles_and_links(tmp_path):
     out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "created" in out.stdout or "no CPU fallback" in out.stdout or "error" in out.stdout
+
+
+def test_ctypes_structs_match_the_c_header_field_by_field(tmp_path):
+    """offsetof / sizeof of every ABI struct as the C compiler sees include/b200qp.h == the ctypes mirrors in _lib.py."""
+    import ctypes
+
+    from dfki_quad_b200 import _lib
+
+    structs = {"b200qp_mpc_config": _lib.MpcConfig, "b200qp_solver_info": _lib.SolverInfo, "b200qp_wbc_config": _lib.WbcConfig,
+               "b200qp_seq_model": _lib.SeqModel}
+    lines = ['#include <stddef.h>', '#include <stdio.h>', '#include "b200qp.h"', "int main(void) {"]
+    for cname, cls in structs.items():
+        lines.append(f'  printf("{cname} size %zu\\n", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'  printf("{cname} {fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += [f'  printf("seq_in_doubles %d\\n", B200QP_SEQ_IN_DOUBLES);', "  return 0; }"]
+    src = tmp_path / "o.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "o"
+    gcc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
+    r = subprocess.run([gcc, "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    out = subprocess.run([str(exe)], capture_output=True, text=True).stdout.split("\n")
+    seen = {}
+    for ln in out:
+        parts = ln.split()
+        if len(parts) == 3:
+            seen[(parts[0], parts[1])] = int(parts[2])
+        elif len(parts) == 2:
+            seen[(parts[0],)] = int(parts[1])
+    for cname, cls in structs.items():
+        assert seen[(cname, "size")] == ctypes.sizeof(cls), cname
+        for fname, _ in cls._fields_:
+            assert seen[(cname, fname)] == getattr(cls, fname).offset, (cname, fname)
+    from dfki_quad_b200 import sequencer
+
+    assert seen[("seq_in_doubles",)] == sequencer.SEQ_IN_DOUBLES == 50
+
+
+def test_rollout_plant_conserves_what_it_should():
+    """Host-side SRBD plant of the closed-loop harness: free fall, torque-free rotation (|L| constant), weight balance."""
+    from dfki_quad_b200 import rollout, sequencer as sq
+
+    n = 4
+    rng = np.random.default_rng(0)
+    quat = sq._yaw_quat(rng.uniform(-1, 1, n))
+    pos = np.tile([0.0, 0.0, 1.0], (n, 1))
+    omega = rng.uniform(-1, 1, (n, 3))
+    vel = rng.uniform(-1, 1, (n, 3))
+    feet = np.zeros((n, 4, 3))
+    zero = np.zeros((n, 4, 3))
+    L0 = np.einsum("nij,nj->ni", sq.quat_to_rot(quat) @ sq.GO2_INERTIA @ np.swapaxes(sq.quat_to_rot(quat), 1, 2), omega)
+    q1, p1, w1, v1 = rollout.srbd_step(quat, pos, omega, vel, feet, zero, 0.2, substeps=400)
+    assert np.allclose(v1, vel + 0.2 * rollout.GRAVITY, atol=1e-12)
+    assert np.allclose(p1, pos + 0.2 * vel + 0.5 * 0.04 * rollout.GRAVITY, atol=2e-3)
+    R1 = sq.quat_to_rot(q1)
+    L1 = np.einsum("nij,nj->ni", R1 @ sq.GO2_INERTIA @ np.swapaxes(R1, 1, 2), w1)
+    assert np.allclose(L1, L0, atol=2e-3)  # angular momentum in the world frame
+    assert np.allclose(np.linalg.norm(q1, axis=1), 1.0)
+    # four feet under the hips carrying m g / 4 each: no acceleration
+    yaw0 = np.zeros(n)
+    quat = sq._yaw_quat(yaw0)
+    pos = np.tile([0.0, 0.0, 0.3], (n, 1))
+    feet = pos[:, None, :] + sq.GO2_SHOULDERS[None]
+    feet[:, :, 2] = 0.0
+    f = np.zeros((n, 4, 3))
+    xf, xr = sq.GO2_SHOULDERS[0, 0], -sq.GO2_SHOULDERS[2, 0]  # hips are not symmetric about the COM: moment balance front / rear
+    w = sq.GO2_MASS * 9.8067
+    f[:, :2, 2] = 0.5 * w * xr / (xf + xr)
+    f[:, 2:, 2] = 0.5 * w * xf / (xf + xr)
+    q2, p2, w2, v2 = rollout.srbd_step(quat, pos, np.zeros((n, 3)), np.zeros((n, 3)), feet, f, 0.05)
+    assert np.abs(v2).max() < 1e-12 and np.abs(w2).max() < 1e-12
