@@ -4,6 +4,8 @@
 //   MPC::GetUBounds              ws/src/controllers/src/mit_controller/mpc.cpp:94-115
 // One thread per (robot, leg); the loop over steps is sequential because the early-contact override
 // (gait.cpp:88-99) carries state from step to step.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace b200qp {
@@ -287,10 +289,189 @@ __global__ void sequencer_kernel(int n, SeqModel M, const double *__restrict__ s
   }
 }
 
+// Same sequencer, one WARP per robot.  The thread-per-robot kernel above is one chain of ~21 stages x ~10 FP64 trigonometric
+// calls (0.09 ms for any batch size); here lane i owns stage i: the yaw of stage i is accumulated by the lane itself in the
+// reference's order (i additions), its orientation / yaw quaternion / velocity are independent of the other stages, the
+// half-way yaw quaternion needs the neighbour's (one shuffle), and the positions are summed per lane in stage order from the
+// steps parked in shared memory - the floating-point operations and their order per output are exactly those of the serial
+// kernel.  Four lanes (one per leg) then run the stateful parts (early-contact latch, Raibert hold / touch-down logic), and the
+// record is written with coalesced stores.  sequencer_kernel stays as the readable statement of the algorithm and as a
+// cross-check in the tests of the two kernels against each other.
+constexpr int SEQ_WARPS = 4;
+__global__ void __launch_bounds__(32 * SEQ_WARPS) sequencer_warp_kernel(int n, SeqModel M, const double *__restrict__ seq_in,
+                                                                        const uint8_t *__restrict__ measured,
+                                                                        double *__restrict__ rec_out,
+                                                                        uint8_t *__restrict__ contact_out, int in_stride) {
+  constexpr int RECMAX = 26 + 13 * (MAXH + 1) + 12 * MAXH;
+  __shared__ double s_rec[SEQ_WARPS][RECMAX];
+  __shared__ double s_in[SEQ_WARPS][52];
+  __shared__ double s_step[SEQ_WARPS][MAXH + 1][2];
+  __shared__ double s_refpos[SEQ_WARPS][MAXH + 1][3], s_refyq[SEQ_WARPS][MAXH + 1][4], s_refvel[SEQ_WARPS][MAXH + 1][3];
+  __shared__ unsigned s_cmask[SEQ_WARPS][MAXH + 1];
+  __shared__ double s_h[SEQ_WARPS][4];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int p = blockIdx.x * SEQ_WARPS + w;
+  if (p >= n) return;  // whole warps leave together; only __syncwarp below
+  const unsigned full = 0xffffffffu;
+  const int N = M.N, steps = N + 1;
+  const double dt = M.dt;
+  double *S = s_in[w];
+  for (int e = lane; e < 50; e += 32) S[e] = seq_in[(size_t)p * 50 + e];
+  __syncwarp();
+  double *rec = s_rec[w];
+  // ---- contact schedule: lane = leg (stateful latch, sequential over the stages) -------------------------------------------------
+  if (lane < 4) {
+    const int leg = lane;
+    const double T = S[41], d = S[42 + leg], off = S[46 + leg];
+    bool early = false;
+    for (int i = 0; i < steps; ++i) {
+      const double leg_phase = fmod(((S[40] + 1.0) - off) + ((double)(unsigned)i * dt) / T, 1.0);
+      bool c = leg_phase < d;
+      if (i == 0 && measured != nullptr) {
+        if (measured[4 * p + leg] != 0 && !c && (leg_phase > ((d + 1.0) / 2.0))) early = true;
+      }
+      if (c) early = false;
+      else if (early) c = true;
+      const unsigned bits = __ballot_sync(0xfu, c) & 0xfu;
+      if (leg == 0) s_cmask[w][i] = bits;
+      if (i < N) contact_out[((size_t)p * N + i) * 4 + leg] = c ? 1 : 0;
+    }
+  }
+  // ---- header ------------------------------------------------------------------------------------------------------------------
+  if (lane < 13) rec[lane] = S[lane];
+  if (lane == 13) rec[13] = M.mass;
+  if (lane >= 14 && lane < 23) rec[lane] = M.inertia[lane - 14];
+  if (lane >= 23 && lane < 26) rec[lane] = M.com[lane - 23];
+  const double hx = S[32], hy = S[33];
+  const double twc[3] = {S[35], S[36], S[34]};
+  const double troll = S[37], tpitch = S[38], tz = S[39];
+  const double min_h = fmin(fmin(S[13 + 2], S[16 + 2]), fmin(S[19 + 2], S[22 + 2]));
+  // ---- per-stage orientation, velocity and position step: lane = stage ----------------------------------------------------------------
+  double q[4] = {0, 0, 0, 1}, yq[4] = {0, 0, 0, 1}, vel[3] = {0, 0, 0};
+  const int i = lane;
+  if (i < steps) {
+    if (i == 0) {
+      for (int c = 0; c < 4; ++c) q[c] = S[c];
+      for (int c = 0; c < 3; ++c) vel[c] = S[10 + c];
+    } else {
+      double R0[3][3], eul[3];
+      quat_to_rot(S, R0);
+      rot_to_euler(R0, eul);
+      for (int t = 0; t < i; ++t) {
+        for (int c = 0; c < 3; ++c) eul[c] = eul[c] + dt * twc[c];
+        eul[1] = tpitch;
+        eul[0] = troll;
+      }
+      e_to_q(eul, q);
+      const double hv[3] = {hx, hy, 0.0};
+      rot_v(q, hv, vel);
+    }
+    yaw_q(q_yaw(q), yq);
+  }
+  double yp[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) yp[c] = __shfl_up_sync(full, yq[c], 1);
+  if (i >= 1 && i < steps) {
+    double mid[4], st3[3];
+    const double dv[3] = {dt * hx, dt * hy, 0.0};
+    slerp_half(yp, yq, mid);
+    rot_v(mid, dv, st3);
+    s_step[w][i][0] = st3[0];
+    s_step[w][i][1] = st3[1];
+  }
+  __syncwarp();
+  if (i < steps) {
+    double pos[3] = {S[4], S[5], S[6]};
+    for (int t = 1; t <= i; ++t) {  // the reference's summation order
+      pos[0] = pos[0] + s_step[w][t][0];
+      pos[1] = pos[1] + s_step[w][t][1];
+    }
+    if (i >= 1) pos[2] = tz + min_h;
+    double *st = rec + 26 + 13 * i;
+    for (int c = 0; c < 4; ++c) st[c] = q[c];
+    for (int c = 0; c < 3; ++c) {
+      st[4 + c] = pos[c];
+      st[7 + c] = (i == 0) ? S[7 + c] : twc[c];
+      st[10 + c] = vel[c];
+      s_refpos[w][i][c] = pos[c];
+      s_refvel[w][i][c] = vel[c];
+    }
+    for (int c = 0; c < 4; ++c) s_refyq[w][i][c] = yq[c];
+  }
+  __syncwarp();
+  // ---- Raibert foot positions: lane = leg ---------------------------------------------------------------------------------------------
+  if (lane < 4) {
+    const int leg = lane;
+    double *fp = rec + 26 + 13 * steps;
+    // heights only change at stage 0 (stance feet take their current height); every leg needs all four afterwards
+    double hleg = S[28 + leg];
+    if ((s_cmask[w][0] >> leg) & 1u) hleg = S[13 + 3 * leg + 2];
+    s_h[w][leg] = hleg;
+    __syncwarp(0xfu);
+    const double hmin = fmin(fmin(s_h[w][0], s_h[w][1]), fmin(s_h[w][2], s_h[w][3]));
+    bool resume = true;
+    double prevfp[3] = {0.0, 0.0, 0.0};
+    const double L = M.max_leg_length;
+    for (int k = 0; k < steps; ++k) {
+      double out[3] = {0.0, 0.0, 0.0};
+      if ((s_cmask[w][k] >> leg) & 1u) {
+        if (k == 0) {
+          for (int c = 0; c < 3; ++c) out[c] = S[13 + 3 * leg + c];
+        } else if (resume) {
+          for (int c = 0; c < 3; ++c) out[c] = prevfp[c];
+        } else {
+          double psh[3];
+          const double sh[3] = {M.shoulders[3 * leg], M.shoulders[3 * leg + 1], M.shoulders[3 * leg + 2]};
+          rot_v(s_refyq[w][k], sh, psh);
+          for (int c = 0; c < 3; ++c) psh[c] = s_refpos[w][k][c] + psh[c];
+          double h = s_refpos[w][k][2] - hmin;
+          h = fmin(fmax(h, 0.0), L);
+          const double *v = S + 25;
+          const double wcx = twc[0], wcy = twc[1], wcz = twc[2];  // k >= 1 here
+          const double cr[3] = {v[1] * wcz - v[2] * wcy, v[2] * wcx - v[0] * wcz, v[0] * wcy - v[1] * wcx};
+          const double kc = 0.5 * sqrt(h / M.raibert_g);
+          const double tst = S[42 + leg] * S[41];
+          double pp[3];
+          for (int c = 0; c < 3; ++c) pp[c] = psh[c] + kc * cr[c] + ((tst / 2.0) * v[c] + M.raibert_k * (v[c] - s_refvel[w][k][c]));
+          pp[2] = hleg;
+          const double dif[3] = {pp[0] - psh[0], pp[1] - psh[1], pp[2] - psh[2]};
+          const double nrm = sqrt(dif[0] * dif[0] + dif[1] * dif[1] + dif[2] * dif[2]);
+          if (nrm > L && fabs(dif[2]) <= L) {
+            double nd[3];
+            if (fabs(dif[0]) > fabs(dif[1])) {
+              nd[0] = -sqrt(-(dif[2] - L) * (dif[2] + L) / ((dif[1] / dif[0]) * (dif[1] / dif[0]) + 1));
+              nd[1] = (dif[1] / dif[0]) * nd[0];
+            } else {
+              nd[1] = -sqrt(-(dif[2] - L) * (dif[2] + L) / ((dif[0] / dif[1]) * (dif[0] / dif[1]) + 1));
+              nd[0] = (dif[0] / dif[1]) * nd[1];
+            }
+            nd[2] = dif[2];
+            for (int c = 0; c < 3; ++c) pp[c] = psh[c] + nd[c];
+          }
+          for (int c = 0; c < 3; ++c) out[c] = pp[c];
+        }
+        resume = true;
+      } else {
+        resume = false;
+      }
+      for (int c = 0; c < 3; ++c) prevfp[c] = out[c];
+      if (k < N)
+        for (int c = 0; c < 3; ++c) fp[12 * k + 3 * leg + c] = out[c];
+    }
+  }
+  __syncwarp();
+  double *dst = rec_out + (size_t)p * in_stride;
+  for (int e = lane; e < in_stride; e += 32) dst[e] = rec[e];
+}
+
 cudaError_t launch_sequencer(int n, const SeqModel &M, const double *seq_in, const uint8_t *measured, double *rec_out,
                              uint8_t *contact_out, int in_stride, cudaStream_t st) {
   if (n <= 0) return cudaSuccess;
-  sequencer_kernel<<<(n + 63) / 64, 64, 0, st>>>(n, M, seq_in, measured, rec_out, contact_out, in_stride);
+  if (getenv("B200QP_SERIAL_SEQUENCER") != nullptr)  // the thread-per-robot statement of the same algorithm (cross-check)
+    sequencer_kernel<<<(n + 63) / 64, 64, 0, st>>>(n, M, seq_in, measured, rec_out, contact_out, in_stride);
+  else
+    sequencer_warp_kernel<<<(n + SEQ_WARPS - 1) / SEQ_WARPS, 32 * SEQ_WARPS, 0, st>>>(n, M, seq_in, measured, rec_out, contact_out,
+                                                                                   in_stride);
   return cudaGetLastError();
 }
 }  // namespace b200qp

@@ -583,3 +583,20 @@ def test_warm_and_hot_start_reach_the_same_optimum(mode, go2_params):
     warm.SetWarmStart(mode)
     f4, _, i4 = warm.solve_records(other["rec"], other["contact"])
     assert np.array_equal(i4.acados_num_iter, i3c.acados_num_iter)
+
+
+def test_sequencer_warp_kernel_equals_the_serial_statement(monkeypatch):
+    """The warp-per-robot sequencer performs the serial kernel's floating-point operations in the same order: identical bits."""
+    from dfki_quad_b200 import sequencer as sq
+
+    N, n = 20, 1500
+    batch = sq.random_batch(n, N, seed=123, gaits=tuple(sq.gaitmod.GAIT_NAMES))
+    rng = np.random.default_rng(1)
+    meas = rng.integers(0, 2, (n, 4)).astype(np.uint8)
+    mpc = _mpc(N, n)
+    mpc.set_model(**sq.go2_seq_model())
+    rec_w, ct_w = mpc.sequence_records(batch["seq_in"], meas)
+    monkeypatch.setenv("B200QP_SERIAL_SEQUENCER", "1")
+    rec_s, ct_s = mpc.sequence_records(batch["seq_in"], meas)
+    assert np.array_equal(ct_w, ct_s)
+    assert np.array_equal(rec_w.view(np.uint64), rec_s.view(np.uint64))
