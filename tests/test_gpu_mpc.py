@@ -600,3 +600,49 @@ def test_sequencer_warp_kernel_equals_the_serial_statement(monkeypatch):
     rec_s, ct_s = mpc.sequence_records(batch["seq_in"], meas)
     assert np.array_equal(ct_w, ct_s)
     assert np.array_equal(rec_w.view(np.uint64), rec_s.view(np.uint64))
+
+
+def test_randomised_options_soak():
+    """Random horizons, gaits, weights, alpha, friction (incl. mu > 1: the x/y box rows can bind, NNLS dual path), force limits,
+    solver and warm-start mode: every problem that fits its solver converges to KKT <= 1e-6, is feasible, has exact zeros on
+    swing legs, and a sample agrees with the (polished) oracle to 1e-5."""
+    from dfki_quad_b200 import BatchedMPC, sequencer
+    from dfki_quad_b200 import gait as gaitmod
+
+    rng = np.random.default_rng(7)
+    cfg = sequencer.GO2_MPC
+    for trial in range(12):
+        N = int(rng.choice([1, 2, 5, 8, 10, 13, 16, 20]))
+        n = 192
+        gaits = tuple(rng.choice(gaitmod.GAIT_NAMES, size=rng.integers(1, 4), replace=False))
+        w = np.array(cfg["state_weights_move"], float) * np.exp(rng.normal(0, 1.0, 12))
+        alpha = float(10 ** rng.uniform(-5.5, -3))
+        mu = float(rng.choice([0.2, 0.4, 0.6, 0.9, 1.2]))
+        fmin = float(rng.choice([0.0, 0.0, 5.0]))
+        fmax = float(rng.choice([120.0, 250.0, 400.0]))
+        solver = str(rng.choice(["CONDENSED_ADMM", "SPARSE_RICCATI", "AUTO"]))
+        ws = int(rng.choice([0, 0, 2]))
+        b = sequencer.random_batch(n, N, seed=2000 + trial, gaits=gaits)
+        mpc = BatchedMPC(alpha, w, mu, fmin, fmax, solver, warm_start=ws, horizon=N, dt=cfg["dt"], max_batch=n)
+        f, x, info = mpc.solve_records(b["rec"], b["contact"])
+        if ws:
+            f, x, info = mpc.solve_records(b["rec"], b["contact"])
+        tag = (trial, N, solver, ws, mu, fmin, fmax, alpha, gaits)
+        nfree = 3 * b["contact"].reshape(n, -1).sum(axis=1)
+        fits = (nfree <= 156) | (solver != "CONDENSED_ADMM")
+        ok = info.success
+        assert ok[fits].all(), (tag, np.unique(info.return_code[fits], return_counts=True))
+        assert (info.kkt[ok].max(axis=1) <= 1e-6).all(), tag
+        F = f.reshape(n, N, 4, 3)[ok]
+        assert (np.abs(F[..., 0]) <= mu * F[..., 2] + 1e-6).all() and (np.abs(F[..., 1]) <= mu * F[..., 2] + 1e-6).all(), tag
+        assert (F[..., 2] <= fmax + 1e-6).all() and np.all(F[b["contact"][ok] == 0] == 0.0), tag
+        assert (F[..., 2][b["contact"][ok] != 0] >= fmin - 1e-6).all(), tag
+        params = dict(mo.GO2_PARAMS, weights=w, alpha=alpha, mu=mu, fmin=fmin, fmax=fmax)
+        p = int(np.nonzero(ok)[0][trial % int(ok.sum())])
+        U, X, qp, dq = mo.solve_reference_qp(N, b["rec"][p], b["contact"][p], params)
+        x2, _, okp = mo.polish_active_set(dq["H"], dq["g"], dq["A"], np.where(dq["l"] <= -mo.INF_THRESHOLD, -np.inf, dq["l"]),
+                                          np.where(dq["u"] >= mo.INF_THRESHOLD, np.inf, dq["u"]), U.reshape(-1),
+                                          _ipm_duals(dq, U.reshape(-1)))
+        Uref = x2.reshape(N, 12) if okp else U
+        assert np.abs(f[p].reshape(N, 12) - Uref).max() / max(1.0, np.abs(Uref).max()) <= 1e-5, tag
+        mpc.close()
