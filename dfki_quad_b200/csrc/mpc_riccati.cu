@@ -208,6 +208,9 @@ __global__ void __launch_bounds__(BS, MINB) mpc_riccati_kernel(const MpcParams P
     const int kf = tid, ks = tid >> 2;
     double hh[10] = {P.fmax, P.fmax, P.fmax, P.fmax, P.fmax, -P.fmin, 0.0, 0.0, 0.0, 0.0};
     double s[10], z[10];
+    double inv_s[10], inv_z[10];  // 1 / s, 1 / z of the current iterate
+#pragma unroll
+    for (int r = 0; r < 10; ++r) inv_s[r] = inv_z[r] = 1.0;
     {
       double g0[10];
       G_apply(on ? sU[3 * kf] : 0.0, on ? sU[3 * kf + 1] : 0.0, on ? sU[3 * kf + 2] : 0.0, mu_f, g0);
@@ -375,7 +378,11 @@ __global__ void __launch_bounds__(BS, MINB) mpc_riccati_kernel(const MpcParams P
         if (on) {
           double w[10];
 #pragma unroll
-          for (int r = 0; r < 10; ++r) w[r] = z[r] / s[r];
+          for (int r = 0; r < 10; ++r) {  // the only FP64 divisions of the iteration: 1/s and 1/z, reused by both passes below
+            inv_s[r] = 1.0 / s[r];
+            inv_z[r] = 1.0 / z[r];
+            w[r] = z[r] * inv_s[r];
+          }
           Rb[0] = P.alpha + (w[0] + w[1]) + (w[6] + w[7]);
           Rb[1] = P.alpha + (w[2] + w[3]) + (w[8] + w[9]);
           Rb[2] = P.alpha + (w[4] + w[5]) + mu_f * mu_f * ((w[6] + w[7]) + (w[8] + w[9]));
@@ -531,7 +538,7 @@ __global__ void __launch_bounds__(BS, MINB) mpc_riccati_kernel(const MpcParams P
 #pragma unroll
             for (int r = 0; r < 10; ++r) {
               const double rc = (pass == 0) ? s[r] * z[r] : (s[r] * z[r] + ds[r] * dz[r] - sigma_mu);
-              t10[r] = (z[r] * rp[r] - rc) / s[r];
+              t10[r] = (z[r] * rp[r] - rc) * inv_s[r];
             }
             GT_apply(t10, mu_f, rt);
             rt[0] += rd[0]; rt[1] += rd[1]; rt[2] += rd[2];
@@ -629,16 +636,16 @@ __global__ void __launch_bounds__(BS, MINB) mpc_riccati_kernel(const MpcParams P
         double st[1] = {1.0};
         double dsn[10], dzn[10];
         if (on) {
-          double Gd[10];
+          double Gd[10], tmax = 0.0;
           G_apply(sDU[3 * kf], sDU[3 * kf + 1], sDU[3 * kf + 2], mu_f, Gd);
 #pragma unroll
           for (int r = 0; r < 10; ++r) {
             const double rc = (pass == 0) ? s[r] * z[r] : (s[r] * z[r] + ds[r] * dz[r] - sigma_mu);
             dsn[r] = -rp[r] - Gd[r];
-            dzn[r] = (-rc - z[r] * dsn[r]) / s[r];
-            if (dsn[r] < 0.0) st[0] = fmin(st[0], -s[r] / dsn[r]);
-            if (dzn[r] < 0.0) st[0] = fmin(st[0], -z[r] / dzn[r]);
+            dzn[r] = (-rc - z[r] * dsn[r]) * inv_s[r];
+            tmax = fmax(tmax, fmax(-dsn[r] * inv_s[r], -dzn[r] * inv_z[r]));  // largest relative decrease
           }
+          if (tmax > 1.0) st[0] = 1.0 / tmax;  // step to the boundary = 1 / max(-ds/s, -dz/z), capped at 1
         }
         block_reduce<1>(st, red, OpMin());
         if (pass == 0) {
