@@ -646,3 +646,37 @@ def test_randomised_options_soak():
         Uref = x2.reshape(N, 12) if okp else U
         assert np.abs(f[p].reshape(N, 12) - Uref).max() / max(1.0, np.abs(Uref).max()) <= 1e-5, tag
         mpc.close()
+
+
+def test_plugin_interface_calls_like_the_reference(go2_params):
+    """The MPCInterface call sequence of mit_controller_node.cpp:764-794 - UpdateState, UpdateModel, UpdateGaitSequence,
+    GetWrenchSequence - on the batched mirror: same answer as the record-level entry point, WrenchSequence / MPCPrediction /
+    SolverInformation shaped as in the reference (wrench_sequence.hpp:9, mpc_prediction.hpp:7-13, mpc_interface.hpp:10-20)."""
+    from dfki_quad_b200 import BatchedMPC, sequencer
+
+    N, n = 10, 64
+    batch = sequencer.random_batch(n, N, seed=17, gaits=("TROT", "STAND"))
+    cfg = sequencer.GO2_MPC
+    mpc = BatchedMPC(cfg["alpha"], cfg["state_weights_move"], cfg["mu"], cfg["fmin"], cfg["fmax"], "PARTIAL_CONDENSING_OSQP",
+                     horizon=N, dt=cfg["dt"], max_batch=n)  # the reference's solver string maps onto the condensed kernel
+    with pytest.raises(RuntimeError):
+        mpc.GetWrenchSequence()  # nothing updated yet
+    mpc.UpdateState(batch["quat"], batch["pos"], batch["omega"], batch["vel"])
+    mpc.UpdateModel(sequencer.GO2_MASS, sequencer.GO2_INERTIA, sequencer.GO2_COM)
+    traj = batch["traj"]
+    mpc.UpdateGaitSequence(dict(contact_sequence=np.pad(batch["contact"], ((0, 0), (0, 5), (0, 0))),  # longer than N, like GAIT_SEQUENCE_SIZE
+                                foot_position_sequence=batch["foot_pos"],
+                                desired_reference_trajectory_orientation=traj["des_quat"],
+                                desired_reference_trajectory_position=traj["des_pos"],
+                                reference_trajectory_twist=traj["ref_twist"], reference_trajectory_velocity=traj["ref_vel"]))
+    forces, pred, info = mpc.GetWrenchSequence()
+    assert forces.shape == (n, N, 4, 3) and pred.raw_data.shape == (n, N + 1, 13)
+    assert pred.orientation.shape == (n, N + 1, 4) and pred.position.shape == (n, N + 1, 3)
+    assert info.success.all() and (info.return_code == 0).all() and info.acados_num_iter.min() >= 0 and info.total_solver_time > 0
+    f2, x2, i2 = mpc.solve_records(batch["rec"], batch["contact"])
+    assert np.array_equal(forces.reshape(n, N, 12), f2) and np.array_equal(pred.raw_data, x2)
+    # prediction row 0 is the measured state (mpc.cpp:392-396, 460-466): position without the COM offset, quaternion up to sign
+    assert np.allclose(pred.position[:, 0], batch["pos"], atol=1e-12)
+    assert np.allclose(np.abs(np.sum(pred.orientation[:, 0] * batch["quat"], axis=1)), 1.0, atol=1e-12)
+    assert np.allclose(pred.linear_velocity[:, 0], batch["vel"], atol=1e-12)
+    _check_against_oracle(N, batch, f2, x2, i2, go2_params, range(2))
