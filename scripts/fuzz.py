@@ -39,6 +39,9 @@ for trial in range(int(os.environ.get("TRIALS", "24"))):
     swing0 = np.all(F[b["contact"][ok] == 0] == 0.0)
     flag = "" if (ok[fits].all() and (kk[ok] <= 1e-6).all() and worst < 1e-4 and feas and swing0) else "   <-- CHECK"
     bad += bool(flag)
+    if flag:
+        badp = np.nonzero(~ok & fits)[0]
+        print("    failed:", [(int(q), int(info.return_code[q]), int(info.acados_num_iter[q]), info.kkt[q].tolist(), int(nfree[q])) for q in badp[:4]])
     print(f"{trial:2d} N={N:2d} {solver:15s} ws={ws} mu={mu} fmin={fmin} fmax={fmax} alpha={alpha:.1e} gaits={','.join(gaits):40s} ok(fits)={ok[fits].mean():.4f} "
           f"kkt_max={kk[ok].max() if ok.any() else float('nan'):.1e} oracle_rel={worst:.1e} feas={feas} swing0={swing0} iters={info.acados_num_iter.mean():.1f}{flag}", flush=True)
     mpc.close()
