@@ -134,6 +134,21 @@ static void fill_params(b200qp_mpc *h) {
 extern "C" {
 
 static int32_t ensure_warm_buffers(b200qp_mpc *h);
+void b200qp_mpc_destroy(b200qp_mpc *h);
+void b200qp_wbc_destroy(b200qp_wbc *h);
+}
+// a create() that fails half-way must not leak what it already allocated
+namespace {
+struct MpcGuard {
+  b200qp_mpc *h;
+  ~MpcGuard() { if (h) b200qp_mpc_destroy(h); }
+};
+struct WbcGuard {
+  b200qp_wbc *h;
+  ~WbcGuard() { if (h) b200qp_wbc_destroy(h); }
+};
+}  // namespace
+extern "C" {
 
 const char *b200qp_version(void) { return "b200qp 0.1 (sm_100a)"; }
 const char *b200qp_last_error(void) { return g_err.c_str(); }
@@ -176,6 +191,7 @@ int32_t b200qp_mpc_create(const b200qp_mpc_config *cfg, b200qp_mpc **out) {
   CK(cudaSetDevice(cfg->device));
   b200qp_mpc *h = new (std::nothrow) b200qp_mpc();
   if (!h) return B200QP_ERR_ARG;
+  MpcGuard guard{h};
   h->cfg = *cfg;
   fill_params(h);
   cudaDeviceProp prop;
@@ -245,6 +261,7 @@ int32_t b200qp_mpc_create(const b200qp_mpc_config *cfg, b200qp_mpc **out) {
   CK(cudaMalloc(&h->d_seq, nb * B200QP_SEQ_IN_DOUBLES * sizeof(double)));
   CK(cudaMalloc(&h->d_measured, nb * 4));
   CK(cudaMallocHost(&h->h_seq, nb * B200QP_SEQ_IN_DOUBLES * sizeof(double) + nb * 4));
+  guard.h = nullptr;
   *out = h;
   return B200QP_OK;
 }
@@ -843,6 +860,7 @@ int32_t b200qp_wbc_create(const b200qp_wbc_config *cfg, b200qp_wbc **out) {
   CK(cudaSetDevice(cfg->device));
   b200qp_wbc *h = new (std::nothrow) b200qp_wbc();
   if (!h) return B200QP_ERR_ARG;
+  WbcGuard guard{h};
   h->cfg = *cfg;
   h->P.nq = cfg->nq;
   h->P.neq = cfg->neq;
@@ -870,6 +888,7 @@ int32_t b200qp_wbc_create(const b200qp_wbc_config *cfg, b200qp_wbc **out) {
   CK(cudaMalloc(&h->d_x, nb * nq * sizeof(double)));
   CK(cudaMalloc(&h->d_info, nb * sizeof(b200qp_solver_info)));
   CK(cudaMalloc(&h->d_next, sizeof(int)));
+  guard.h = nullptr;
   *out = h;
   return B200QP_OK;
 }
