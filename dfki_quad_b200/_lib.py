@@ -13,9 +13,11 @@ ACADOS_SUCCESS, ACADOS_NAN_DETECTED, ACADOS_MAXITER, ACADOS_MINSTEP, ACADOS_QP_F
 NAN_AFTER_SUCCESS = -7777
 SOLVER_CONDENSED_ADMM, SOLVER_SPARSE_RICCATI, SOLVER_AUTO = 0, 1, 2
 SOLVERS = {"CONDENSED_ADMM": 0, "SPARSE_RICCATI": 1, "AUTO": 2,
-           # the reference's acados plan names (mit_controller_node.cpp:502-519) map onto the two kernels
-           "PARTIAL_CONDENSING_OSQP": 0, "FULL_CONDENSING_HPIPM": 0, "FULL_CONDENSING_QPOASES": 0,
-           "FULL_CONDENSING_DAQP": 0, "PARTIAL_CONDENSING_HPIPM": 1}
+           # The reference's acados plan names (mit_controller_node.cpp:502-519).  Its solvers take any problem size, so the
+           # condensing plans map onto AUTO (condensed kernel where the reduced problem fits, Riccati kernel otherwise);
+           # the sparse HPIPM plan maps onto the Riccati interior-point kernel.
+           "PARTIAL_CONDENSING_OSQP": 2, "FULL_CONDENSING_HPIPM": 2, "FULL_CONDENSING_QPOASES": 2,
+           "FULL_CONDENSING_DAQP": 2, "PARTIAL_CONDENSING_HPIPM": 1}
 
 
 class MpcConfig(C.Structure):

@@ -658,7 +658,7 @@ def test_plugin_interface_calls_like_the_reference(go2_params):
     batch = sequencer.random_batch(n, N, seed=17, gaits=("TROT", "STAND"))
     cfg = sequencer.GO2_MPC
     mpc = BatchedMPC(cfg["alpha"], cfg["state_weights_move"], cfg["mu"], cfg["fmin"], cfg["fmax"], "PARTIAL_CONDENSING_OSQP",
-                     horizon=N, dt=cfg["dt"], max_batch=n)  # the reference's solver string maps onto the condensed kernel
+                     horizon=N, dt=cfg["dt"], max_batch=n)  # the reference's plan string -> AUTO (condensed kernel here: n <= 156)
     with pytest.raises(RuntimeError):
         mpc.GetWrenchSequence()  # nothing updated yet
     mpc.UpdateState(batch["quat"], batch["pos"], batch["omega"], batch["vel"])
