@@ -38,8 +38,8 @@ struct WMax { __device__ double operator()(double a, double b) const { return fm
 struct WMin { __device__ double operator()(double a, double b) const { return fmin(a, b); } };
 struct WSum { __device__ double operator()(double a, double b) const { return a + b; } };
 
-// In-place lower Cholesky of the n x n row-major matrix A (ld = n) by the whole block, then Li = L^-1 (row-major).
-__device__ void chol_and_inverse(double *A, double *Li, int n, double *diag0) {
+// In-place lower Cholesky of the n x n row-major matrix A (ld = n) by the whole block, then A <- L^-1 (lower triangle, row-major).
+__device__ void chol_and_inverse(double *A, int n, double *diag0) {
   const int tid = threadIdx.x, BS = blockDim.x;
   if (tid < n) diag0[tid] = A[tid * n + tid];
   __syncthreads();
@@ -59,16 +59,20 @@ __device__ void chol_and_inverse(double *A, double *Li, int n, double *diag0) {
     }
     __syncthreads();
   }
-  // L^-1: thread j computes column j by forward substitution
-  for (int j = tid; j < n; j += BS) {
-    for (int i = 0; i < j; ++i) Li[i * n + j] = 0.0;
-    for (int i = j; i < n; ++i) {
-      double acc = (i == j) ? 1.0 : 0.0;
-      for (int k = j; k < i; ++k) acc -= A[i * n + k] * Li[k * n + j];
-      Li[i * n + j] = acc * diag0[i];
+  // L^-1 IN PLACE (the factor is not needed afterwards, and a separate array would cost an n x n block of shared memory = two
+  // resident blocks per SM): columns from the last to the first, X[i][j] = -X[j][j] * sum_{k=j+1..i} X[i][k] L[k][j], thread i
+  // owns row i; column j of L is only overwritten after every row has read it.
+  for (int j = n - 1; j >= 0; --j) {
+    double t = 0.0;
+    if (tid > j && tid < n) {
+      for (int k = j + 1; k <= tid; ++k) t = fma(A[tid * n + k], A[k * n + j], t);
+      t *= -diag0[j];
     }
+    __syncthreads();
+    if (tid > j && tid < n) A[tid * n + j] = t;
+    else if (tid == j) A[j * n + j] = diag0[j];
+    __syncthreads();
   }
-  __syncthreads();
 }
 
 // dx, dnu from r~ (srt) and re (sre):  u1 = -L^-1 r~,  dnu = S^-1 (re + Y'u1),  dx = L^-T (u1 - Y dnu)
@@ -117,7 +121,7 @@ __device__ void kkt_solve(int nq, int me, const double *sLi, const double *sY, c
 // NQ_ / ME_ / MI_ > 0 fix the problem dimensions at compile time (Go2 reduced TSID: 30 / 18 / 28): the element loops divide by
 // them (a runtime integer division is ~25 instructions) and their inner products unroll.  0 = take the dimension from P.
 template <int NQ_, int ME_, int MI_>
-__global__ void __launch_bounds__(64) wbc_qp_kernel(const WbcParams P, int nprob, const double *__restrict__ Hg,
+__global__ void __launch_bounds__(64, 5) wbc_qp_kernel(const WbcParams P, int nprob, const double *__restrict__ Hg,
                                                     const double *__restrict__ gg, const double *__restrict__ Ag,
                                                     const double *__restrict__ log, const double *__restrict__ hig,
                                                     double *__restrict__ xout, b200qp_solver_info *__restrict__ info,
@@ -128,11 +132,11 @@ __global__ void __launch_bounds__(64) wbc_qp_kernel(const WbcParams P, int nprob
   double *sAe = sH + nq * nq;       // [me*nq] row-major
   double *sAi = sAe + me * nq;      // [mi*nq]
   double *sPhi = sAi + mi * nq;     // [nq*nq] Phi -> L
-  double *sLi = sPhi + nq * nq;     // [nq*nq] L^-1
-  double *sY = sLi + nq * nq;       // [nq*me]  Y = L^-1 Aeq'
-  double *sS = sY + nq * me;        // [me*me]  S -> Ls
-  double *sSi = sS + me * me;       // [me*me]  Ls^-1
-  double *sx = sSi + me * me;       // [nq]
+  double *sLi = sPhi;               // L^-1 overwrites the factor in place
+  double *sY = sPhi + nq * nq;      // [nq*me]  Y = L^-1 Aeq'
+  double *sS = sY + nq * me;        // [me*me]  S -> Ls -> Ls^-1
+  double *sSi = sS;
+  double *sx = sS + me * me;        // [nq]
   double *sg = sx + nq;             // [nq]
   double *snu = sg + nq;            // [me]
   double *sbe = snu + me;           // [me]
@@ -282,7 +286,7 @@ __global__ void __launch_bounds__(64) wbc_qp_kernel(const WbcParams P, int nprob
         sPhi[e] = a;
       }
       __syncthreads();
-      chol_and_inverse(sPhi, sLi, nq, sd0);
+      chol_and_inverse(sPhi, nq, sd0);
       for (int e = tid; e < nq * me; e += BS) {  // Y[i][r] = sum_{k<=i} Li[i][k] Aeq[r][k]
         const int i = e / me, r = e - i * me;
         double a = 0.0;
@@ -298,7 +302,7 @@ __global__ void __launch_bounds__(64) wbc_qp_kernel(const WbcParams P, int nprob
         sS[e] = a;
       }
       __syncthreads();
-      chol_and_inverse(sS, sSi, me, sd0);
+      chol_and_inverse(sS, me, sd0);
 
       if (init) {  // starting point as in CVXOPT's coneqp: solve with W = I, then shift s and z into the interior
         if (row) sw[tid] = (hasu ? hi : 0.0) - (hasl ? lo : 0.0);
@@ -418,7 +422,7 @@ __global__ void __launch_bounds__(64) wbc_qp_kernel(const WbcParams P, int nprob
 
 size_t wbc_smem_bytes(const WbcParams &P) {
   const size_t nq = P.nq, me = P.neq, mi = P.nin;
-  const size_t d = nq * nq * 3 + me * nq + mi * nq + nq * me + 2 * me * me + 10 * nq + 7 * me + (nq > me ? nq : me) + mi + 8;
+  const size_t d = nq * nq * 2 + me * nq + mi * nq + nq * me + me * me + 10 * nq + 7 * me + (nq > me ? nq : me) + mi + 8;
   return d * sizeof(double) + 64;
 }
 
