@@ -784,6 +784,7 @@ __global__ void __launch_bounds__(BS, (BS == 64 && !B200QP_TC_GJ) ? 6 : 1) mpc_a
       if (tid == 0) {
         const volatile int *flag = B.ready + prob / B.ready_chunk;
         while (*flag == 0) __nanosleep(500);
+        __threadfence_system();  // acquire: the record reads below must not be satisfied by anything older than the flag
       }
       __syncthreads();
     }
