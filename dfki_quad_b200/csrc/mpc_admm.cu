@@ -1240,6 +1240,7 @@ __global__ void __launch_bounds__(BS, (BS == 64 && !B200QP_TC_GJ) ? 6 : 1) mpc_a
         __syncthreads();
         double grp = 0.0;
         if (tid < nr) grp = vp[0] * s_r[3 * ap] + vp[1] * s_r[3 * ap + 1] + vp[2] * s_r[3 * ap + 2];
+        __syncthreads();  // s_r is part of the pivot-row staging area (prow = s_v..s_w) the inversion below writes first
         PH(6);
         constexpr bool TC = (BS == 64 && NV == 64 && B200QP_TC_GJ);
         double wred = 0.0;

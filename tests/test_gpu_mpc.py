@@ -680,3 +680,35 @@ def test_plugin_interface_calls_like_the_reference(go2_params):
     assert np.allclose(np.abs(np.sum(pred.orientation[:, 0] * batch["quat"], axis=1)), 1.0, atol=1e-12)
     assert np.allclose(pred.linear_velocity[:, 0], batch["vel"], atol=1e-12)
     _check_against_oracle(N, batch, f2, x2, i2, go2_params, range(2))
+
+
+def test_streamed_inputs_give_the_resident_answer_every_time():
+    """Host-buffer call with streamed record chunks (kernel polls per-chunk ready flags) vs the device-resident solve of the same
+    batch: identical bits, 25 times in a row (pinned and pageable callers)."""
+    import torch
+    from dfki_quad_b200 import sequencer
+
+    N, n = 10, 4096
+    batch = sequencer.random_batch(n, N, seed=314, gaits=("TROT", "PACE", "WALKING_TROT"))
+    mpc = _mpc(N, n)
+    dev = torch.device("cuda", 0)
+    ext = torch.cuda.ExternalStream(mpc.stream(), device=dev)
+    with torch.cuda.stream(ext):
+        d_in, d_ct = torch.from_numpy(batch["rec"]).to(dev), torch.from_numpy(batch["contact"]).to(dev)
+        d_f = torch.zeros((n, N, 12), dtype=torch.float64, device=dev)
+        d_x = torch.zeros((n, N + 1, 13), dtype=torch.float64, device=dev)
+        d_i = torch.zeros((n, 48), dtype=torch.uint8, device=dev)
+    ext.synchronize()
+    mpc.solve_device(n, d_in.data_ptr(), d_ct.data_ptr(), d_f.data_ptr(), d_x.data_ptr(), d_i.data_ptr(), sync=True)
+    f_ref, x_ref = d_f.cpu().numpy(), d_x.cpu().numpy()
+    rec_p, ct_p = torch.from_numpy(batch["rec"]).pin_memory().numpy(), torch.from_numpy(batch["contact"]).pin_memory().numpy()
+    f_p = torch.zeros((n, N, 12), dtype=torch.float64).pin_memory().numpy()
+    x_p = torch.zeros((n, N + 1, 13), dtype=torch.float64).pin_memory().numpy()
+    for rep in range(25):
+        f_p[:] = 0.0
+        if rep % 2 == 0:
+            f, x, info = mpc.solve_records(rec_p, ct_p, f_p, x_p)
+        else:
+            f, x, info = mpc.solve_records(batch["rec"], batch["contact"])
+        assert info.success.all(), rep
+        assert np.array_equal(f, f_ref) and np.array_equal(x, x_ref), rep
