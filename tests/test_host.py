@@ -302,3 +302,20 @@ def test_rollout_plant_conserves_what_it_should():
     f[:, 2:, 2] = 0.5 * w * xf / (xf + xr)
     q2, p2, w2, v2 = rollout.srbd_step(quat, pos, np.zeros((n, 3)), np.zeros((n, 3)), feet, f, 0.05)
     assert np.abs(v2).max() < 1e-12 and np.abs(w2).max() < 1e-12
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` needs no GPU (it times the CPU restatement): one JSON line with the contract keys."""
+    import json
+
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--batch", "64", "--steps", "1",
+                          "--warmup", "1"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in line, k
+    assert line["impl"] == "reference" and line["value"] > 0 and line["unit"] == "solves/s" and line["vs_baseline"] is None
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"]
+    assert line["cpu_baseline"]["kind"] in ("port", "reference") and line["cpu_baseline"]["cores"] >= 1
+    assert "workload" in line["config"]
