@@ -712,3 +712,27 @@ def test_streamed_inputs_give_the_resident_answer_every_time():
             f, x, info = mpc.solve_records(batch["rec"], batch["contact"])
         assert info.success.all(), rep
         assert np.array_equal(f, f_ref) and np.array_equal(x, x_ref), rep
+
+
+def test_bench_own_arm_prints_the_contract_line():
+    """bench.py on a small batch: one JSON line with every key the measurement contract names."""
+    import json
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--batch", "512", "--steps", "3", "--warmup", "3",
+                          "--cpu-budget", "1", "--no-closed-loop"], capture_output=True, text=True, timeout=900, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+              "dtype", "data", "config", "e2e", "gpu_launches", "clocks", "roofline", "cpu_baseline"):
+        assert k in line, k
+    assert line["value"] > 0 and line["n_gpus"] == 1 and line["steps"] == 3 and line["dtype"] == "f64" and line["scaling"] == "weak"
+    assert line["e2e"]["value"] > 0 and line["e2e"]["h2d_bytes_per_step"] > 0 and line["e2e"]["d2h_bytes_per_step"] > 0
+    assert line["gpu_launches"] > 0 and line["config"]["converged_fraction"] == 1.0 and "workload" in line["config"]
+    r = line["roofline"]
+    assert r["bound"] in ("hbm", "tensor") and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12 and r["unit"] == "GB/s"
+    assert line["cpu_baseline"]["value"] > 0 and line["cpu_baseline"]["kind"] == "port"
+    assert set(line["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
