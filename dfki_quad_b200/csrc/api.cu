@@ -76,6 +76,7 @@ struct b200qp_mpc {
   b200qp_solver_info *d_info = nullptr;
   int *d_bin_count = nullptr;  // [5] counts (4 condensed bins + overflow), [5..8] condensed work counters, [9] Riccati counter
   int *d_bin_lists = nullptr;  // [5][max_batch]
+  int *d_retry = nullptr;      // [max_batch] solver AUTO: problems handed from the condensed to the Riccati kernel
   double *d_hscratch[4] = {nullptr, nullptr, nullptr, nullptr};
   int grid[4] = {0, 0, 0, 0};
   double *d_ric_scratch = nullptr;
@@ -222,6 +223,7 @@ int32_t b200qp_mpc_create(const b200qp_mpc_config *cfg, b200qp_mpc **out) {
   CK(cudaMalloc(&h->d_info, nb * sizeof(b200qp_solver_info)));
   CK(cudaMalloc(&h->d_bin_count, 16 * sizeof(int)));
   CK(cudaMalloc(&h->d_bin_lists, 5 * nb * sizeof(int)));
+  CK(cudaMalloc(&h->d_retry, nb * sizeof(int)));
   CK(cudaMemset(h->d_forces, 0, nb * N * 12 * sizeof(double)));
   CK(cudaMemset(h->d_xpred, 0, nb * (N + 1) * 13 * sizeof(double)));
   if (cfg->solver != B200QP_SOLVER_SPARSE_RICCATI) {
@@ -278,6 +280,7 @@ void b200qp_mpc_destroy(b200qp_mpc *h) {
   cudaFree(h->d_info);
   cudaFree(h->d_bin_count);
   cudaFree(h->d_bin_lists);
+  cudaFree(h->d_retry);
   for (int b = 0; b < 4; ++b) cudaFree(h->d_hscratch[b]);
   cudaFree(h->d_ric_scratch);
   cudaFreeHost(h->h_in);
@@ -380,6 +383,8 @@ static int32_t solve_device_impl(b200qp_mpc *h, int32_t n, const double *d_in, c
       B.bin_count = h->d_bin_count + b;
       B.bin_next = h->d_bin_count + 5 + b;
       B.hscratch = h->d_hscratch[b];
+      B.retry_list = autosel ? h->d_retry : nullptr;
+      B.retry_count = autosel ? h->d_bin_count + 10 : nullptr;
       B.warm_mode = (h->cfg.warm_start > 0 && h->d_warm_x != nullptr && dbg_index < 0 && !h->want_duals) ? h->cfg.warm_start : 0;
       B.warm_x = h->d_warm_x;
       B.warm_y = h->d_warm_y;
@@ -420,6 +425,13 @@ static int32_t solve_device_impl(b200qp_mpc *h, int32_t n, const double *d_in, c
       CK(cudaEventRecord(h->ev_join[b], h->bin_stream[b]));
       CK(cudaStreamWaitEvent(h->stream, h->ev_join[b], 0));
     }
+  if (autosel) {  // second opinion: what the condensed kernel gave up on goes through the interior-point kernel (usually nothing)
+    int g = h->ric_grid < 64 ? h->ric_grid : 64;
+    CK(launch_mpc_riccati(h->P, n, d_in, d_contact, d_forces, d_xpred, d_info,
+                          h->want_duals ? h->d_lam_box : nullptr, h->want_duals ? h->d_lam_g : nullptr,
+                          h->d_ric_scratch, h->d_bin_count + 11, g, h->stream, nullptr, h->d_retry, h->d_bin_count + 10));
+    ++launches;
+  }
   CK(cudaEventRecord(h->ev1, h->stream));
   h->have_timing = true;
   h->last_launches = launches;

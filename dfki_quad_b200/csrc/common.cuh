@@ -34,6 +34,10 @@ struct MpcBuffers {
   const int *bin_count;
   int *bin_next;     // atomic work counter
   double *hscratch;  // [gridDim.x][BS*BS] condensed Hessian per resident block
+  // solver AUTO: problems the condensed kernel could not solve (iteration cap) are appended here for a second opinion by the
+  // Riccati kernel; nullptr otherwise
+  int *retry_list;
+  int *retry_count;
   // chunked input streaming (host-buffer entry point): ready[c] != 0 once the records of chunk c = prob / ready_chunk have
   // landed in device memory; nullptr = everything is resident
   const int *ready;

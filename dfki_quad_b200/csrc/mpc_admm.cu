@@ -1521,6 +1521,8 @@ __global__ void __launch_bounds__(BS, (BS == 64 && !B200QP_TC_GJ) ? 6 : 1) mpc_a
       inf.kkt[2] = kkt_ineq;
       inf.kkt[3] = kkt_comp;
       B.info[prob] = inf;
+      if (B.retry_list != nullptr && (status == B200QP_ACADOS_MAXITER || status == B200QP_ACADOS_MINSTEP))
+        B.retry_list[atomicAdd(B.retry_count, 1)] = prob;
     }
   }
 }

@@ -48,7 +48,8 @@ extern "C" {
 #define B200QP_SOLVER_CONDENSED_ADMM 0 /* replaces PARTIAL_CONDENSING_OSQP with small cond_N / FULL_CONDENSING_* */
 #define B200QP_SOLVER_SPARSE_RICCATI 1 /* replaces PARTIAL_CONDENSING_HPIPM with cond_N == N                     */
 #define B200QP_SOLVER_AUTO 2           /* per problem: condensed kernel when the reduced size fits (<= 156 free     */
-                                       /* variables), sparse Riccati kernel otherwise; same optimum either way      */
+                                       /* variables), sparse Riccati kernel otherwise; same optimum either way;     */
+                                       /* problems the condensed kernel gives up on are retried on the Riccati one  */
 
 /* Replaces the MPC constructor arguments (mpc.hpp:117-127) + compile-time constants (mit_controller_params.hpp). */
 typedef struct b200qp_mpc_config {

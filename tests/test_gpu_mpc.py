@@ -736,3 +736,21 @@ def test_bench_own_arm_prints_the_contract_line():
     assert r["bound"] in ("hbm", "tensor") and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12 and r["unit"] == "GB/s"
     assert line["cpu_baseline"]["value"] > 0 and line["cpu_baseline"]["kind"] == "port"
     assert set(line["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
+
+
+def test_auto_solver_gives_condensed_failures_a_second_opinion(go2_params):
+    """Solver AUTO hands problems the condensed kernel gives up on (iteration cap) to the Riccati kernel.  With the ADMM cap set
+    absurdly low the condensed kernel alone fails most problems; AUTO still solves all of them, to the same optimum."""
+    from dfki_quad_b200 import sequencer
+
+    N, n = 10, 512
+    batch = sequencer.random_batch(n, N, seed=55, gaits=("TROT", "WALKING_TROT"))
+    f_ref, x_ref, i_ref = _mpc(N, n).solve_records(batch["rec"], batch["contact"])
+    fc, _, ic = _mpc(N, n, admm_max_iter=10, polish_max_rounds=1).solve_records(batch["rec"], batch["contact"])
+    assert (~ic.success).mean() > 0.2 and set(np.unique(ic.return_code[~ic.success])) <= {2, 3}
+    fa, xa, ia = _mpc(N, n, solver="AUTO", admm_max_iter=10, polish_max_rounds=1).solve_records(batch["rec"], batch["contact"])
+    assert ia.success.all() and np.all(ia.kkt.max(axis=1) <= 1e-6)
+    rescued = ~ic.success
+    assert (ia.polish_rounds[rescued] == 0).all()  # those came from the interior-point kernel
+    scale = np.maximum(1.0, np.abs(f_ref).reshape(n, -1).max(axis=1))
+    assert (np.abs(fa - f_ref).reshape(n, -1).max(axis=1) / scale).max() <= 1e-5
