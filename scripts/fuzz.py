@@ -55,6 +55,6 @@ for trial in range(int(os.environ.get("TRIALS", "24"))):
                 print("    ", s2, "status", int(i2.return_code[q]), "forces", np.round(f2[q], 4).tolist(), "kkt", i2.kkt[q].tolist())
         print("    failed:", [(int(q), int(info.return_code[q]), int(info.acados_num_iter[q]), info.kkt[q].tolist(), int(nfree[q])) for q in badp[:4]])
     print(f"{trial:2d} N={N:2d} {solver:15s} ws={ws} mu={mu} fmin={fmin} fmax={fmax} alpha={alpha:.1e} gaits={','.join(gaits):40s} ok(fits)={ok[fits].mean():.4f} "
-          f"kkt_max={kk[ok].max() if ok.any() else float('nan'):.1e} oracle_rel={worst:.1e} feas={feas} swing0={swing0} iters={info.acados_num_iter.mean():.1f}{flag}", flush=True)
+          f"kkt_max={kk[ok].max() if ok.any() else float('nan'):.1e} oracle_rel={worst:.1e} feas={feas} swing0={swing0} iters={info.acados_num_iter.mean():.1f} max={int(info.acados_num_iter[ok].max()) if ok.any() else -1}{flag}", flush=True)
     mpc.close()
 print("trials needing a look:", bad)
