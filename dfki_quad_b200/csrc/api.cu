@@ -403,7 +403,11 @@ static int32_t solve_device_impl(b200qp_mpc *h, int32_t n, const double *d_in, c
         CK(cudaStreamWaitEvent(st, h->ev_fork, 0));
         forked[b - 1] = true;
       }
-      CK(launch_mpc_admm(b, h->P, B, g, st));
+      MpcParams Pb = h->P;
+      // AUTO: a straggler that needs more than a few hundred ADMM iterations (tight force limits with a tiny input weight:
+      // up to 1800) is cheaper on the interior-point kernel, and it would otherwise stretch the whole launch
+      if (autosel && Pb.max_iter > 300) Pb.max_iter = 300;
+      CK(launch_mpc_admm(b, Pb, B, g, st));
       ++launches;
     }
   }
