@@ -1,4 +1,5 @@
 // C ABI of libb200qp.so (include/b200qp.h): handle management, staging buffers, kernel launches.
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -121,7 +122,8 @@ static void fill_params(b200qp_mpc *h) {
   P.mu = c.mu;
   P.fmin = c.fmin;
   P.fmax = c.fmax;
-  P.rho0 = c.admm_rho > 0 ? c.admm_rho : 5e-5;
+  // the best initial penalty scales with the input weight (measured: alpha 1e-6 / 1e-5 / 1e-4 / 1e-3 -> rho0 5e-7 / 5e-5 / 5e-4 / 5e-4)
+  P.rho0 = c.admm_rho > 0 ? c.admm_rho : fmin(fmax(5.0 * c.alpha, 1e-6), 5e-4);
   P.sigma = c.admm_sigma > 0 ? c.admm_sigma : 1e-6;
   P.relax = c.admm_alpha > 0 ? c.admm_alpha : 1.6;
   P.eps = c.admm_eps > 0 ? c.admm_eps : 1e-3;

@@ -64,7 +64,7 @@ typedef struct b200qp_mpc_config {
   double fmin;                /* (mpc.cpp:94-115)                                                                */
   double fmax;
   /* solver options (0 => library default) */
-  double admm_rho;            /* initial ADMM penalty                                     default 5e-5          */
+  double admm_rho;            /* initial ADMM penalty            default 5 alpha in [1e-6, 5e-4] (5e-5 at 1e-5) */
   double admm_sigma;          /* ADMM proximal weight                                     default 1e-6          */
   double admm_alpha;          /* ADMM over-relaxation                                     default 1.6           */
   double admm_eps;            /* relative tolerance at which ADMM hands over to polish    default 1e-3          */
