@@ -754,3 +754,25 @@ def test_auto_solver_gives_condensed_failures_a_second_opinion(go2_params):
     assert (ia.polish_rounds[rescued] == 0).all()  # those came from the interior-point kernel
     scale = np.maximum(1.0, np.abs(f_ref).reshape(n, -1).max(axis=1))
     assert (np.abs(fa - f_ref).reshape(n, -1).max(axis=1) / scale).max() <= 1e-5
+
+
+def test_riccati_two_cycle_regression():
+    """A rotary-gallop problem with single-foot stance stages at alpha = 1.1e-6 on which Mehrotra's method used to fall into a
+    two-cycle (gap 0.3 <-> 0.65 for 200 iterations; found by scripts/fuzz.py).  The monotone-gap safeguard must solve it and its
+    neighbourhood, to the condensed kernel's answer."""
+    import os
+    from dfki_quad_b200 import BatchedMPC, sequencer
+
+    d = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "riccati_two_cycle.npz"))
+    N, cfg = int(d["N"]), sequencer.GO2_MPC
+    rng = np.random.default_rng(0)
+    recs = np.repeat(d["rec"][None], 64, axis=0)
+    recs[1:, 4:13] += rng.normal(0, 1e-3, (63, 9))
+    cts = np.repeat(d["contact"][None], 64, axis=0)
+    args = (float(d["alpha"]), d["w"], float(d["mu"]), float(d["fmin"]), float(d["fmax"]))
+    fr, _, ir = BatchedMPC(*args, "SPARSE_RICCATI", horizon=N, dt=cfg["dt"], max_batch=64).solve_records(recs, cts)
+    fa, _, ia = BatchedMPC(*args, "CONDENSED_ADMM", horizon=N, dt=cfg["dt"], max_batch=64).solve_records(recs, cts)
+    assert ir.success.all() and ia.success.all(), (np.unique(ir.return_code, return_counts=True))
+    assert ir.acados_num_iter.max() <= 25
+    scale = np.maximum(1.0, np.abs(fa).reshape(64, -1).max(axis=1))
+    assert (np.abs(fr - fa).reshape(64, -1).max(axis=1) / scale).max() <= 1e-5
