@@ -104,7 +104,7 @@ static void chol_solve(const double *L, int n, int ld, double *b) {
 typedef struct {
   double A[NX * NX];          /* row-major */
   double B[MAXN][NX * NU];    /* row-major */
-  double xref[MAXN + 1][NX], x0[NX];
+  double xref[MAXN + 1][NX], q[MAXN + 1][NX], x0[NX]; /* q_k = -Q xref_k (mpc.cpp:380) */
   double lbu[MAXN][NU], ubu[MAXN][NU];
   double H[MAXV * MAXV], g[MAXV], K[MAXV * MAXV];
   double Gam[MAXN][MAXN][NX * NU]; /* Gamma block (i,j): state i+1 <- input j */
@@ -215,6 +215,7 @@ static void build_qp(const ref_params *P, const double *rec, const uint8_t *ct, 
     t[0] = e[0]; t[1] = e[1]; t[2] = desired_yaw;
     for (int i = 0; i < 3; ++i) { t[3 + i] = st[4 + i] + com[i]; t[6 + i] = st[7 + i]; t[9 + i] = st[10 + i]; }
     t[12] = 0;
+    for (int i = 0; i < NX; ++i) W->q[k][i] = (i < 12) ? -(P->w[i] * t[i]) : 0.0; /* qs_[k] = -(Q_ * target_state), mpc.cpp:380 */
   }
   quat_to_rot(rec, R);
   rot_to_euler(R, e);
@@ -249,7 +250,7 @@ static void condense(const ref_params *P, ref_ws *W) {
     double nx[NX];
     for (int r = 0; r < NX; ++r) { double s = 0; for (int t = 0; t < NX; ++t) s += W->A[r * NX + t] * xs[t]; nx[r] = s; }
     memcpy(xs, nx, sizeof(xs));
-    for (int r = 0; r < NX; ++r) e[i][r] = Q[r] * (xs[r] - W->xref[i + 1][r]);
+    for (int r = 0; r < NX; ++r) e[i][r] = Q[r] * xs[r] + W->q[i + 1][r];
   }
   for (int j = 0; j < N; ++j)
     for (int c = 0; c < NU; ++c) {
@@ -471,11 +472,16 @@ static int polish(const ref_params *P, ref_ws *W, double *kkt) {
 }
 
 /* (3) OSQP-style ADMM on the condensed QP */
+static void solve_ws(const ref_params *P, ref_ws *W, double *forces, double *xpred, ref_info *info);
 static void solve_one(const ref_params *P, const double *rec, const uint8_t *ct, ref_ws *W, double *forces, double *xpred,
                       ref_info *info) {
+  build_qp(P, rec, ct, W);
+  solve_ws(P, W, forces, xpred, info);
+}
+/* condensing + ADMM + polish on the stage data held in W (A, B_k, q_k, x0, lbu_k, ubu_k) */
+static void solve_ws(const ref_params *P, ref_ws *W, double *forces, double *xpred, ref_info *info) {
   const int N = P->N, n = NU * N, m = 28 * N;
   const double mu = P->mu, sigma = P->sigma, al = P->relax;
-  build_qp(P, rec, ct, W);
   condense(P, W);
   double rho = P->rho;
   set_rho(P, W, rho);
@@ -593,6 +599,27 @@ int ref_solve_batch(const ref_params *P, int n, const double *in, const uint8_t 
     free(W);
   }
   return solved;
+}
+
+/* Solve an OCP-QP handed over as STAGE DATA (column-major, the acados setters' layout): used by oracle/ref_harness.cpp,
+ * where the reference's own MPC::GetWrenchSequence (compiled from /root/reference) assembled A, B_k, q_k, x0 and the
+ * bounds and calls ocp_qp_solve().  The cost / constraint structure (Q diagonal, R = alpha I, pyramid rows with mu,
+ * boxes with fmin / fmax) is checked by the caller and arrives through P. */
+int ref_solve_ocp(const ref_params *P, const double *A_cm, const double *const *B_cm, const double *const *q, const double *x0,
+                  const double *const *lbu, const double *const *ubu, double *u_out, double *x_out, ref_info *info) {
+  if (P->N < 1 || P->N > MAXN) return -1;
+  ref_ws *W = (ref_ws *)malloc(sizeof(ref_ws));
+  for (int r = 0; r < NX; ++r) for (int c = 0; c < NX; ++c) W->A[r * NX + c] = A_cm[c * NX + r];
+  for (int k = 0; k < P->N; ++k) {
+    for (int r = 0; r < NX; ++r) for (int c = 0; c < NU; ++c) W->B[k][r * NU + c] = B_cm[k][c * NX + r];
+    memcpy(W->lbu[k], lbu[k], sizeof(double) * NU);
+    memcpy(W->ubu[k], ubu[k], sizeof(double) * NU);
+  }
+  for (int k = 0; k <= P->N; ++k) memcpy(W->q[k], q[k], sizeof(double) * NX);
+  memcpy(W->x0, x0, sizeof(double) * NX);
+  solve_ws(P, W, u_out, x_out, info);
+  free(W);
+  return info->status;
 }
 
 /* condensed H (row-major 12N x 12N) and g of one problem, for cross-checks */
