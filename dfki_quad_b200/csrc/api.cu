@@ -71,6 +71,7 @@ struct b200qp_mpc {
   cudaEvent_t ev_fork = nullptr, ev_join[4] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   int num_sms = 0;
+  int async_engines = 0;  // copy engines that can run beside a kernel (0: streamed inputs are not used)
   // device buffers sized for max_batch
   double *d_in = nullptr, *d_forces = nullptr, *d_xpred = nullptr, *d_lam_box = nullptr, *d_lam_g = nullptr;
   uint8_t *d_contact = nullptr;
@@ -150,6 +151,20 @@ struct WbcGuard {
   b200qp_wbc *h;
   ~WbcGuard() { if (h) b200qp_wbc_destroy(h); }
 };
+// device temporaries of the diagnostic entry points: released on every exit path
+struct DevTmp {
+  void *p[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  int n = 0;
+  template <class T>
+  cudaError_t alloc(T **out, size_t bytes) {
+    cudaError_t e = cudaMalloc(reinterpret_cast<void **>(out), bytes);
+    if (e == cudaSuccess && n < 6) p[n++] = *out;
+    return e;
+  }
+  ~DevTmp() {
+    for (int i = 0; i < n; ++i) cudaFree(p[i]);
+  }
+};
 }  // namespace
 extern "C" {
 
@@ -200,6 +215,7 @@ int32_t b200qp_mpc_create(const b200qp_mpc_config *cfg, b200qp_mpc **out) {
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, cfg->device));
   h->num_sms = prop.multiProcessorCount;
+  h->async_engines = prop.asyncEngineCount;
   const size_t nb = (size_t)cfg->max_batch;
   const int N = cfg->horizon;
   const size_t in_d = (size_t)b200qp_mpc_in_doubles(N);
@@ -552,7 +568,7 @@ int32_t b200qp_mpc_solve_batch(b200qp_mpc *h, int32_t n, const double *in, const
   // The records (2.3 KB per problem, the bulk of the input) go up in chunks on the copy stream while the condensed kernel is
   // already solving the chunks that have landed: a per-chunk flag, written by a 4-byte copy queued behind the chunk's data,
   // is what the kernel polls before it stages a record.  The Riccati kernel has no such wait, so only CONDENSED_ADMM streams.
-  const int chunks = (h->cfg.solver == B200QP_SOLVER_CONDENSED_ADMM && !h->no_zero_copy && n >= 2048) ? 4 : 1;
+  const int chunks = (h->cfg.solver == B200QP_SOLVER_CONDENSED_ADMM && !h->no_zero_copy && h->async_engines >= 1 && n >= 2048) ? 4 : 1;
   if (chunks == 1) {
     CK(cudaMemcpyAsync(h->d_in, src_in, in_b, cudaMemcpyHostToDevice, h->stream));
     return solve_and_fetch(h, n, forces, xpred, info);
@@ -675,30 +691,26 @@ int32_t b200qp_mpc_sequence_solve_batch_device(b200qp_mpc *h, int32_t n, const d
 int32_t b200qp_mpc_get_duals(b200qp_mpc *h, int32_t n, double *lam_box, double *lam_g) {
   if (!h || n < 0 || n > h->last_n || !lam_box || !lam_g || !h->last_in) return B200QP_ERR_ARG;
   CK(cudaSetDevice(h->cfg.device));
-  // re-run the last batch with dual output enabled (diagnostic path, not timed)
+  // Re-runs the last batch with dual output enabled (diagnostic path, not timed).  The inputs of the last solve must
+  // still be alive: after b200qp_mpc_solve_batch they are the handle's own buffers; after ..._solve_batch_device they are
+  // the CALLER's device pointers, which must not have been freed or overwritten in between.
   const int N = h->cfg.horizon;
-  h->want_duals = true;
+  DevTmp tmp;
   double *tf = nullptr, *tx = nullptr;
   b200qp_solver_info *ti = nullptr;
-  CK(cudaMalloc(&tf, (size_t)n * N * 12 * sizeof(double)));
-  CK(cudaMalloc(&tx, (size_t)n * (N + 1) * 13 * sizeof(double)));
-  CK(cudaMalloc(&ti, (size_t)n * sizeof(b200qp_solver_info)));
+  CK(tmp.alloc(&tf, (size_t)n * N * 12 * sizeof(double)));
+  CK(tmp.alloc(&tx, (size_t)n * (N + 1) * 13 * sizeof(double)));
+  CK(tmp.alloc(&ti, (size_t)n * sizeof(b200qp_solver_info)));
   CK(cudaMemsetAsync(h->d_lam_box, 0, (size_t)n * N * 12 * sizeof(double), h->stream));
   CK(cudaMemsetAsync(h->d_lam_g, 0, (size_t)n * N * 16 * sizeof(double), h->stream));
-  int32_t rc = solve_device_impl(h, n, h->last_in, h->last_contact, tf, tx, ti, -1, nullptr, nullptr);
+  h->want_duals = true;
+  const int32_t rc = solve_device_impl(h, n, h->last_in, h->last_contact, tf, tx, ti, -1, nullptr, nullptr);
   h->want_duals = false;
   if (rc == B200QP_OK) {
-    cudaMemcpyAsync(lam_box, h->d_lam_box, (size_t)n * N * 12 * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
-    cudaMemcpyAsync(lam_g, h->d_lam_g, (size_t)n * N * 16 * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+    CK(cudaMemcpyAsync(lam_box, h->d_lam_box, (size_t)n * N * 12 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(lam_g, h->d_lam_g, (size_t)n * N * 16 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   }
-  cudaError_t e = cudaStreamSynchronize(h->stream);
-  cudaFree(tf);
-  cudaFree(tx);
-  cudaFree(ti);
-  if (e != cudaSuccess) {
-    set_err("b200qp_mpc_get_duals", e);
-    return B200QP_ERR_CUDA;
-  }
+  CK(cudaStreamSynchronize(h->stream));
   return rc;
 }
 
@@ -708,40 +720,38 @@ int32_t b200qp_mpc_get_condensed(b200qp_mpc *h, int32_t index, double *H, int32_
   CK(cudaSetDevice(h->cfg.device));
   const int N = h->cfg.horizon;
   const size_t in_d = (size_t)b200qp_mpc_in_doubles(N);
+  DevTmp tmp;
   double *dH = nullptr, *dg = nullptr, *tf = nullptr, *tx = nullptr;
   b200qp_solver_info *ti = nullptr;
   const int nmax = 12 * N;
-  CK(cudaMalloc(&dH, (size_t)nmax * nmax * sizeof(double)));
-  CK(cudaMalloc(&dg, (size_t)nmax * sizeof(double)));
-  CK(cudaMalloc(&tf, (size_t)N * 12 * sizeof(double)));
-  CK(cudaMalloc(&tx, (size_t)(N + 1) * 13 * sizeof(double)));
-  CK(cudaMalloc(&ti, sizeof(b200qp_solver_info)));
+  CK(tmp.alloc(&dH, (size_t)nmax * nmax * sizeof(double)));
+  CK(tmp.alloc(&dg, (size_t)nmax * sizeof(double)));
+  CK(tmp.alloc(&tf, (size_t)N * 12 * sizeof(double)));
+  CK(tmp.alloc(&tx, (size_t)(N + 1) * 13 * sizeof(double)));
+  CK(tmp.alloc(&ti, sizeof(b200qp_solver_info)));
+  CK(cudaMemsetAsync(dH, 0, (size_t)nmax * nmax * sizeof(double), h->stream));
+  CK(cudaMemsetAsync(dg, 0, (size_t)nmax * sizeof(double), h->stream));
   const double *sv_in = h->last_in;
   const uint8_t *sv_ct = h->last_contact;
   const int sv_n = h->last_n;
-  int32_t rc = solve_device_impl(h, 1, sv_in + (size_t)index * in_d, sv_ct + (size_t)index * N * 4, tf, tx, ti, 0, dH, dg);
+  const int32_t rc = solve_device_impl(h, 1, sv_in + (size_t)index * in_d, sv_ct + (size_t)index * N * 4, tf, tx, ti, 0, dH, dg);
   h->last_in = sv_in;
   h->last_contact = sv_ct;
   h->last_n = sv_n;
+  if (rc != B200QP_OK) return rc;
   b200qp_solver_info inf;
   memset(&inf, 0, sizeof(inf));
-  int nfree = -1;
-  if (rc == B200QP_OK && cudaMemcpyAsync(&inf, ti, sizeof(inf), cudaMemcpyDeviceToHost, h->stream) == cudaSuccess &&
-      cudaStreamSynchronize(h->stream) == cudaSuccess) {
-    nfree = inf.n_free;
-    if (nfree > 0 && nfree <= nmax && ldh >= nfree) {
-      cudaMemcpy2D(H, (size_t)ldh * sizeof(double), dH, (size_t)nfree * sizeof(double), (size_t)nfree * sizeof(double),
-                   nfree, cudaMemcpyDeviceToHost);
-      cudaMemcpy(g, dg, (size_t)nfree * sizeof(double), cudaMemcpyDeviceToHost);
-    } else if (nfree > 0) {
-      nfree = B200QP_ERR_ARG;
-    }
-  }
-  cudaFree(dH);
-  cudaFree(dg);
-  cudaFree(tf);
-  cudaFree(tx);
-  cudaFree(ti);
+  CK(cudaMemcpyAsync(&inf, ti, sizeof(inf), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  const int nfree = inf.n_free;
+  // only the condensed kernel forms H and g: a problem that went to the Riccati kernel (solver AUTO, more than 156 free
+  // variables) has none to report
+  if (nfree > 156) return B200QP_ERR_UNSUPPORTED;
+  if (nfree <= 0) return nfree;
+  if (nfree > nmax || ldh < nfree) return B200QP_ERR_ARG;
+  CK(cudaMemcpy2D(H, (size_t)ldh * sizeof(double), dH, (size_t)nfree * sizeof(double), (size_t)nfree * sizeof(double), nfree,
+                  cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(g, dg, (size_t)nfree * sizeof(double), cudaMemcpyDeviceToHost));
   return nfree;
 }
 
@@ -890,8 +900,7 @@ int32_t b200qp_wbc_create(const b200qp_wbc_config *cfg, b200qp_wbc **out) {
   h->grid = wbc_grid(h->P, prop.multiProcessorCount);
   if (h->grid <= 0) {
     g_err = "b200qp_wbc_create: problem dimensions do not fit shared memory";
-    delete h;
-    return B200QP_ERR_UNSUPPORTED;
+    return B200QP_ERR_UNSUPPORTED;  // the guard releases h
   }
   const size_t nb = cfg->max_batch, nq = cfg->nq, nc = cfg->neq + cfg->nin;
   CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));

@@ -783,10 +783,28 @@ __global__ void __launch_bounds__(BS, (BS == 64 && !B200QP_TC_GJ) ? 6 : 1) mpc_a
     if (B.ready != nullptr) {  // the H2D copy of this problem's chunk may still be in flight (copy engine, own stream)
       if (tid == 0) {
         const volatile int *flag = B.ready + prob / B.ready_chunk;
-        while (*flag == 0) __nanosleep(500);
+        // bounded: a chunk copy that failed, or that cannot run beside the kernel (no free copy engine, a tool that
+        // serialises streams), must not hang the grid - after ~2 s the problem is reported as failed instead
+        const long long t0 = clock64();
+        int landed = 1;
+        while (*flag == 0) {
+          __nanosleep(500);
+          if (clock64() - t0 > 4000000000LL) {
+            landed = 0;
+            break;
+          }
+        }
         __threadfence_system();  // acquire: the record reads below must not be satisfied by anything older than the flag
+        s_changed = landed;
       }
       __syncthreads();
+      if (s_changed == 0) {
+        if (tid == 0) {
+          b200qp_solver_info inf = {B200QP_ACADOS_QP_FAILURE, 0, 0, 0, {0, 0, 0, 0}};
+          B.info[prob] = inf;
+        }
+        continue;
+      }
     }
     {
       const double *grec = B.in + (size_t)prob * P.in_stride;

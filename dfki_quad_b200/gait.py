@@ -58,6 +58,12 @@ def contact_schedule(period, duty, offset, phase, steps, dt, measured_contact=No
     return (contact, swing, lbu, ubu) if want_bounds else (contact, swing)
 
 
-def sequencer_phase(time_in_phase, period):
-    """SimpleGaitSequencer::UpdateState phase (simple_gait_sequencer.cpp:71-75), vectorised C fmod."""
-    return np.fmod(np.asarray(time_in_phase, dtype=np.float64) / np.asarray(period, dtype=np.float64), 1.0)
+def sequencer_phase(time_in_phase, period, duty=None):
+    """SimpleGaitSequencer::UpdateState phase (simple_gait_sequencer.cpp:62-80): fmod((t - t0) / T, 1) with C fmod; a pure
+    standing gait (every duty factor 0 or 1, :66-69) keeps phase 0.  `duty` [n,4] enables the standing branch."""
+    ph = np.fmod(np.asarray(time_in_phase, dtype=np.float64) / np.asarray(period, dtype=np.float64), 1.0)
+    if duty is not None:
+        d = np.asarray(duty, dtype=np.float64)
+        moving = np.any((d != 0.0) & (d != 1.0), axis=-1)
+        ph = np.where(moving, ph, 0.0)
+    return ph

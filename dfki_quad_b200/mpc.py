@@ -112,6 +112,7 @@ class BatchedMPC:
         self._state = None
         self._model = None
         self._gs = None
+        self._last = None  # (forces, xpred) of the previous GetWrenchSequence: a failed problem keeps them (mpc.cpp:447-455)
 
     # -- lifetime ---------------------------------------------------------------------------------------------------
     def close(self):
@@ -142,7 +143,9 @@ class BatchedMPC:
         self._gs = gait_sequence
 
     def GetWrenchSequence(self):
-        """-> (forces [n,N,4,3], MPCPrediction, SolverInformation); failed problems keep zeros (fresh buffers)."""
+        """-> (forces [n,N,4,3], MPCPrediction, SolverInformation).  As in the reference, whose caller passes the same
+        WrenchSequence / MPCPrediction objects every cycle, a problem whose solve fails keeps the wrench and prediction of
+        the previous call (mpc.cpp:447-455) - zeros only before the first success.  The returned arrays are copies."""
         if self._state is None or self._model is None or self._gs is None:
             raise RuntimeError("UpdateState / UpdateModel / UpdateGaitSequence must be called first")
         q, p, w, v = self._state
@@ -154,7 +157,10 @@ class BatchedMPC:
                            gs["reference_trajectory_twist"], gs["reference_trajectory_velocity"],
                            gs["foot_position_sequence"])
         contact = np.ascontiguousarray(np.asarray(gs["contact_sequence"])[:, : self.N], dtype=np.uint8)
-        forces, xpred, info = self.solve_records(rec, contact)
+        if self._last is None or self._last[0].shape[0] != n:
+            self._last = (np.zeros((n, self.N, 12)), np.zeros((n, self.N + 1, 13)))
+        forces, xpred, info = self.solve_records(rec, contact, self._last[0], self._last[1])
+        forces, xpred = forces.copy(), xpred.copy()
         com_b = np.broadcast_to(com, (n, 3))[:, None, :]
         pred = MPCPrediction(
             orientation=euler_to_quaternion(xpred[:, :, 0:3]),  # mpc.cpp:463

@@ -68,7 +68,10 @@ def closed_loop(mpc, n, steps, target, gait="TROT", seed=0, dt=0.05, v_filter_le
     feet[:, :, 2] = 0.0
     heights = np.zeros((n, 4))
     tgt = {k: np.broadcast_to(np.asarray(target[k], float), (n,)).copy() for k in sq.TARGET_FIELDS}
-    phase = rng.uniform(0.0, 1.0, n)
+    # SimpleGaitSequencer::UpdateState (simple_gait_sequencer.cpp:62-80): phase = fmod((t - t0) / T, 1), 0 for a pure standing gait;
+    # every robot gets its own t0 so that the batch covers all phases
+    t_since_t0 = rng.uniform(0.0, 1.0, n) * period
+    phase = gaitmod.sequencer_phase(t_since_t0, period, duty)
     vhist = [vel.copy()]
     prev_contact = None
     hist = dict(pos=[pos.copy()], vel=[vel.copy()], quat=[quat.copy()], ok=[], fz=[], iters=[], rounds=[], kernel_ms=[])
@@ -93,7 +96,8 @@ def closed_loop(mpc, n, steps, target, gait="TROT", seed=0, dt=0.05, v_filter_le
         has = contact.astype(bool).any(axis=1)
         feet = np.where((~c0 & has)[:, :, None], nxt, feet)
         quat, pos, omega, vel = srbd_step(quat, pos, omega, vel, feet, f0 * c0[:, :, None], dt, plant_inertia=plant_inertia)
-        phase = np.fmod(phase + dt / period, 1.0)
+        t_since_t0 = t_since_t0 + dt
+        phase = gaitmod.sequencer_phase(t_since_t0, period, duty)
         prev_contact = c0
         vhist.append(vel.copy())
         hist["pos"].append(pos.copy()); hist["vel"].append(vel.copy()); hist["quat"].append(quat.copy())

@@ -40,6 +40,8 @@ def load():
         _lib.ref_condense.restype = C.c_int
         _lib.ref_condense.argtypes = [C.POINTER(RefParams), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         _lib.ref_max_threads.restype = C.c_int
+        _lib.ref_kkt_batch.restype = C.c_int
+        _lib.ref_kkt_batch.argtypes = [C.POINTER(RefParams), C.c_int] + [C.c_void_p] * 7 + [C.c_int]
     return _lib
 
 
@@ -70,6 +72,23 @@ def solve_batch(N, rec, contact, params, threads=0, **kw):
     arr = np.frombuffer(info, dtype=np.dtype([("status", "i4"), ("iters", "i4"), ("n_fact", "i4"), ("polished", "i4"),
                                               ("kkt", "f8", (4,))]), count=n).copy()
     return forces, xpred, arr, solved
+
+
+def kkt_batch(N, rec, contact, params, forces, xpred=None, lam_box=None, lam_g=None, threads=0):
+    """Independent C KKT checker (mpc_ref.c::kkt_one) over a whole batch -> [n][4] = stationarity, dynamics, inequality,
+    complementarity inf-norms in the sparse OCP form."""
+    lib = load()
+    rec = np.ascontiguousarray(rec, dtype=np.float64)
+    contact = np.ascontiguousarray(contact, dtype=np.uint8)
+    n = rec.shape[0]
+    P = make_params(N, params)
+    arrs = [np.ascontiguousarray(a, dtype=np.float64) if a is not None else None for a in (forces, xpred, lam_box, lam_g)]
+    kkt = np.zeros((n, 4))
+    ptr = [a.ctypes.data if a is not None else None for a in arrs]
+    rc = lib.ref_kkt_batch(C.byref(P), n, rec.ctypes.data, contact.ctypes.data, ptr[0], ptr[1], ptr[2], ptr[3], kkt.ctypes.data,
+                           threads)
+    assert rc == 0
+    return kkt
 
 
 def condense(N, rec, contact, params):

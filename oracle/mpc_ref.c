@@ -622,6 +622,116 @@ int ref_solve_ocp(const ref_params *P, const double *A_cm, const double *const *
   return info->status;
 }
 
+
+/* ---- independent KKT check of a candidate solution, sparse OCP form (what acados' ocp_qp_inf_norm_residuals reports,
+ * mpc.cpp:430-433): stationarity, dynamics, inequality, complementarity inf-norms.  The checker shares nothing with the
+ * solvers above but build_qp: the states are rolled out with the explicit A, B_k, the dynamics multipliers are the
+ * exact adjoint lam_k = Q x_k + q_k + A' lam_{k+1}, and - when the solver's inequality multipliers are not supplied
+ * (lam_box [N][12] > 0 at the upper, < 0 at the lower bound; lam_g [N][16] likewise, the reference's row order) - the
+ * sign-feasible multipliers of the rows that are tight within 1e-7 (scaled) are reconstructed per foot by exact NNLS. */
+static void kkt_one(const ref_params *P, const double *rec, const uint8_t *ct, const double *U, const double *Xpred,
+                    const double *lam_box, const double *lam_g, ref_ws *W, double kkt[4]) {
+  const int N = P->N;
+  const double mu = P->mu;
+  build_qp(P, rec, ct, W);
+  static __thread double X[MAXN + 1][NX], lam[MAXN + 2][NX];
+  double dyn = 0, stat = 0, ineq = 0, comp = 0;
+  memcpy(X[0], W->x0, sizeof(double) * NX);
+  for (int k = 0; k < N; ++k)
+    for (int r = 0; r < NX; ++r) {
+      double s = 0;
+      for (int t = 0; t < NX; ++t) s += W->A[r * NX + t] * X[k][t];
+      for (int c = 0; c < NU; ++c) s += W->B[k][r * NU + c] * U[NU * k + c];
+      X[k + 1][r] = s;
+    }
+  if (Xpred) { /* the solver's own prediction must satisfy the dynamics: x0 fixed, x_{k+1} = A x_k + B_k u_k */
+    for (int r = 0; r < NX; ++r) dyn = fmax(dyn, fabs(Xpred[r] - W->x0[r]));
+    for (int k = 0; k < N; ++k)
+      for (int r = 0; r < NX; ++r) {
+        double s = 0;
+        for (int t = 0; t < NX; ++t) s += W->A[r * NX + t] * Xpred[NX * k + t];
+        for (int c = 0; c < NU; ++c) s += W->B[k][r * NU + c] * U[NU * k + c];
+        dyn = fmax(dyn, fabs(Xpred[NX * (k + 1) + r] - s));
+      }
+  }
+  memset(lam[N + 1], 0, sizeof(double) * NX);
+  for (int k = N; k >= 1; --k)
+    for (int r = 0; r < NX; ++r) {
+      double s = (r < 12 ? P->w[r] : 0.0) * X[k][r] + W->q[k][r];
+      if (k < N) for (int t = 0; t < NX; ++t) s += W->A[t * NX + r] * lam[k + 1][t];
+      lam[k][r] = s;
+    }
+  const double lo[7] = {-P->fmax, -P->fmax, P->fmin, -HUGE_VAL, 0, -HUGE_VAL, 0}, hi[7] = {P->fmax, P->fmax, P->fmax, 0, HUGE_VAL, 0, HUGE_VAL};
+  for (int k = 0; k < N; ++k)
+    for (int f = 0; f < 4; ++f) {
+      const double *u = U + NU * k + 3 * f;
+      double g[3];
+      for (int c = 0; c < 3; ++c) {
+        double s = P->alpha * u[c];
+        for (int t = 0; t < NX; ++t) s += W->B[k][t * NU + 3 * f + c] * lam[k + 1][t];
+        g[c] = s;
+      }
+      if (!ct[4 * k + f]) { /* lbu = ubu = 0: an equality, any multiplier is admissible */
+        ineq = fmax(ineq, fmax(fabs(u[0]), fmax(fabs(u[1]), fabs(u[2]))));
+        continue;
+      }
+      const double ax[7] = {u[0], u[1], u[2], u[0] - mu * u[2], u[0] + mu * u[2], u[1] - mu * u[2], u[1] + mu * u[2]};
+      for (int r = 0; r < 7; ++r) {
+        if (lo[r] > -HUGE_VAL) ineq = fmax(ineq, lo[r] - ax[r]);
+        if (hi[r] < HUGE_VAL) ineq = fmax(ineq, ax[r] - hi[r]);
+      }
+      if (lam_box) {
+        double y[7];
+        for (int c = 0; c < 3; ++c) y[c] = lam_box[NU * k + 3 * f + c];
+        for (int r = 0; r < 4; ++r) y[3 + r] = lam_g[16 * k + 4 * f + r];
+        double rs[3] = {g[0], g[1], g[2]};
+        for (int r = 0; r < 7; ++r) {
+          double a[3];
+          foot_row(r, mu, a);
+          for (int c = 0; c < 3; ++c) rs[c] += a[c] * y[r];
+          if (y[r] > 0) { if (hi[r] < HUGE_VAL) comp = fmax(comp, y[r] * fabs(hi[r] - ax[r])); else stat = fmax(stat, y[r]); }
+          if (y[r] < 0) { if (lo[r] > -HUGE_VAL) comp = fmax(comp, -y[r] * fabs(ax[r] - lo[r])); else stat = fmax(stat, -y[r]); }
+        }
+        stat = fmax(stat, fmax(fabs(rs[0]), fmax(fabs(rs[1]), fabs(rs[2]))));
+      } else {
+        const double sc = fmax(1.0, fmax(fabs(u[0]), fmax(fabs(u[1]), fabs(u[2])))), tt = 1e-7 * sc;
+        double Mc[14][3], coef[14], slack[14];
+        int m = 0;
+        for (int r = 0; r < 7; ++r) {
+          double a[3];
+          foot_row(r, mu, a);
+          if (lo[r] > -HUGE_VAL && ax[r] - lo[r] <= tt && m < 8) { Mc[m][0] = -a[0]; Mc[m][1] = -a[1]; Mc[m][2] = -a[2]; slack[m++] = fabs(ax[r] - lo[r]); }
+          if (hi[r] < HUGE_VAL && hi[r] - ax[r] <= tt && m < 8) { Mc[m][0] = a[0]; Mc[m][1] = a[1]; Mc[m][2] = a[2]; slack[m++] = fabs(hi[r] - ax[r]); }
+        }
+        const double b3[3] = {-g[0], -g[1], -g[2]};
+        stat = fmax(stat, nnls_enum(Mc, m, b3, coef));
+        for (int q = 0; q < m; ++q) comp = fmax(comp, coef[q] * slack[q]);
+      }
+    }
+  kkt[0] = stat; kkt[1] = dyn; kkt[2] = fmax(ineq, 0.0); kkt[3] = comp;
+}
+
+/* batch entry; xpred, lam_box, lam_g may be NULL.  kkt [n][4]. */
+int ref_kkt_batch(const ref_params *P, int n, const double *in, const uint8_t *contact, const double *forces, const double *xpred,
+                  const double *lam_box, const double *lam_g, double *kkt, int threads) {
+  if (P->N < 1 || P->N > MAXN) return -1;
+  const int stride = 26 + 13 * (P->N + 1) + 12 * P->N;
+#ifdef _OPENMP
+  if (threads > 0) omp_set_num_threads(threads);
+#endif
+#pragma omp parallel
+  {
+    ref_ws *W = (ref_ws *)malloc(sizeof(ref_ws));
+#pragma omp for schedule(dynamic, 16)
+    for (int p = 0; p < n; ++p)
+      kkt_one(P, in + (size_t)p * stride, contact + (size_t)p * P->N * 4, forces + (size_t)p * P->N * NU,
+              xpred ? xpred + (size_t)p * (P->N + 1) * NX : 0, lam_box ? lam_box + (size_t)p * P->N * NU : 0,
+              lam_g ? lam_g + (size_t)p * P->N * 16 : 0, W, kkt + 4 * (size_t)p);
+    free(W);
+  }
+  return 0;
+}
+
 /* condensed H (row-major 12N x 12N) and g of one problem, for cross-checks */
 int ref_condense(const ref_params *P, const double *rec, const uint8_t *ct, double *H, double *g) {
   ref_ws *W = (ref_ws *)malloc(sizeof(ref_ws));

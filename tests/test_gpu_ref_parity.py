@@ -1,0 +1,166 @@
+"""GPU parity tests against the REFERENCE'S OWN code (oracle/_ref, built from /root/reference in the build container and
+shipped to the GPU box as a prebuilt library) and WHOLE-BATCH checks of the BASELINE configurations against the C port +
+the independent C KKT checker.  Everything on the product side goes through the C ABI (libb200qp.so via ctypes)."""
+import numpy as np
+import pytest
+
+from oracle import c_oracle
+from oracle import mpc_oracle as mo
+from oracle import ref_binding as rb
+
+pytestmark = pytest.mark.gpu
+
+
+def _mpc(N, max_batch, solver="CONDENSED_ADMM", weights="state_weights_move", **opts):
+    from dfki_quad_b200 import BatchedMPC, sequencer
+
+    cfg = sequencer.GO2_MPC
+    return BatchedMPC(cfg["alpha"], cfg[weights], cfg["mu"], cfg["fmin"], cfg["fmax"], solver, horizon=N, dt=cfg["dt"],
+                      max_batch=max_batch, **opts)
+
+
+def _need_ref(N=10):
+    if not rb.available(N):
+        pytest.skip("oracle/_ref was not built (needs /root/reference in the build container)")
+
+
+# ---------------------------------------------------------------------------------------------------- K4 vs gait.cpp
+def test_gait_schedule_1M_pairs_byte_equal_with_reference_gait_cpp():
+    """Kernel K4 against the reference's compiled Gait::update_sequence (gait.cpp:67-112) on 2^20 (gait, phase, measured
+    contact) triples, including exact-boundary phases: contact masks byte-equal, swing times bit-equal."""
+    _need_ref()
+    from dfki_quad_b200 import gait
+
+    rng = np.random.default_rng(20261020)
+    steps, dt, chunk = 21, 0.05, 1 << 17
+    total = 0
+    for c in range(8):
+        ids = rng.integers(0, len(gait.GAIT_NAMES), chunk)
+        per, duty, off = gait.gait_arrays(ids)
+        phase = rng.uniform(0, 1, chunk)
+        phase[:20000] = rng.integers(0, 40, 20000) * 0.025          # multiples of dt / T and of the offsets
+        phase[20000:24000] = np.nextafter(rng.integers(1, 20, 4000) * 0.05, rng.choice([0.0, 1.0], 4000))
+        phase[24000:25000] = 0.0
+        meas = rng.integers(0, 2, (chunk, 4)).astype(np.uint8)
+        cg, sg = gait.contact_schedule(per, duty, off, phase, steps, dt, measured_contact=meas)
+        cr, sr, _, _ = rb.gait_update_sequence(per, duty, off, phase, dt=dt, steps=steps, measured=meas)
+        assert np.array_equal(cg, cr), ("mask", c, np.argwhere(cg != cr)[:3])
+        assert np.array_equal(sg.view(np.uint64), sr.view(np.uint64)), ("swing time", c)
+        total += chunk
+    assert total == 1 << 20
+
+
+def test_gait_bounds_every_step_follow_the_reference_masks():
+    """lbu / ubu of MPC::GetUBounds (mpc.cpp:94-115) at EVERY step, from the reference's masks: byte-equal."""
+    _need_ref()
+    from dfki_quad_b200 import gait
+
+    rng = np.random.default_rng(11)
+    n, steps = 32768, 21
+    ids = rng.integers(0, len(gait.GAIT_NAMES), n)
+    per, duty, off = gait.gait_arrays(ids)
+    phase = rng.uniform(0, 1, n)
+    meas = rng.integers(0, 2, (n, 4)).astype(np.uint8)
+    fmin, fmax = 5.0, 333.0
+    c, s, lbu, ubu = gait.contact_schedule(per, duty, off, phase, steps, 0.05, measured_contact=meas, fmin=fmin, fmax=fmax,
+                                           want_bounds=True)
+    cr, _, _, _ = rb.gait_update_sequence(per, duty, off, phase, dt=0.05, steps=steps, measured=meas)
+    on = np.repeat(cr.astype(bool), 3, axis=2)                       # [n, steps, 12]
+    lo_st = np.tile(np.array([-fmax, -fmax, fmin]), 4)
+    assert np.array_equal(lbu, np.where(on, lo_st, 0.0)) and np.array_equal(ubu, np.where(on, fmax, 0.0))
+
+
+def test_gait_golden_reference_fixture():
+    """Committed reference outputs (tests/golden/ref_golden.npz), usable without the library."""
+    import os
+
+    from dfki_quad_b200 import gait
+
+    G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_golden.npz"))
+    per, duty, off = gait.gait_arrays(G["gait_ids"])
+    c, s = gait.contact_schedule(per, duty, off, G["gait_phase"], 25, 0.05, measured_contact=G["gait_meas"])
+    assert np.array_equal(c, G["gait_contact"]) and np.array_equal(s.view(np.uint64), G["gait_swing"].view(np.uint64))
+    c, s = gait.contact_schedule(per, duty, off, G["gait_phase"], 25, 0.05)
+    assert np.array_equal(c, G["gait_contact_nomeas"]) and np.array_equal(s.view(np.uint64), G["gait_swing_nomeas"].view(np.uint64))
+
+
+# ---------------------------------------------------------------------------------------------------- MPC vs mpc.cpp
+@pytest.mark.parametrize("N,solver", [(10, "CONDENSED_ADMM"), (16, "SPARSE_RICCATI"), (20, "AUTO"), (10, "PARTIAL_CONDENSING_HPIPM")])
+def test_reference_fixture_solutions(N, solver):
+    """Solutions that came out of the reference's MPC::GetWrenchSequence (fixture): GRFs 1e-5 relative, states 1e-8."""
+    import os
+
+    G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_golden.npz"))
+    rec, ct, F, X = G[f"mpc{N}_rec"], G[f"mpc{N}_contact"], G[f"mpc{N}_forces"], G[f"mpc{N}_xpred"]
+    forces, xpred, info = _mpc(N, rec.shape[0], solver=solver).solve_records(rec, ct)
+    ok = info.success if solver != "CONDENSED_ADMM" else (3 * ct.reshape(len(ct), -1).sum(axis=1) <= 156)
+    assert info.success[ok].all() and ok.sum() >= len(ok) - 2
+    scale = np.maximum(1.0, np.abs(F).reshape(len(F), -1).max(axis=1))
+    assert (np.abs(forces - F).reshape(len(F), -1).max(axis=1)[ok] / scale[ok]).max() <= 1e-5
+    assert np.abs(xpred - X)[ok].max() <= (1e-8 if solver == "CONDENSED_ADMM" else 1e-6)
+
+
+@pytest.mark.parametrize("N,gaits,solver", [(10, ("TROT",), "CONDENSED_ADMM"), (10, ("STAND", "PACE", "BOUND", "STATIC_WALK"), "AUTO"),
+                                            (16, ("TROT", "PACE", "BOUND"), "SPARSE_RICCATI")])
+def test_cuda_path_vs_reference_mpc_class_live(N, gaits, solver, go2_params):
+    """256 new random problems through the reference's own MPC class (mpc.cpp compiled from /root/reference; QP solve behind
+    its acados call by the C port, KKT <= 1e-9) and through the CUDA path: GRFs within 1e-5 relative, predicted states 1e-7."""
+    _need_ref(N)
+    from dfki_quad_b200 import sequencer
+
+    n = 256
+    batch = sequencer.random_batch(n, N, seed=555 + N + len(gaits), gaits=gaits)
+    forces, xpred, info = _mpc(N, n, solver=solver).solve_records(batch["rec"], batch["contact"])
+    assert info.success.all(), np.unique(info.return_code, return_counts=True)
+    Fr, Xr, ok = rb.solve_batch(N, batch["rec"], batch["contact"], go2_params, mass=mo.GO2_MASS, inertia=mo.GO2_INERTIA)
+    assert ok.all()
+    scale = np.maximum(1.0, np.abs(Fr).reshape(n, -1).max(axis=1))
+    err = np.abs(forces - Fr).reshape(n, -1).max(axis=1) / scale
+    assert err.max() <= 1e-5, (err.max(), int(np.argmax(err)))
+    assert np.abs(xpred - Xr).max() <= 1e-7
+
+
+# ---------------------------------------------------------------------------------------------------- whole batches
+def _whole_batch(N, n, seed, gaits, solver, go2_params):
+    from dfki_quad_b200 import sequencer
+
+    if not c_oracle.available():
+        pytest.skip("C oracle not built")
+    batch = sequencer.random_batch(n, N, seed=seed, gaits=gaits)
+    mpc = _mpc(N, n, solver=solver)
+    forces, xpred, info = mpc.solve_records(batch["rec"], batch["contact"])
+    assert info.success.all(), np.unique(info.return_code, return_counts=True)
+    # (1) every problem against the C port (full condensing + ADMM + polish on the reference's 12N-variable formulation)
+    Fc, Xc, ci, solved = c_oracle.solve_batch(N, batch["rec"], batch["contact"], go2_params)
+    assert solved == n, (solved, n)
+    scale = np.maximum(1.0, np.abs(Fc).reshape(n, -1).max(axis=1))
+    err = np.abs(forces - Fc).reshape(n, -1).max(axis=1) / scale
+    assert err.max() <= 1e-5, (err.max(), int(np.argmax(err)), int((err > 1e-5).sum()))
+    assert np.abs(xpred - Xc).max() <= 1e-6
+    # (2) every problem through the independent C KKT checker (sparse OCP form, own roll-out and adjoint)
+    if solver == "SPARSE_RICCATI":   # interior point: weakly active rows carry small multipliers -> check with the solver's duals
+        lam_box, lam_g = mpc.get_duals(n)
+        kkt = c_oracle.kkt_batch(N, batch["rec"], batch["contact"], go2_params, forces, xpred, lam_box, lam_g)
+    else:
+        kkt = c_oracle.kkt_batch(N, batch["rec"], batch["contact"], go2_params, forces, xpred)
+    assert kkt.max() <= 1e-6, (kkt.max(axis=0), int(np.argmax(kkt.max(axis=1))))
+    # (3) swing legs exactly zero
+    F = forces.reshape(n, N, 4, 3)
+    assert np.all(F[batch["contact"] == 0] == 0.0)
+    return err, kkt
+
+
+def test_config2_every_problem_against_port_and_c_kkt_checker(go2_params):
+    """BASELINE.json configs[1], all 4096 problems (not a sample)."""
+    err, kkt = _whole_batch(10, 4096, 20261019 + 2, ("TROT",), "CONDENSED_ADMM", go2_params)
+    print(f"config 2: max rel GRF error vs C port {err.max():.2e}, max KKT {kkt.max(axis=0)}")
+
+
+def test_config3_every_problem_against_port_and_c_kkt_checker(go2_params):
+    """BASELINE.json configs[2], all 16384 problems, sparse Riccati kernel."""
+    err, kkt = _whole_batch(16, 16384, 20261019 + 3, ("TROT", "PACE", "BOUND"), "SPARSE_RICCATI", go2_params)
+    print(f"config 3: max rel GRF error vs C port {err.max():.2e}, max KKT {kkt.max(axis=0)}")
+
+
+def test_config3_distribution_through_auto_every_problem(go2_params):
+    _whole_batch(16, 4096, 20261019 + 33, ("TROT", "PACE", "BOUND", "STAND"), "AUTO", go2_params)
