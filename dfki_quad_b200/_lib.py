@@ -11,13 +11,14 @@ LIB_PATH = os.environ.get("B200QP_LIB") or os.path.join(_HERE, "libb200qp.so")  
 OK, ERR_ARG, ERR_CUDA, ERR_UNSUPPORTED = 0, -1, -2, -3
 ACADOS_SUCCESS, ACADOS_NAN_DETECTED, ACADOS_MAXITER, ACADOS_MINSTEP, ACADOS_QP_FAILURE, ACADOS_READY = range(6)
 NAN_AFTER_SUCCESS = -7777
-SOLVER_CONDENSED_ADMM, SOLVER_SPARSE_RICCATI, SOLVER_AUTO = 0, 1, 2
-SOLVERS = {"CONDENSED_ADMM": 0, "SPARSE_RICCATI": 1, "AUTO": 2,
+SOLVER_CONDENSED_ADMM, SOLVER_SPARSE_RICCATI, SOLVER_AUTO, SOLVER_PARTIAL_CONDENSING = 0, 1, 2, 3
+SOLVERS = {"CONDENSED_ADMM": 0, "SPARSE_RICCATI": 1, "AUTO": 2, "PARTIAL_CONDENSING": 3,
            # The reference's acados plan names (mit_controller_node.cpp:502-519).  Its solvers take any problem size, so the
            # condensing plans map onto AUTO (condensed kernel where the reduced problem fits, Riccati kernel otherwise);
-           # the sparse HPIPM plan maps onto the Riccati interior-point kernel.
+           # the HPIPM partial-condensing plan maps onto the block-condensed Riccati interior-point kernel, which takes the
+           # reference's `condensing_N` (any value in 1..N, same optimum).
            "PARTIAL_CONDENSING_OSQP": 2, "FULL_CONDENSING_HPIPM": 2, "FULL_CONDENSING_QPOASES": 2,
-           "FULL_CONDENSING_DAQP": 2, "PARTIAL_CONDENSING_HPIPM": 1}
+           "FULL_CONDENSING_DAQP": 2, "PARTIAL_CONDENSING_HPIPM": 3}
 
 
 class MpcConfig(C.Structure):
@@ -28,7 +29,7 @@ class MpcConfig(C.Structure):
         ("admm_rho", C.c_double), ("admm_sigma", C.c_double), ("admm_alpha", C.c_double), ("admm_eps", C.c_double),
         ("kkt_tol", C.c_double),
         ("admm_max_iter", C.c_int32), ("admm_check_every", C.c_int32), ("polish_max_rounds", C.c_int32),
-        ("ipm_max_iter", C.c_int32), ("warm_start", C.c_int32),
+        ("ipm_max_iter", C.c_int32), ("warm_start", C.c_int32), ("cond_N", C.c_int32),
     ]
 
 

@@ -24,6 +24,11 @@ cudaError_t launch_mpc_riccati(const MpcParams &P, int n, const double *in, cons
                                int *next, int grid, cudaStream_t st, long long *dbg_cycles, const int *list,
                                const int *list_count);
 int riccati_grid(int num_sms, int horizon);
+cudaError_t launch_mpc_pcond(const MpcParams &P, int n, const double *in, const uint8_t *contact, double *forces, double *xpred,
+                             b200qp_solver_info *info, double *lam_box, double *lam_g, double *scratch, int *next, int grid,
+                             cudaStream_t st, const int *list, const int *list_count, int condN, int nub_limit, long long *dbg);
+int pcond_grid(int num_sms, int N, int condN, int nub_limit);
+size_t pcond_scratch_doubles(int N);
 struct SeqModel {
   double mass, inertia[9], com[3], shoulders[12], raibert_k, raibert_g, max_leg_length, dt;
   int N;
@@ -83,6 +88,8 @@ struct b200qp_mpc {
   int grid[4] = {0, 0, 0, 0};
   double *d_ric_scratch = nullptr;
   int ric_grid = 0;
+  double *d_pc_scratch = nullptr;  // partial-condensing kernel: block constants (+ factors that do not fit shared memory)
+  int pc_grid = 0, pc_cond = 0, pc_nub = 0;
   // pinned staging
   double *h_in = nullptr, *h_forces = nullptr, *h_xpred = nullptr;
   uint8_t *h_contact = nullptr;
@@ -196,7 +203,7 @@ int32_t b200qp_mpc_create(const b200qp_mpc_config *cfg, b200qp_mpc **out) {
     return B200QP_ERR_ARG;
   }
   if (cfg->solver != B200QP_SOLVER_CONDENSED_ADMM && cfg->solver != B200QP_SOLVER_SPARSE_RICCATI &&
-      cfg->solver != B200QP_SOLVER_AUTO) {
+      cfg->solver != B200QP_SOLVER_AUTO && cfg->solver != B200QP_SOLVER_PARTIAL_CONDENSING) {
     g_err = "b200qp_mpc_create: unknown solver";
     return B200QP_ERR_ARG;
   }
@@ -244,7 +251,20 @@ int32_t b200qp_mpc_create(const b200qp_mpc_config *cfg, b200qp_mpc **out) {
   CK(cudaMalloc(&h->d_retry, nb * sizeof(int)));
   CK(cudaMemset(h->d_forces, 0, nb * N * 12 * sizeof(double)));
   CK(cudaMemset(h->d_xpred, 0, nb * (N + 1) * 13 * sizeof(double)));
-  if (cfg->solver != B200QP_SOLVER_SPARSE_RICCATI) {
+  if (cfg->solver == B200QP_SOLVER_PARTIAL_CONDENSING) {
+    if (cfg->cond_N < 0 || cfg->cond_N > cfg->horizon) {
+      g_err = "b200qp_mpc_create: cond_N must be 0 (default) or 1..horizon";
+      return B200QP_ERR_ARG;
+    }
+    h->pc_cond = cfg->cond_N > 0 ? cfg->cond_N : (cfg->horizon + 3) / 4;  // default: blocks of 4 stages
+    if (const char *e = getenv("B200QP_PCOND_NUB")) h->pc_nub = atoi(e);  // development: cap on the stacked inputs of a block
+    int g = pcond_grid(h->num_sms, cfg->horizon, h->pc_cond, h->pc_nub);
+    if (const char *e = getenv("B200QP_BLOCKS_PER_SM")) g = h->num_sms * (atoi(e) > 0 ? atoi(e) : 1);
+    if ((size_t)g > nb) g = (int)nb;
+    h->pc_grid = g;
+    CK(cudaMalloc(&h->d_pc_scratch, (size_t)g * pcond_scratch_doubles(cfg->horizon) * sizeof(double)));
+  }
+  if (cfg->solver == B200QP_SOLVER_CONDENSED_ADMM || cfg->solver == B200QP_SOLVER_AUTO) {
     for (int b = 0; b < 4; ++b) {
       const int bs = admm_block_size(b);
       int g = h->num_sms * admm_occupancy(b);
@@ -254,7 +274,7 @@ int32_t b200qp_mpc_create(const b200qp_mpc_config *cfg, b200qp_mpc **out) {
       CK(cudaMalloc(&h->d_hscratch[b], (size_t)g * ((size_t)bs * bs + B200QP_MAX_HORIZON * 36) * sizeof(double)));
     }
   }
-  if (cfg->solver != B200QP_SOLVER_CONDENSED_ADMM) {
+  if (cfg->solver == B200QP_SOLVER_SPARSE_RICCATI || cfg->solver == B200QP_SOLVER_AUTO) {
     int g = riccati_grid(h->num_sms, cfg->horizon);
     if ((size_t)g > nb) g = (int)nb;
     h->ric_grid = g;
@@ -301,6 +321,7 @@ void b200qp_mpc_destroy(b200qp_mpc *h) {
   cudaFree(h->d_retry);
   for (int b = 0; b < 4; ++b) cudaFree(h->d_hscratch[b]);
   cudaFree(h->d_ric_scratch);
+  cudaFree(h->d_pc_scratch);
   cudaFreeHost(h->h_in);
   cudaFreeHost(h->h_contact);
   cudaFreeHost(h->h_forces);
@@ -378,8 +399,14 @@ static int32_t solve_device_impl(b200qp_mpc *h, int32_t n, const double *d_in, c
   int launches = 0;
   CK(cudaEventRecord(h->ev0, h->stream));
   CK(cudaMemsetAsync(h->d_bin_count, 0, 16 * sizeof(int), h->stream));
-  const bool use_admm = h->cfg.solver != B200QP_SOLVER_SPARSE_RICCATI;
+  const bool use_admm = h->cfg.solver == B200QP_SOLVER_CONDENSED_ADMM || h->cfg.solver == B200QP_SOLVER_AUTO;
   const bool autosel = h->cfg.solver == B200QP_SOLVER_AUTO;
+  if (h->cfg.solver == B200QP_SOLVER_PARTIAL_CONDENSING) {  // block-condensed Riccati IPM over the whole batch
+    CK(launch_mpc_pcond(h->P, n, d_in, d_contact, d_forces, d_xpred, d_info, h->want_duals ? h->d_lam_box : nullptr,
+                        h->want_duals ? h->d_lam_g : nullptr, h->d_pc_scratch, h->d_bin_count + 9, h->pc_grid, h->stream, nullptr,
+                        nullptr, h->pc_cond, h->pc_nub, h->d_dbg_cycles));
+    ++launches;
+  }
   // The size bins (and the Riccati overflow list) are independent launches: bin 0 stays on the handle's stream, the others
   // fork onto their own streams after the binning kernel and join before the end event, so their tails overlap instead of
   // adding up (their persistent grids are sized for a whole GPU each; the hardware interleaves the resident blocks).
@@ -429,7 +456,7 @@ static int32_t solve_device_impl(b200qp_mpc *h, int32_t n, const double *d_in, c
       ++launches;
     }
   }
-  if (!use_admm || autosel) {  // whole batch, or (AUTO) the list of problems too large for the condensed kernel
+  if (h->cfg.solver == B200QP_SOLVER_SPARSE_RICCATI || autosel) {  // whole batch, or (AUTO) the problems too large for the condensed kernel
     cudaStream_t st = h->stream;
     if (autosel) {
       st = h->bin_stream[3];
@@ -716,7 +743,7 @@ int32_t b200qp_mpc_get_duals(b200qp_mpc *h, int32_t n, double *lam_box, double *
 
 int32_t b200qp_mpc_get_condensed(b200qp_mpc *h, int32_t index, double *H, int32_t ldh, double *g) {
   if (!h || !H || !g || index < 0 || index >= h->last_n || !h->last_in) return B200QP_ERR_ARG;
-  if (h->cfg.solver == B200QP_SOLVER_SPARSE_RICCATI) return B200QP_ERR_UNSUPPORTED;
+  if (h->cfg.solver == B200QP_SOLVER_SPARSE_RICCATI || h->cfg.solver == B200QP_SOLVER_PARTIAL_CONDENSING) return B200QP_ERR_UNSUPPORTED;
   CK(cudaSetDevice(h->cfg.device));
   const int N = h->cfg.horizon;
   const size_t in_d = (size_t)b200qp_mpc_in_doubles(N);

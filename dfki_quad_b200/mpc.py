@@ -85,8 +85,9 @@ def euler_to_quaternion(e):
 class BatchedMPC:
     """Drop-in for `MPC` over a batch.  Constructor arguments follow mpc.hpp:117-127; `solver` accepts the reference's
     acados plan names ("PARTIAL_CONDENSING_HPIPM", "PARTIAL_CONDENSING_OSQP", ...) or the kernel names
-    "CONDENSED_ADMM" / "SPARSE_RICCATI"; `condensing_N`, `hpipm_mode`, `warm_start` are accepted for signature
-    compatibility (the GPU kernels always solve to `kkt_tol`)."""
+    "CONDENSED_ADMM" / "SPARSE_RICCATI" / "PARTIAL_CONDENSING" / "AUTO"; `condensing_N` is the reference's cond_N (used by the
+    partial-condensing kernel: number of blocks, None = library default), `hpipm_mode` is accepted for signature compatibility
+    (the GPU kernels always solve to `kkt_tol`), `warm_start` as in the reference (0 cold, 1 warm, 2 hot)."""
 
     def __init__(self, alpha, state_weights, mu, fmin, fmax, solver="CONDENSED_ADMM", condensing_N=None,
                  hpipm_mode="BALANCE", warm_start=0, *, horizon=10, dt=0.05, max_batch=4096, device=0, **opts):
@@ -99,6 +100,7 @@ class BatchedMPC:
         sw = np.asarray(state_weights, dtype=np.float64).reshape(12)
         for i in range(12):
             cfg.state_weights[i] = sw[i]
+        cfg.cond_N = int(condensing_N) if condensing_N else 0  # MPC::MPC condensing_N (mpc.hpp:125)
         cfg.warm_start = int(warm_start)  # MPC::MPC warm_start (mpc.hpp:127): 0 cold, 1 warm, 2 hot
         for k, v in opts.items():
             if not hasattr(cfg, k):

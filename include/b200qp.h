@@ -47,6 +47,9 @@ extern "C" {
 /* solver selection, named after the reference's acados plans (mit_controller_node.cpp:502-519) */
 #define B200QP_SOLVER_CONDENSED_ADMM 0 /* replaces PARTIAL_CONDENSING_OSQP with small cond_N / FULL_CONDENSING_* */
 #define B200QP_SOLVER_SPARSE_RICCATI 1 /* replaces PARTIAL_CONDENSING_HPIPM with cond_N == N                     */
+#define B200QP_SOLVER_PARTIAL_CONDENSING 3 /* replaces PARTIAL_CONDENSING_HPIPM for ANY cond_N in 1..N (mpc.cpp:219-225):  */
+                                       /* block-condensed Riccati interior-point kernel, b200qp_mpc_config.cond_N blocks;  */
+                                       /* cond_N = N is the sparse formulation, cond_N = 1 the fully condensed one          */
 #define B200QP_SOLVER_AUTO 2           /* per problem: condensed kernel when the reduced size fits (<= 156 free     */
                                        /* variables), sparse Riccati kernel otherwise; same optimum either way;     */
                                        /* problems the condensed kernel gives up on are retried on the Riccati one  */
@@ -78,6 +81,10 @@ typedef struct b200qp_mpc_config {
                               /* (primal, duals) of this handle; 2 hot start - the previous active set is tried first (one        */
                               /* polish round, no factorisation of K) and ADMM only runs, warm-started, if that is not optimal.   */
                               /* Condensed kernel only; the Riccati IPM always starts cold.                                       */
+  int32_t cond_N;             /* B200QP_SOLVER_PARTIAL_CONDENSING: number of blocks the horizon is condensed into, the reference's */
+                              /* `condensing_N` constructor argument (mpc.hpp:125, mpc.cpp:219-225; HPIPM block sizes: N / cond_N,  */
+                              /* the first N mod cond_N blocks one longer).  0 => library default (blocks of 4 stages).  Every      */
+                              /* value gives the same optimum; blocks with more than 128 stacked stance inputs are split.           */
 } b200qp_mpc_config;
 
 /* Input record of one problem = the subset of {StateInterface, ModelInterface, GaitSequence} that

@@ -43,12 +43,14 @@ struct SolverInformation {    // mpc_interface.hpp:10-20
 class BatchedMPC {
  public:
   // Arguments follow MPC::MPC (mpc.hpp:117-127); `solver` is B200QP_SOLVER_* (AUTO picks the kernel per problem),
-  // `warm_start` as the reference's last constructor argument (0 cold, 1 warm, 2 hot start per batch slot).
+  // `warm_start` as the reference's last constructor argument (0 cold, 1 warm, 2 hot start per batch slot), `condensing_N`
+  // as the reference's cond_N (B200QP_SOLVER_PARTIAL_CONDENSING; 0 = library default).
   BatchedMPC(double alpha, const std::array<double, 12> &state_weights, double mu, double fmin, double fmax, int solver,
-             int horizon, double dt, int max_batch, int device = 0, int warm_start = 0)
+             int horizon, double dt, int max_batch, int device = 0, int warm_start = 0, int condensing_N = 0)
       : N_(horizon), max_batch_(max_batch) {
     b200qp_mpc_config c{};
     c.horizon = horizon; c.solver = solver; c.max_batch = max_batch; c.device = device; c.warm_start = warm_start;
+    c.cond_N = condensing_N;
     c.dt = dt; c.alpha = alpha; c.mu = mu; c.fmin = fmin; c.fmax = fmax;
     for (int i = 0; i < 12; ++i) c.state_weights[i] = state_weights[i];
     check(b200qp_mpc_create(&c, &h_), "b200qp_mpc_create");

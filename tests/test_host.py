@@ -43,7 +43,7 @@ def test_struct_layout_matches_header():
     from dfki_quad_b200 import _lib
 
     assert ctypes.sizeof(_lib.SolverInfo) == 48
-    assert ctypes.sizeof(_lib.MpcConfig) == 16 + 8 * (2 + 12 + 3 + 5) + 24  # 5 trailing int32 (incl. warm_start) + padding
+    assert ctypes.sizeof(_lib.MpcConfig) == 16 + 8 * (2 + 12 + 3 + 5) + 24  # 6 trailing int32 (incl. warm_start, cond_N)
 
 
 def test_no_gpu_fails_loudly():
