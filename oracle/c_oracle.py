@@ -41,6 +41,8 @@ def load():
         _lib.ref_condense.argtypes = [C.POINTER(RefParams), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         _lib.ref_max_threads.restype = C.c_int
         _lib.ref_kkt_batch.restype = C.c_int
+        _lib.ref_riccati_batch.restype = C.c_int
+        _lib.ref_riccati_batch.argtypes = [C.POINTER(RefParams), C.c_int] + [C.c_void_p] * 5 + [C.c_double, C.c_int, C.c_int]
         _lib.ref_kkt_batch.argtypes = [C.POINTER(RefParams), C.c_int] + [C.c_void_p] * 7 + [C.c_int]
     return _lib
 
@@ -69,6 +71,48 @@ def solve_batch(N, rec, contact, params, threads=0, **kw):
     P = make_params(N, params, **kw)
     solved = lib.ref_solve_batch(C.byref(P), n, rec.ctypes.data, contact.ctypes.data, forces.ctypes.data, xpred.ctypes.data,
                                  C.addressof(info), threads)
+    arr = np.frombuffer(info, dtype=np.dtype([("status", "i4"), ("iters", "i4"), ("n_fact", "i4"), ("polished", "i4"),
+                                              ("kkt", "f8", (4,))]), count=n).copy()
+    return forces, xpred, arr, solved
+
+
+class WbcInfo(C.Structure):
+    _fields_ = [("status", C.c_int), ("iters", C.c_int), ("kkt", C.c_double * 4)]
+
+
+def wbc_batch(H, g, A, lo, hi, neq, tol=1e-8, max_iter=60, threads=0):
+    """C dense primal-dual IPM (wbc_ref.c) over a batch of WBC QPs in the C-ABI layout (column-major H [n,nq*nq], A [n,(neq+nin)*nq])."""
+    lib = load()
+    lib.wbc_ref_batch.restype = C.c_int
+    lib.wbc_ref_batch.argtypes = [C.c_int] * 4 + [C.c_void_p] * 5 + [C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+    H, g, A, lo, hi = (np.ascontiguousarray(a, dtype=np.float64) for a in (H, g, A, lo, hi))
+    n, nq = g.shape[0], g.shape[1]
+    nc = lo.shape[1]
+    x = np.zeros((n, nq))
+    info = (WbcInfo * n)()
+    solved = lib.wbc_ref_batch(n, nq, neq, nc - neq, H.ctypes.data, g.ctypes.data, A.ctypes.data, lo.ctypes.data, hi.ctypes.data, tol,
+                               max_iter, x.ctypes.data, C.addressof(info), threads)
+    arr = np.frombuffer(info, dtype=np.dtype([("status", "i4"), ("iters", "i4"), ("kkt", "f8", (4,))]), count=n).copy()
+    return x, arr, solved
+
+
+RICCATI_MODES = {"SPEED": (1e-6, 15), "BALANCE": (1e-8, 30), "parity": (1e-11, 60)}  # (residual target, iteration cap)
+
+
+def riccati_batch(N, rec, contact, params, mode="parity", threads=0):
+    """C Riccati primal-dual IPM on the sparse OCP-QP (mpc_ref.c::riccati_ipm_one): the restatement of the reference's default
+    PARTIAL_CONDENSING_HPIPM plan.  mode: SPEED-like / BALANCE-like / parity (same tolerance as the GPU kernels)."""
+    lib = load()
+    rec = np.ascontiguousarray(rec, dtype=np.float64)
+    contact = np.ascontiguousarray(contact, dtype=np.uint8)
+    n = rec.shape[0]
+    forces = np.zeros((n, N, 12))
+    xpred = np.zeros((n, N + 1, 13))
+    info = (RefInfo * n)()
+    P = make_params(N, params)
+    tol, cap = RICCATI_MODES[mode]
+    solved = lib.ref_riccati_batch(C.byref(P), n, rec.ctypes.data, contact.ctypes.data, forces.ctypes.data, xpred.ctypes.data,
+                                   C.addressof(info), tol, cap, threads)
     arr = np.frombuffer(info, dtype=np.dtype([("status", "i4"), ("iters", "i4"), ("n_fact", "i4"), ("polished", "i4"),
                                               ("kkt", "f8", (4,))]), count=n).copy()
     return forces, xpred, arr, solved

@@ -732,6 +732,274 @@ int ref_kkt_batch(const ref_params *P, int n, const double *in, const uint8_t *c
   return 0;
 }
 
+
+/* ---- (4) Riccati-based primal-dual interior-point method on the SPARSE OCP-QP: the restatement of the reference's
+ * default plan PARTIAL_CONDENSING_HPIPM (config/mit_controller_sim_go2.yaml:24) at cond_N = N.  HPIPM's algorithm
+ * (Frison & Diehl, "HPIPM: a high-performance quadratic programming framework for model predictive control", 2020) is
+ * a Mehrotra predictor-corrector IPM whose Newton systems are solved by a backward Riccati recursion; its modes differ in
+ * tolerances / iteration caps / refinement (mpc.cpp:226-234 only passes the mode string; the constants are upstream's and
+ * not verifiable here).  This port uses dense nx = 13, nu = 12 stage matrices as the reference formulates them; forces of
+ * swing feet (lbu = ubu = 0, mpc.cpp:110-113) are eliminated.  `tol` is the residual target, `max_iter` the cap:
+ *     SPEED-like  : tol 1e-6,  max_iter 15        BALANCE-like: tol 1e-8, max_iter 30        parity: tol 1e-11, max_iter 60
+ * CPU baseline of bench.py for the sparse configuration; never linked into the product. */
+typedef struct {
+  double K[MAXN][NU * NX], L[MAXN][NU * NU], kff[MAXN][NU], P[NX * NX], p[NX];
+  double X[MAXN + 1][NX], lam[MAXN + 2][NX], U[MAXN][NU], dU[MAXN][NU];
+  double s[MAXN][4][10], z[MAXN][4][10], ds[MAXN][4][10], dz[MAXN][4][10], rp[MAXN][4][10], rd[MAXN][NU], rt[MAXN][NU];
+  int idx[MAXN][NU], nu[MAXN];
+} ric_ws;
+
+static void foot_G(const double *f, double mu, double g[10]) {
+  g[0] = f[0]; g[1] = -f[0]; g[2] = f[1]; g[3] = -f[1]; g[4] = f[2]; g[5] = -f[2];
+  g[6] = f[0] - mu * f[2]; g[7] = -f[0] - mu * f[2]; g[8] = f[1] - mu * f[2]; g[9] = -f[1] - mu * f[2];
+}
+static void foot_GT(const double *v, double mu, double o[3]) {
+  o[0] = (v[0] - v[1]) + (v[6] - v[7]);
+  o[1] = (v[2] - v[3]) + (v[8] - v[9]);
+  o[2] = (v[4] - v[5]) - mu * ((v[6] + v[7]) + (v[8] + v[9]));
+}
+
+static int riccati_ipm_one(const ref_params *P, const double *rec, const uint8_t *ct, ref_ws *W, ric_ws *R, double tol, int max_iter,
+                           double *forces, double *xpred, ref_info *info) {
+  const int N = P->N;
+  const double mu = P->mu;
+  build_qp(P, rec, ct, W);
+  double Q[NX];
+  for (int i = 0; i < 12; ++i) Q[i] = P->w[i];
+  Q[12] = 0;
+  const double hh[10] = {P->fmax, P->fmax, P->fmax, P->fmax, P->fmax, -P->fmin, 0, 0, 0, 0};
+  int mtot = 0;
+  for (int k = 0; k < N; ++k) {
+    int ns = ct[4 * k] + ct[4 * k + 1] + ct[4 * k + 2] + ct[4 * k + 3];
+    R->nu[k] = 0;
+    for (int j = 0; j < NU; ++j) {
+      R->U[k][j] = 0;
+      if (ct[4 * k + j / 3]) {
+        R->idx[k][R->nu[k]++] = j;
+        if (j % 3 == 2) { /* weight-sharing start, strictly inside the box and the pyramid */
+          double v = rec[13] * 9.8067 / ns, span = P->fmax - P->fmin;
+          R->U[k][j] = fmin(fmax(v, P->fmin + 0.05 * span), P->fmax - 0.05 * span);
+        }
+      }
+    }
+    for (int f = 0; f < 4; ++f) if (ct[4 * k + f]) {
+      double g[10];
+      foot_G(R->U[k] + 3 * f, mu, g);
+      for (int r = 0; r < 10; ++r) { R->s[k][f][r] = fmax(hh[r] - g[r], 1e-2); R->z[k][f][r] = 1.0 / R->s[k][f][r]; }
+      mtot += 10;
+    }
+  }
+  memset(info, 0, sizeof(*info));
+  info->status = 2;
+  int it;
+  for (it = 0; it <= max_iter; ++it) {
+    /* roll-out and exact adjoint */
+    memcpy(R->X[0], W->x0, sizeof(double) * NX);
+    for (int k = 0; k < N; ++k)
+      for (int r = 0; r < NX; ++r) {
+        double a = 0;
+        for (int t = 0; t < NX; ++t) a += W->A[r * NX + t] * R->X[k][t];
+        for (int c = 0; c < NU; ++c) a += W->B[k][r * NU + c] * R->U[k][c];
+        R->X[k + 1][r] = a;
+      }
+    memset(R->lam[N + 1], 0, sizeof(double) * NX);
+    for (int k = N; k >= 1; --k)
+      for (int r = 0; r < NX; ++r) {
+        double a = Q[r] * R->X[k][r] + W->q[k][r];
+        if (k < N) for (int t = 0; t < NX; ++t) a += W->A[t * NX + r] * R->lam[k + 1][t];
+        R->lam[k][r] = a;
+      }
+    /* residuals */
+    double res = 0, cmax = 0, gap = 0;
+    for (int k = 0; k < N; ++k)
+      for (int f = 0; f < 4; ++f) {
+        if (!ct[4 * k + f]) continue;
+        double g[10], gz[3];
+        foot_G(R->U[k] + 3 * f, mu, g);
+        foot_GT(R->z[k][f], mu, gz);
+        for (int c = 0; c < 3; ++c) {
+          double a = P->alpha * R->U[k][3 * f + c] + gz[c];
+          for (int t = 0; t < NX; ++t) a += W->B[k][t * NU + 3 * f + c] * R->lam[k + 1][t];
+          R->rd[k][3 * f + c] = a;
+          res = fmax(res, fabs(a));
+        }
+        for (int r = 0; r < 10; ++r) {
+          R->rp[k][f][r] = g[r] + R->s[k][f][r] - hh[r];
+          res = fmax(res, fabs(R->rp[k][f][r]));
+          cmax = fmax(cmax, R->s[k][f][r] * R->z[k][f][r]);
+          gap += R->s[k][f][r] * R->z[k][f][r];
+        }
+      }
+    info->kkt[0] = res; info->kkt[3] = cmax;
+    if (!(res < 1e300)) { info->status = 1; break; }
+    if ((res <= tol && cmax <= tol) || mtot == 0) { info->status = 0; break; }
+    if (it == max_iter) { if (res <= 1e3 * tol && cmax <= 1e3 * tol && res <= 1e-6) info->status = 0; break; }
+    const double mu_c = gap / mtot;
+    /* Riccati factorisation with R~ = alpha I + G' W G */
+    for (int i = 0; i < NX * NX; ++i) R->P[i] = 0;
+    for (int i = 0; i < NX; ++i) R->P[i * NX + i] = Q[i];
+    for (int k = N - 1; k >= 0; --k) {
+      const int nu = R->nu[k];
+      const int *ix = R->idx[k];
+      double PA[NX * NX], PB[NX * NU], Huu[NU * NU], Hux[NU * NX];
+      for (int r = 0; r < NX; ++r) {
+        for (int c = 0; c < NX; ++c) { double a = 0; for (int t = 0; t < NX; ++t) a += R->P[r * NX + t] * W->A[t * NX + c]; PA[r * NX + c] = a; }
+        for (int j = 0; j < nu; ++j) { double a = 0; for (int t = 0; t < NX; ++t) a += R->P[r * NX + t] * W->B[k][t * NU + ix[j]]; PB[r * NU + j] = a; }
+      }
+      for (int i = 0; i < nu; ++i) {
+        for (int j = 0; j <= i; ++j) { double a = 0; for (int t = 0; t < NX; ++t) a += W->B[k][t * NU + ix[i]] * PB[t * NU + j]; Huu[i * NU + j] = a; }
+        for (int c = 0; c < NX; ++c) { double a = 0; for (int t = 0; t < NX; ++t) a += W->B[k][t * NU + ix[i]] * PA[t * NX + c]; Hux[i * NX + c] = a; }
+      }
+      for (int f = 0; f < 4; ++f) {
+        if (!ct[4 * k + f]) continue;
+        double w[10];
+        for (int r = 0; r < 10; ++r) w[r] = R->z[k][f][r] / R->s[k][f][r];
+        int b = 0;
+        while (ix[b] != 3 * f) ++b;
+        Huu[b * NU + b] += P->alpha + (w[0] + w[1]) + (w[6] + w[7]);
+        Huu[(b + 1) * NU + b + 1] += P->alpha + (w[2] + w[3]) + (w[8] + w[9]);
+        Huu[(b + 2) * NU + b + 2] += P->alpha + (w[4] + w[5]) + mu * mu * ((w[6] + w[7]) + (w[8] + w[9]));
+        Huu[(b + 2) * NU + b] += -mu * (w[6] - w[7]);
+        Huu[(b + 2) * NU + b + 1] += -mu * (w[8] - w[9]);
+      }
+      if (nu > 0 && chol(Huu, nu, NU)) { info->status = 1; goto done; }
+      memcpy(R->L[k], Huu, sizeof(Huu));
+      /* K = -Huu^-1 Hux (column by column), P <- Q + A'PA + Hux' K */
+      for (int c = 0; c < NX; ++c) {
+        double col[NU];
+        for (int i = 0; i < nu; ++i) col[i] = Hux[i * NX + c];
+        chol_solve(Huu, nu, NU, col);
+        for (int i = 0; i < nu; ++i) R->K[k][i * NX + c] = -col[i];
+      }
+      double Pn[NX * NX];
+      for (int r = 0; r < NX; ++r)
+        for (int c = 0; c < NX; ++c) {
+          double a = (r == c) ? Q[r] : 0.0;
+          for (int t = 0; t < NX; ++t) a += W->A[t * NX + r] * PA[t * NX + c];
+          for (int i = 0; i < nu; ++i) a += Hux[i * NX + r] * R->K[k][i * NX + c];
+          Pn[r * NX + c] = a;
+        }
+      memcpy(R->P, Pn, sizeof(Pn));
+    }
+    /* predictor / corrector */
+    double sigma_mu = 0;
+    for (int pass = 0; pass < 2; ++pass) {
+      for (int k = 0; k < N; ++k)
+        for (int f = 0; f < 4; ++f) {
+          if (!ct[4 * k + f]) continue;
+          double t10[10], o[3];
+          for (int r = 0; r < 10; ++r) {
+            double rc = R->s[k][f][r] * R->z[k][f][r] + (pass ? R->ds[k][f][r] * R->dz[k][f][r] - sigma_mu : 0.0);
+            t10[r] = (R->z[k][f][r] * R->rp[k][f][r] - rc) / R->s[k][f][r];
+          }
+          foot_GT(t10, mu, o);
+          for (int c = 0; c < 3; ++c) R->rt[k][3 * f + c] = R->rd[k][3 * f + c] + o[c];
+        }
+      memset(R->p, 0, sizeof(R->p));
+      for (int k = N - 1; k >= 0; --k) { /* hu = r~ + B'p, kff = -Huu^-1 hu, p <- A'p + Hux' kff = A'p - K' hu */
+        const int nu = R->nu[k];
+        const int *ix = R->idx[k];
+        double hu[NU], pn[NX];
+        for (int i = 0; i < nu; ++i) { double a = R->rt[k][ix[i]]; for (int t = 0; t < NX; ++t) a += W->B[k][t * NU + ix[i]] * R->p[t]; hu[i] = a; }
+        for (int r = 0; r < NX; ++r) {
+          double a = 0;
+          for (int t = 0; t < NX; ++t) a += W->A[t * NX + r] * R->p[t];
+          for (int i = 0; i < nu; ++i) a += R->K[k][i * NX + r] * hu[i];
+          pn[r] = a;
+        }
+        chol_solve(R->L[k], nu, NU, hu);
+        for (int i = 0; i < nu; ++i) R->kff[k][i] = -hu[i];
+        memcpy(R->p, pn, sizeof(pn));
+      }
+      double dx[NX] = {0};
+      for (int k = 0; k < N; ++k) {
+        const int nu = R->nu[k];
+        const int *ix = R->idx[k];
+        double nx[NX];
+        for (int c = 0; c < NU; ++c) R->dU[k][c] = 0;
+        for (int i = 0; i < nu; ++i) { double a = R->kff[k][i]; for (int c = 0; c < NX; ++c) a += R->K[k][i * NX + c] * dx[c]; R->dU[k][ix[i]] = a; }
+        for (int r = 0; r < NX; ++r) {
+          double a = 0;
+          for (int t = 0; t < NX; ++t) a += W->A[r * NX + t] * dx[t];
+          for (int i = 0; i < nu; ++i) a += W->B[k][r * NU + ix[i]] * R->dU[k][ix[i]];
+          nx[r] = a;
+        }
+        memcpy(dx, nx, sizeof(nx));
+      }
+      double tmax = 0, g2 = 0, c1 = 0, c2 = 0;
+      static __thread double dsn[MAXN][4][10], dzn[MAXN][4][10];
+      for (int k = 0; k < N; ++k)
+        for (int f = 0; f < 4; ++f) {
+          if (!ct[4 * k + f]) continue;
+          double gd[10];
+          foot_G(R->dU[k] + 3 * f, mu, gd);
+          for (int r = 0; r < 10; ++r) {
+            double sk = R->s[k][f][r], zk = R->z[k][f][r];
+            double rc = sk * zk + (pass ? R->ds[k][f][r] * R->dz[k][f][r] - sigma_mu : 0.0);
+            dsn[k][f][r] = -R->rp[k][f][r] - gd[r];
+            dzn[k][f][r] = (-rc - zk * dsn[k][f][r]) / sk;
+            tmax = fmax(tmax, fmax(-dsn[k][f][r] / sk, -dzn[k][f][r] / zk));
+          }
+        }
+      double a = tmax > 1.0 ? 1.0 / tmax : 1.0;
+      if (pass == 0) {
+        for (int k = 0; k < N; ++k)
+          for (int f = 0; f < 4; ++f) if (ct[4 * k + f])
+            for (int r = 0; r < 10; ++r) {
+              g2 += (R->s[k][f][r] + a * dsn[k][f][r]) * (R->z[k][f][r] + a * dzn[k][f][r]);
+              R->ds[k][f][r] = dsn[k][f][r]; R->dz[k][f][r] = dzn[k][f][r];
+            }
+        double ratio = (g2 / mtot) / fmax(mu_c, 1e-300);
+        sigma_mu = ratio * ratio * ratio * mu_c;
+      } else {
+        a = fmin(1.0, 0.995 * a);
+        if (res < cmax) { /* monotone-gap safeguard against Mehrotra's two-cycle */
+          for (int k = 0; k < N; ++k)
+            for (int f = 0; f < 4; ++f) if (ct[4 * k + f])
+              for (int r = 0; r < 10; ++r) { c1 += R->s[k][f][r] * dzn[k][f][r] + R->z[k][f][r] * dsn[k][f][r]; c2 += dsn[k][f][r] * dzn[k][f][r]; }
+          double lin = c1 + 0.1 * gap;
+          if (c2 > 0 && lin < 0) a = fmin(a, -lin / c2);
+        }
+        for (int k = 0; k < N; ++k) {
+          for (int c = 0; c < NU; ++c) R->U[k][c] += a * R->dU[k][c];
+          for (int f = 0; f < 4; ++f) if (ct[4 * k + f])
+            for (int r = 0; r < 10; ++r) { R->s[k][f][r] += a * dsn[k][f][r]; R->z[k][f][r] += a * dzn[k][f][r]; }
+        }
+      }
+    }
+  }
+done:
+  info->iters = it;
+  if (info->status == 0) {
+    if (forces) for (int k = 0; k < N; ++k) memcpy(forces + NU * k, R->U[k], sizeof(double) * NU);
+    if (xpred) for (int k = 0; k <= N; ++k) memcpy(xpred + NX * k, R->X[k], sizeof(double) * NX);
+  }
+  return info->status;
+}
+
+/* batch entry of the Riccati IPM port: one problem per thread.  Returns the number of problems with status 0. */
+int ref_riccati_batch(const ref_params *P, int n, const double *in, const uint8_t *contact, double *forces, double *xpred,
+                      ref_info *info, double tol, int max_iter, int threads) {
+  if (P->N < 1 || P->N > MAXN) return -1;
+  const int stride = 26 + 13 * (P->N + 1) + 12 * P->N;
+  int solved = 0;
+#ifdef _OPENMP
+  if (threads > 0) omp_set_num_threads(threads);
+#endif
+#pragma omp parallel reduction(+ : solved)
+  {
+    ref_ws *W = (ref_ws *)malloc(sizeof(ref_ws));
+    ric_ws *R = (ric_ws *)malloc(sizeof(ric_ws));
+#pragma omp for schedule(dynamic, 4)
+    for (int p = 0; p < n; ++p)
+      solved += riccati_ipm_one(P, in + (size_t)p * stride, contact + (size_t)p * P->N * 4, W, R, tol, max_iter,
+                                forces ? forces + (size_t)p * P->N * NU : 0, xpred ? xpred + (size_t)p * (P->N + 1) * NX : 0, info + p) == 0;
+    free(W);
+    free(R);
+  }
+  return solved;
+}
+
 /* condensed H (row-major 12N x 12N) and g of one problem, for cross-checks */
 int ref_condense(const ref_params *P, const double *rec, const uint8_t *ct, double *H, double *g) {
   ref_ws *W = (ref_ws *)malloc(sizeof(ref_ws));
