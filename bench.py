@@ -202,7 +202,7 @@ def run_reference(args):
             total_t += res["seconds"]
     value = total_solved / total_t
     line = {
-        "impl": "reference", "metric": "MPC QP solves/sec (Go2, horizon 10, batch N)", "value": value, "unit": "solves/s",
+        "impl": "reference", "metric": f"MPC QP solves/sec (Go2, horizon {N}, batch N)", "value": value, "unit": "solves/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total_t / max(args.steps, 1),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": wl["name"], "horizon": N, "batch_per_gpu": B, "gait": "/".join(wl["gaits"]), "solver": res["solver"]},
@@ -365,9 +365,13 @@ def run_b200(args):
                 cpu = cpu_reference(N, batch["rec"], batch["contact"], args.cpu_budget)
             except Exception as e:  # the CPU baseline is a reported extra, never a reason to lose the GPU line
                 cpu = {"error": repr(e)}
+        fp64_frac = fl / kern_s / 1e12 / fp64_peak if fp64_peak else None
         line = {
-            "metric": "MPC QP solves/sec (Go2, horizon 10, batch N)", "value": value, "unit": "solves/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms_max / args.steps, "higher_is_better": True,
+            "metric": f"MPC QP solves/sec (Go2, horizon {N}, batch N)", "value": value, "unit": "solves/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms_max / args.steps,
+            "step_ms": {"min": float(min(step_ms)), "median": float(np.median(step_ms)), "max": float(max(step_ms)),
+                        "note": "per-step device time on rank 0 (CUDA events on the handle's stream)"},
+            "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": wl["name"], "horizon": N, "batch_per_gpu": B, "gait": "/".join(wl["gaits"]), "solver": wl["solver"],
                        "l2": "256 MiB flush between timed iterations", "converged_fraction": conv_all / issued_all,
@@ -384,10 +388,15 @@ def run_b200(args):
             "clocks": clocks.summary(),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "kernel": wl["kernel"],
-                         "algorithmic_bytes_per_solve": ab,
-                         "note": "latency/FP64-bound on-chip solve: HBM fraction is tiny by design (SURVEY.md 8d)"},
+                         "algorithmic_bytes_per_solve": ab, "binding_ceiling": "fp64 FMA pipe / shared-memory latency (on-chip working set)",
+                         "fp64_frac": fp64_frac,
+                         "note": "HBM is NOT the binding ceiling of this kernel (SURVEY.md 8d): the on-chip solve is bound by the FP64 "
+                                 "pipe and shared-memory latency, so the contract's HBM fraction is tiny by design and fp64_frac "
+                                 "(algorithmic FLOPs / step time / measured DFMA peak, details under `fp64`) is the number to read. "
+                                 "algorithmic_bytes uses the library's 48-byte info record (status, iterations, polish rounds, n_free, "
+                                 "KKT 4-tuple); SURVEY 8d's formula with a 16-byte record gives 32 bytes less per solve (0.7 %)."},
             "fp64": {"flops_per_step": fl, "achieved_tflops": fl / kern_s / 1e12, "measured_peak_tflops": fp64_peak,
-                     "frac": fl / kern_s / 1e12 / fp64_peak if fp64_peak else None, "nominal_peak_tflops": 37.0,
+                     "frac": fp64_frac, "nominal_peak_tflops": 37.0,
                      "note": "algorithmic FP64 FLOPs of the method as implemented / step time; peak = DFMA microbenchmark on this GPU"},
         }
         if wl["solver"] == "CONDENSED_ADMM" and not args.no_closed_loop:
@@ -397,13 +406,368 @@ def run_b200(args):
                 line["closed_loop_hot_start"] = {"error": repr(e)}
         if cpu is not None and "error" not in cpu:
             line["cpu_baseline"] = {"value": cpu["solved"] / cpu["seconds"], "unit": "solves/s", "cores": cpu["cores"],
-                                    "kind": cpu["kind"], "sample": cpu["sample"]}
+                                    "kind": cpu["kind"], "sample": cpu["sample"], "solver": cpu.get("solver"),
+                                    "note": "any GPU/CPU ratio depends on this box's host core count - quote it with `cores`"}
+            if not args.no_extras:
+                try:
+                    line["cpu_baseline"]["more"] = cpu_extras(N, batch["rec"], batch["contact"], wl)
+                except Exception as e:
+                    line["cpu_baseline"]["more"] = {"error": repr(e)}
         elif cpu is not None:
             line["cpu_baseline"] = cpu
+    # ---- the other BASELINE.json configurations, budgeted (a few seconds each), every rank takes part ---------------------
+    extras = None
+    if args.workload == "config2" and not args.no_extras:
+        extras = {}
+        for name, fn in (("config3", extra_config3), ("config4", extra_config4), ("config5_strong", extra_config5), ("fp32", extra_fp32)):
+            try:
+                extras[name] = fn(args, dev, rank, world)
+            except Exception as e:  # an extra never costs the headline line
+                extras[name] = {"error": repr(e)}
+    if rank == 0:
+        if extras is not None:
+            line["other_configs"] = extras
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+# ----------------------------------------------------------------------------------------------------- extras
+INFO_DT = np.dtype([("status", "i4"), ("iterations", "i4"), ("polish_rounds", "i4"), ("n_free", "i4"), ("kkt", "f8", (4,))])
+
+
+def _reduce(world, dev, maxes, sums):
+    import torch
+
+    if world == 1:
+        return list(maxes), list(sums)
+    import torch.distributed as dist
+
+    a = torch.tensor(maxes, dtype=torch.float64, device=dev)
+    b = torch.tensor(sums, dtype=torch.float64, device=dev)
+    dist.all_reduce(a, op=dist.ReduceOp.MAX)
+    dist.all_reduce(b, op=dist.ReduceOp.SUM)
+    return a.tolist(), b.tolist()
+
+
+def cpu_extras(N, rec, contact, wl):
+    """More of the restated reference CPU path on the headline batch (rank 0, bounded): OSQP's library-default penalty, the
+    Riccati IPM port in its three modes, and config 1 = single-problem single-thread latency."""
+    from oracle import c_oracle, mpc_oracle as mo
+
+    params = dict(mo.GO2_PARAMS)
+    params["weights"] = params["w_move"]
+    cores = os.cpu_count() or 1
+    m = min(rec.shape[0], 64 * cores)
+    out = {}
+    t0 = time.perf_counter()
+    _, _, inf, solved = c_oracle.solve_batch(N, rec[:m], contact[:m], params, threads=cores, rho=0.1)
+    out["admm_osqp_default_rho_0.1"] = {"value": solved / (time.perf_counter() - t0), "unit": "solves/s", "cores": cores,
+                                        "mean_iterations": float(inf["iters"].mean()), "sample": f"first {m} problems"}
+    for mode in ("SPEED", "BALANCE", "parity"):
+        t0 = time.perf_counter()
+        _, _, inf, solved = c_oracle.riccati_batch(N, rec[:m], contact[:m], params, mode=mode, threads=cores)
+        out[f"riccati_ipm_{mode}"] = {"value": m / (time.perf_counter() - t0), "unit": "solves/s", "cores": cores,
+                                      "reached_tolerance": solved / m, "mean_iterations": float(inf["iters"].mean()),
+                                      "sample": f"first {m} problems",
+                                      "tolerance_cap": dict(zip(("tol", "max_iter"), c_oracle.RICCATI_MODES[mode]))}
+    # BASELINE.json configs[0]: one trot problem at a time on one thread
+    lat = {}
+    k = min(200, rec.shape[0])
+    for name, fn in (("admm_tuned", lambda i: c_oracle.solve_batch(N, rec[i:i + 1], contact[i:i + 1], params, threads=1)),
+                     ("admm_osqp_default", lambda i: c_oracle.solve_batch(N, rec[i:i + 1], contact[i:i + 1], params, threads=1, rho=0.1)),
+                     ("riccati_ipm_SPEED", lambda i: c_oracle.riccati_batch(N, rec[i:i + 1], contact[i:i + 1], params, mode="SPEED", threads=1)),
+                     ("riccati_ipm_BALANCE", lambda i: c_oracle.riccati_batch(N, rec[i:i + 1], contact[i:i + 1], params, mode="BALANCE", threads=1))):
+        ts = []
+        for i in range(k):
+            t0 = time.perf_counter()
+            fn(i)
+            ts.append(time.perf_counter() - t0)
+        ts = np.array(ts[5:]) * 1e3
+        lat[name] = {"median_ms": float(np.median(ts)), "p99_ms": float(np.percentile(ts, 99)), "problems": int(len(ts))}
+    out["config1_single_problem_latency_1_thread"] = lat
+    return out
+
+
+def _mpc_pass(mpc, ext, dev, B, N, rec, contact, steps, warmup, flush):
+    """device-resident + host-buffer timing of one handle on one batch -> dict of raw numbers (per rank)."""
+    import torch
+
+    rec_h = torch.from_numpy(rec).pin_memory()
+    ct_h = torch.from_numpy(contact).pin_memory()
+    with torch.cuda.stream(ext):
+        d_in, d_ct = rec_h.to(dev, non_blocking=True), ct_h.to(dev, non_blocking=True)
+        d_f = torch.zeros((B, N, 12), dtype=torch.float64, device=dev)
+        d_x = torch.zeros((B, N + 1, 13), dtype=torch.float64, device=dev)
+        d_info = torch.zeros((B, 48), dtype=torch.uint8, device=dev)
+    ext.synchronize()
+    for _ in range(warmup):
+        mpc.solve_device(B, d_in.data_ptr(), d_ct.data_ptr(), d_f.data_ptr(), d_x.data_ptr(), d_info.data_ptr(), sync=False)
+    ext.synchronize()
+    evs = []
+    for _ in range(steps):
+        with torch.cuda.stream(ext):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(ext)
+            mpc.solve_device(B, d_in.data_ptr(), d_ct.data_ptr(), d_f.data_ptr(), d_x.data_ptr(), d_info.data_ptr(), sync=False)
+            e1.record(ext)
+        evs.append((e0, e1))
+    ext.synchronize()
+    ms = float(sum(a.elapsed_time(b) for a, b in evs))
+    info = np.frombuffer(d_info.cpu().numpy().tobytes(), dtype=INFO_DT)
+    conv = (info["status"] == 0) & (info["kkt"].max(axis=1) <= KKT_TOL)
+    f_h = torch.zeros((B, N, 12), dtype=torch.float64).pin_memory().numpy()
+    x_h = torch.zeros((B, N + 1, 13), dtype=torch.float64).pin_memory().numpy()
+    mpc.solve_records(rec_h.numpy(), ct_h.numpy(), f_h, x_h)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        _, _, inf = mpc.solve_records(rec_h.numpy(), ct_h.numpy(), f_h, x_h)
+    e2e_s = time.perf_counter() - t0
+    conv_e2e = int((inf.success & (inf.kkt.max(axis=1) <= KKT_TOL)).sum())
+    return dict(ms=ms, conv=int(conv.sum()), e2e_s=e2e_s, conv_e2e=conv_e2e, info=info)
+
+
+def extra_config3(args, dev, rank, world, steps=3):
+    """BASELINE.json configs[2]: sparse Go2 MPC, horizon 16, 16384 mixed trot / pace / bound problems per GPU, Riccati IPM kernel."""
+    import torch
+
+    from dfki_quad_b200 import BatchedMPC, _lib, sequencer
+
+    wl = WORKLOADS["config3"]
+    N, B = wl["horizon"], wl["batch"]
+    cfg = sequencer.GO2_MPC
+    batch = sequencer.random_batch(B, N, seed=wl["seed"] + 1000 * rank, gaits=wl["gaits"], device=dev)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    out = {}
+    raw = {}
+    for key, solver, kw in (("riccati_kernel", "SPARSE_RICCATI", {}), ("partial_condensing_cond_N_4", "PARTIAL_CONDENSING", dict(condensing_N=4)),
+                            ("auto", "AUTO", {})):
+        mpc = BatchedMPC(cfg["alpha"], cfg["state_weights_move"], cfg["mu"], cfg["fmin"], cfg["fmax"], solver, horizon=N, dt=cfg["dt"],
+                         max_batch=B, device=dev, **kw)
+        ext = torch.cuda.ExternalStream(mpc.stream(), device=dev)
+        r = _mpc_pass(mpc, ext, dev, B, N, batch["rec"], batch["contact"], steps, 3, flush)
+        mpc.close()
+        (ms, e2e_s), (conv, conv_e2e) = _reduce(world, dev, [r["ms"], r["e2e_s"]], [r["conv"] * steps, r["conv_e2e"] * steps])
+        raw[key] = r
+        out[key] = {"value": conv / (ms * 1e-3), "unit": "solves/s", "ms_per_step": ms / steps,
+                    "e2e": {"value": conv_e2e / e2e_s, "unit": "solves/s"}, "converged_fraction": conv / (B * steps * world),
+                    "mean_iterations": float(r["info"]["iterations"].mean())}
+    if rank == 0:
+        info = raw["riccati_kernel"]["info"]
+        fl = float(info["iterations"].sum()) * N * (9600.0 + 2 * 1200.0)
+        kern_s = raw["riccati_kernel"]["ms"] / steps * 1e-3
+        try:
+            pk = _lib.fp64_peak_tflops(dev)
+            out["riccati_kernel"]["fp64"] = {"flops_per_step": fl, "achieved_tflops": fl / kern_s / 1e12, "frac": fl / kern_s / 1e12 / pk}
+        except Exception:
+            pass
+        peak, _ = measured_peaks()
+        out["riccati_kernel"]["roofline_hbm_frac"] = algorithmic_bytes(N) * B / kern_s / 1e9 / peak
+        if not args.no_cpu_baseline:
+            from oracle import c_oracle, mpc_oracle as mo
+
+            params = dict(mo.GO2_PARAMS)
+            params["weights"] = params["w_move"]
+            cores = os.cpu_count() or 1
+            m = min(B, 96 * cores)
+            cb = {}
+            for mode in ("SPEED", "BALANCE", "parity"):
+                t0 = time.perf_counter()
+                _, _, inf, solved = c_oracle.riccati_batch(N, batch["rec"][:m], batch["contact"][:m], params, mode=mode, threads=cores)
+                cb[f"riccati_ipm_{mode}"] = {"value": m / (time.perf_counter() - t0), "reached_tolerance": solved / m,
+                                             "mean_iterations": float(inf["iters"].mean())}
+            t0 = time.perf_counter()
+            _, _, inf, solved = c_oracle.solve_batch(N, batch["rec"][:m // 4], batch["contact"][:m // 4], params, threads=cores)
+            cb["dense_admm_port"] = {"value": solved / (time.perf_counter() - t0)}
+            out["cpu_baseline"] = {"unit": "solves/s", "cores": cores, "kind": "port", "sample": f"first {m} problems of rank 0's batch",
+                                   "value": cb["riccati_ipm_parity"]["value"], "modes": cb,
+                                   "note": "value = C Riccati IPM port (restatement of the reference's default PARTIAL_CONDENSING_HPIPM plan) "
+                                           "at the GPU kernels' tolerance; SPEED / BALANCE-like caps beside it"}
+    out["config"] = {"workload": wl["name"], "horizon": N, "batch_per_gpu": B, "gaits": "/".join(wl["gaits"]), "steps": steps,
+                     "l2": "256 MiB flush between timed iterations"}
+    return out
+
+
+def extra_config4(args, dev, rank, world, steps=3):
+    """BASELINE.json configs[3]: WBC task-space QP, 16384 per GPU."""
+    import torch
+
+    from dfki_quad_b200 import wbc
+
+    wl = WORKLOADS["config4"]
+    B = wl["batch"]
+    b = wbc.random_wbc_batch(B, seed=wl["seed"] + 1000 * rank, device=dev)
+    solver = wbc.BatchedWBCSolver(max_batch=B, device=dev)
+    H, g, A, lo, hi = solver.abi_arrays(b["qp"])
+    ext = torch.cuda.ExternalStream(solver.stream(), device=dev)
+    with torch.cuda.stream(ext):
+        dH, dg, dA, dlo, dhi = (torch.from_numpy(a).to(dev) for a in (H, g, A, lo, hi))
+        dx = torch.zeros((B, 30), dtype=torch.float64, device=dev)
+        dinfo = torch.zeros((B, 48), dtype=torch.uint8, device=dev)
+        flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    ext.synchronize()
+
+    def step():
+        solver.solve_device(B, dH.data_ptr(), dg.data_ptr(), dA.data_ptr(), dlo.data_ptr(), dhi.data_ptr(), dx.data_ptr(), dinfo.data_ptr(), sync=False)
+
+    for _ in range(3):
+        step()
+    ext.synchronize()
+    evs = []
+    for _ in range(steps):
+        with torch.cuda.stream(ext):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(ext)
+            step()
+            e1.record(ext)
+        evs.append((e0, e1))
+    ext.synchronize()
+    ms = float(sum(a.elapsed_time(c) for a, c in evs))
+    info = np.frombuffer(dinfo.cpu().numpy().tobytes(), dtype=INFO_DT)
+    conv = int(((info["status"] == 0) & (info["kkt"].max(axis=1) <= KKT_TOL)).sum())
+    Hp, gp, Ap, lop, hip = (torch.from_numpy(a).pin_memory().numpy() for a in (H, g, A, lo, hi))
+    xh = torch.zeros((B, 30), dtype=torch.float64).pin_memory().numpy()
+    solver.solve_abi(Hp, gp, Ap, lop, hip, xh)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        _, inf = solver.solve_abi(Hp, gp, Ap, lop, hip, xh)
+    e2e_s = time.perf_counter() - t0
+    conv_e2e = int(((inf["status"] == 0) & (inf["kkt"].max(axis=1) <= KKT_TOL)).sum())
+    (ms_m, e2e_m), (c1, c2) = _reduce(world, dev, [ms, e2e_s], [conv * steps, conv_e2e * steps])
+    out = {"metric": "WBC task-space QP solves/sec (Go2 reduced TSID, 30 vars, 18 eq, 28 ineq)", "value": c1 / (ms_m * 1e-3), "unit": "solves/s",
+           "ms_per_step": ms_m / steps, "e2e": {"value": c2 / e2e_m, "unit": "solves/s", "h2d_bytes_per_step": int(B * 19512), "d2h_bytes_per_step": int(B * 288)},
+           "converged_fraction": c1 / (B * steps * world), "mean_iterations": float(info["iterations"].mean()),
+           "kkt_max_converged": float(info["kkt"][(info["status"] == 0)].max()),
+           "config": {"workload": wl["name"], "batch_per_gpu": B, "steps": steps, "l2": "256 MiB flush between timed iterations"}}
+    if rank == 0 and not args.no_cpu_baseline:
+        from oracle import c_oracle
+
+        cores = os.cpu_count() or 1
+        m = min(B, 512 * cores)
+        t0 = time.perf_counter()
+        _, inf2, solved = c_oracle.wbc_batch(H[:m], g[:m], A[:m], lo[:m], hi[:m], 18, threads=cores)
+        out["cpu_baseline"] = {"value": solved / (time.perf_counter() - t0), "unit": "solves/s", "cores": cores, "kind": "port",
+                               "solved_fraction": solved / m, "sample": f"first {m} QPs of rank 0's batch",
+                               "solver": "C dense primal-dual IPM (oracle/wbc_ref.c), OpenMP over the batch"}
+    return out
+
+
+def extra_config5(args, dev, rank, world):
+    """BASELINE.json configs[4]: 1 048 576 DISTINCT problems (half config-2, half config-3 distribution), contiguous slices over
+    the GPUs (STRONG scaling: the total is fixed), host buffers end to end.  Every robot enters as a sequencer input
+    (state, feet, Target, gait, phase: 400 B) - trajectory planner, contact schedule and Raibert footholds run as a kernel -
+    and its GRFs + predicted states come back to pinned host memory.  `value` = problems / sum of kernel time (max over ranks),
+    `e2e` = problems / wall time of the host-buffer calls (max over ranks)."""
+    import torch
+
+    from dfki_quad_b200 import BatchedMPC, sequencer
+    from dfki_quad_b200.shard import shard_range
+
+    total = 1 << 20
+    lo_i, hi_i = shard_range(total, rank, world)
+    mine = hi_i - lo_i
+    chunk = 65536
+    cfg = sequencer.GO2_MPC
+    res = []
+    kern_ms = wall = 0.0
+    conv = 0
+    sample = None
+    for tag, N, gaits, solver, lo_p, hi_p in (("h10_trot", 10, ("TROT",), "CONDENSED_ADMM", 0, total // 2),
+                                               ("h16_mixed", 16, ("TROT", "PACE", "BOUND"), "AUTO", total // 2, total)):
+        a, b = max(lo_i, lo_p), min(hi_i, hi_p)
+        if b <= a:
+            continue
+        # distinct problems: the global problem index seeds nothing twice (one generator stream per 65536-problem chunk)
+        mpc = BatchedMPC(cfg["alpha"], cfg["state_weights_move"], cfg["mu"], cfg["fmin"], cfg["fmax"], solver, horizon=N, dt=cfg["dt"],
+                         max_batch=chunk, device=dev)
+        mpc.set_model(**sequencer.go2_seq_model())
+        f_h = torch.zeros((chunk, N, 12), dtype=torch.float64).pin_memory().numpy()
+        x_h = torch.zeros((chunk, N + 1, 13), dtype=torch.float64).pin_memory().numpy()
+        seq_pin = torch.zeros((chunk, 50), dtype=torch.float64).pin_memory().numpy()
+        first = True
+        for c0 in range(a, b, chunk):
+            n = min(chunk, b - c0)
+            seq_pin[:n] = sequencer.random_seq_inputs(n, seed=WORKLOADS["config5"]["seed"] + c0 // 4096 + 7, gaits=gaits)
+            if first:  # warm-up on the first chunk (untimed), and a CPU sample of the same problems
+                mpc.sequence_and_solve(seq_pin[:n], None, f_h[:n], x_h[:n])
+                if rank == 0 and sample is None and not args.no_cpu_baseline:
+                    sample = (N,) + mpc.sequence_records(seq_pin[: min(n, 4096)])
+                first = False
+            t0 = time.perf_counter()
+            _, _, inf = mpc.sequence_and_solve(seq_pin[:n], None, f_h[:n], x_h[:n])
+            wall += time.perf_counter() - t0
+            kern_ms += inf.total_solver_time * 1e3
+            conv += int((inf.success & (inf.kkt.max(axis=1) <= KKT_TOL)).sum())
+        mpc.close()
+    (kern_m, wall_m), (conv_all,) = _reduce(world, dev, [kern_ms, wall], [conv])
+    out = {"metric": "MPC QP solves/sec (Go2, 1M-problem mixed sweep: horizon 10 trot + horizon 16 trot/pace/bound)", "scaling": "strong",
+           "value": conv_all / (kern_m * 1e-3), "unit": "solves/s", "e2e": {"value": conv_all / wall_m, "unit": "solves/s",
+                                                                           "h2d_bytes_per_step": int(total * 400),
+                                                                           "d2h_bytes_per_step": int(total // 2 * (2152 + 3368))},
+           "converged_fraction": conv_all / total, "seconds_for_the_sweep_e2e": wall_m,
+           "config": {"workload": WORKLOADS["config5"]["name"], "total_problems": total, "distinct_problems": True, "chunk": chunk,
+                      "solver": "CONDENSED_ADMM (horizon 10) + AUTO (horizon 16)", "entry": "b200qp_mpc_sequence_solve_batch, pinned host buffers",
+                      "l2": "every chunk is new data: 26 MB in, 138 - 221 MB out per chunk (larger than L2)", "parallelism": f"shard{world}"}}
+    if rank == 0 and sample is not None:
+        from oracle import c_oracle, mpc_oracle as mo
+
+        params = dict(mo.GO2_PARAMS)
+        params["weights"] = params["w_move"]
+        N, rec, ct = sample
+        cores = os.cpu_count() or 1
+        t0 = time.perf_counter()
+        _, _, _, solved = c_oracle.solve_batch(N, rec, ct, params, threads=cores)
+        out["cpu_baseline"] = {"value": solved / (time.perf_counter() - t0), "unit": "solves/s", "cores": cores, "kind": "port",
+                               "sample": f"{rec.shape[0]} problems of the horizon-{N} half, C ADMM port"}
+    return out
+
+
+def extra_fp32(args, dev, rank, world):
+    """North star: "with the FP32 error stated separately".  The condensed kernel is run on rank 0's config-2 batch with every
+    stored intermediate rounded to binary32 (b200qp_mpc_config.precision): (1) FP32 K^-1 + ADMM iterations on FP64 problem data
+    with the polish in FP64, (2) FP32 everywhere (assembly, factor, iterations, polish).  Errors are against the FP64 path on the same problems; KKT by the C checker in FP64."""
+    if rank != 0:
+        return None
+    from dfki_quad_b200 import BatchedMPC, sequencer
+
+    wl = WORKLOADS["config2"]
+    N, B = wl["horizon"], wl["batch"]
+    cfg = sequencer.GO2_MPC
+    batch = sequencer.random_batch(B, N, seed=wl["seed"], gaits=wl["gaits"], device=dev)
+    out = {}
+    ref = None
+    for key, prec in (("fp64", 0), ("fp32_factor_and_admm_fp64_assembly_and_polish", 1), ("fp32_everywhere", 2)):
+        mpc = BatchedMPC(cfg["alpha"], cfg["state_weights_move"], cfg["mu"], cfg["fmin"], cfg["fmax"], "CONDENSED_ADMM", horizon=N,
+                         dt=cfg["dt"], max_batch=B, device=dev, precision=prec)
+        f, x, info = mpc.solve_records(batch["rec"], batch["contact"])
+        mpc.close()
+        if prec == 0:
+            ref = f
+            continue
+        ok = info.success
+        sc = np.maximum(1.0, np.abs(ref).reshape(B, -1).max(axis=1))
+        err = np.abs(f - ref).reshape(B, -1).max(axis=1) / sc
+        d = {"solved_fraction": float(ok.mean()), "mean_admm_iterations": float(info.acados_num_iter.mean()),
+             "mean_polish_rounds": float(info.polish_rounds.mean()),
+             "grf_rel_error_vs_fp64": {"median": float(np.median(err[ok])), "p99": float(np.percentile(err[ok], 99)), "max": float(err[ok].max())}}
+        if not args.no_cpu_baseline:
+            try:
+                from oracle import c_oracle, mpc_oracle as mo
+
+                params = dict(mo.GO2_PARAMS)
+                params["weights"] = params["w_move"]
+                kkt = c_oracle.kkt_batch(N, batch["rec"][ok], batch["contact"][ok], params, f[ok], x[ok])
+                d["kkt_fp64_checker"] = {"median": [float(v) for v in np.median(kkt, axis=0)], "max": [float(v) for v in kkt.max(axis=0)],
+                                         "order": "stationarity, dynamics, inequality, complementarity"}
+            except Exception as e:
+                d["kkt_fp64_checker"] = {"error": repr(e)}
+        out[key] = d
+    out["note"] = ("rounding study: the FP64 kernel with every stored intermediate rounded to binary32; no FP32 build is shipped - the "
+                   "reference computes in double and the 1e-5 GRF / 1e-6 KKT bar is an FP64 bar")
+    return out
 
 
 def run_b200_wbc(args):
@@ -620,6 +984,7 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     ap.add_argument("--no-closed-loop", action="store_true", help="skip the closed-loop hot-start extra")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the budgeted runs of the other BASELINE configs (config 3, 4, 5)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

@@ -29,7 +29,7 @@ class MpcConfig(C.Structure):
         ("admm_rho", C.c_double), ("admm_sigma", C.c_double), ("admm_alpha", C.c_double), ("admm_eps", C.c_double),
         ("kkt_tol", C.c_double),
         ("admm_max_iter", C.c_int32), ("admm_check_every", C.c_int32), ("polish_max_rounds", C.c_int32),
-        ("ipm_max_iter", C.c_int32), ("warm_start", C.c_int32), ("cond_N", C.c_int32),
+        ("ipm_max_iter", C.c_int32), ("warm_start", C.c_int32), ("cond_N", C.c_int32), ("precision", C.c_int32),
     ]
 
 
@@ -54,6 +54,8 @@ EXPORTS = [
     "b200qp_mpc_solve_batch", "b200qp_mpc_solve_batch_device", "b200qp_mpc_get_duals", "b200qp_mpc_get_condensed",
     "b200qp_mpc_last_timing", "b200qp_mpc_stream", "b200qp_mpc_set_model", "b200qp_mpc_sequence_batch",
     "b200qp_mpc_sequence_solve_batch", "b200qp_mpc_sequence_solve_batch_device", "b200qp_gait_schedule", "b200qp_gait_schedule_device",
+    "b200qp_mpc_create_sharded", "b200qp_mpc_destroy_sharded", "b200qp_mpc_solve_batch_sharded", "b200qp_mpc_sharded_handle",
+    "b200qp_mpc_sharded_devices", "b200qp_shard_range",
     "b200qp_wbc_create", "b200qp_wbc_destroy", "b200qp_wbc_solve_batch", "b200qp_wbc_solve_batch_device", "b200qp_wbc_stream",
 ]
 
@@ -94,6 +96,14 @@ def load() -> C.CDLL:
     lib.b200qp_mpc_sequence_solve_batch.argtypes = [vp, i32, vp, vp, vp, vp, vp]
     lib.b200qp_mpc_sequence_solve_batch_device.argtypes = [vp, i32, vp, vp, vp, vp, vp, i32]
     lib.b200qp_mpc_stream.restype = vp
+    lib.b200qp_mpc_create_sharded.argtypes = [p(MpcConfig), p(i32), i32, p(vp)]
+    lib.b200qp_mpc_destroy_sharded.argtypes = [vp]
+    lib.b200qp_mpc_destroy_sharded.restype = None
+    lib.b200qp_mpc_solve_batch_sharded.argtypes = [vp, i32, vp, vp, vp, vp, vp]
+    lib.b200qp_mpc_sharded_handle.argtypes = [vp, i32]
+    lib.b200qp_mpc_sharded_handle.restype = vp
+    lib.b200qp_mpc_sharded_devices.argtypes = [vp]
+    lib.b200qp_shard_range.argtypes = [i32, i32, i32, p(i32), p(i32)]
     lib.b200qp_gait_schedule.argtypes = [i32, i32, i32, dbl, vp, vp, vp, vp, vp, dbl, dbl, vp, vp, vp, vp]
     lib.b200qp_gait_schedule_device.argtypes = [i32, i32, dbl, vp, vp, vp, vp, vp, dbl, dbl, vp, vp, vp, vp, vp]
     lib.b200qp_wbc_create.argtypes = [p(WbcConfig), p(vp)]

@@ -5,6 +5,8 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <thread>
+#include <vector>
 
 #include "common.cuh"
 
@@ -140,6 +142,8 @@ static void fill_params(b200qp_mpc *h) {
   P.check_every = c.admm_check_every > 0 ? c.admm_check_every : 15;
   P.polish_rounds = c.polish_max_rounds > 0 ? c.polish_max_rounds : 8;
   P.ipm_max_iter = c.ipm_max_iter > 0 ? c.ipm_max_iter : 40;
+  P.precision = c.precision;
+  if (c.precision == 2 && !(c.kkt_tol > 0)) P.kkt_tol = 5e-2;  // FP32 polish: stationarity of O(1e-3) is all there is
 }
 
 extern "C" {
@@ -200,6 +204,10 @@ int32_t b200qp_mpc_create(const b200qp_mpc_config *cfg, b200qp_mpc **out) {
   if (cfg->horizon < 1 || cfg->horizon > B200QP_MAX_HORIZON || cfg->max_batch < 1 || !(cfg->dt > 0) ||
       !(cfg->alpha > 0) || !(cfg->mu >= 0) || !(cfg->fmax >= cfg->fmin)) {
     g_err = "b200qp_mpc_create: invalid configuration";
+    return B200QP_ERR_ARG;
+  }
+  if (cfg->precision < 0 || cfg->precision > 2 || (cfg->precision != 0 && cfg->solver != B200QP_SOLVER_CONDENSED_ADMM)) {
+    g_err = "b200qp_mpc_create: precision must be 0 (FP64); 1 / 2 (FP32 error study) need solver CONDENSED_ADMM";
     return B200QP_ERR_ARG;
   }
   if (cfg->solver != B200QP_SOLVER_CONDENSED_ADMM && cfg->solver != B200QP_SOLVER_SPARSE_RICCATI &&
@@ -616,6 +624,90 @@ int32_t b200qp_mpc_solve_batch(b200qp_mpc *h, int32_t n, const double *in, const
   h->stream_chunk = 0;
   CK(cudaStreamSynchronize(h->copy_stream));
   return rc;
+}
+
+// ---- one batch over several GPUs: independent slices, one host thread per GPU ------------------------------------------
+int32_t b200qp_shard_range(int32_t n, int32_t rank, int32_t world, int32_t *lo, int32_t *hi) {
+  if (n < 0 || world < 1 || rank < 0 || rank >= world || !lo || !hi) return B200QP_ERR_ARG;
+  const int64_t per = ((int64_t)n + world - 1) / world;  // contiguous slices of ceil(n / G); the last ones may be short or empty
+  int64_t a = per * rank, b = a + per;
+  if (a > n) a = n;
+  if (b > n) b = n;
+  *lo = (int32_t)a;
+  *hi = (int32_t)b;
+  return B200QP_OK;
+}
+}  // extern "C"
+struct b200qp_mpc_sharded {
+  std::vector<b200qp_mpc *> h;
+  int max_batch = 0;
+};
+extern "C" {
+int32_t b200qp_mpc_create_sharded(const b200qp_mpc_config *cfg, const int32_t *devices, int32_t n_devices, b200qp_mpc_sharded **out) {
+  if (!cfg || !devices || !out || n_devices < 1 || cfg->max_batch < 1) return B200QP_ERR_ARG;
+  *out = nullptr;
+  b200qp_mpc_sharded *s = new (std::nothrow) b200qp_mpc_sharded();
+  if (!s) return B200QP_ERR_ARG;
+  s->max_batch = cfg->max_batch;
+  int32_t lo = 0, hi = 0;
+  b200qp_shard_range(cfg->max_batch, 0, n_devices, &lo, &hi);
+  for (int g = 0; g < n_devices; ++g) {
+    b200qp_mpc_config c = *cfg;
+    c.device = devices[g];
+    c.max_batch = hi - lo > 0 ? hi - lo : 1;  // slice 0 is the largest
+    b200qp_mpc *hg = nullptr;
+    const int32_t rc = b200qp_mpc_create(&c, &hg);
+    if (rc != B200QP_OK) {
+      for (b200qp_mpc *p : s->h) b200qp_mpc_destroy(p);
+      delete s;
+      return rc;
+    }
+    s->h.push_back(hg);
+  }
+  *out = s;
+  return B200QP_OK;
+}
+void b200qp_mpc_destroy_sharded(b200qp_mpc_sharded *s) {
+  if (!s) return;
+  for (b200qp_mpc *p : s->h) b200qp_mpc_destroy(p);
+  delete s;
+}
+b200qp_mpc *b200qp_mpc_sharded_handle(b200qp_mpc_sharded *s, int32_t g) {
+  return (s && g >= 0 && g < (int32_t)s->h.size()) ? s->h[g] : nullptr;
+}
+int32_t b200qp_mpc_sharded_devices(const b200qp_mpc_sharded *s) { return s ? (int32_t)s->h.size() : 0; }
+
+int32_t b200qp_mpc_solve_batch_sharded(b200qp_mpc_sharded *s, int32_t n, const double *in, const uint8_t *contact, double *forces,
+                                       double *xpred, b200qp_solver_info *info) {
+  if (!s || n < 0 || n > s->max_batch || (n > 0 && (!in || !contact || !forces || !xpred || !info))) {
+    g_err = "b200qp_mpc_solve_batch_sharded: bad arguments";
+    return B200QP_ERR_ARG;
+  }
+  const int G = (int)s->h.size();
+  std::vector<int32_t> rc(G, B200QP_OK);
+  std::vector<std::string> err(G);
+  std::vector<std::thread> th;
+  th.reserve(G);
+  for (int g = 0; g < G; ++g) {
+    int32_t lo = 0, hi = 0;
+    b200qp_shard_range(n, g, G, &lo, &hi);
+    if (hi <= lo) continue;
+    b200qp_mpc *hg = s->h[g];
+    const int N = hg->cfg.horizon;
+    const size_t rec_d = (size_t)b200qp_mpc_in_doubles(N);
+    th.emplace_back([=, &rc, &err]() {  // one host thread per GPU: its own device context, stream and staging buffers
+      rc[g] = b200qp_mpc_solve_batch(hg, hi - lo, in + (size_t)lo * rec_d, contact + (size_t)lo * N * 4, forces + (size_t)lo * N * 12,
+                                     xpred + (size_t)lo * (N + 1) * 13, info + lo);
+      if (rc[g] != B200QP_OK) err[g] = b200qp_last_error();  // thread-local message of the worker
+    });
+  }
+  for (std::thread &t : th) t.join();
+  for (int g = 0; g < G; ++g)
+    if (rc[g] != B200QP_OK) {
+      g_err = "slice " + std::to_string(g) + ": " + err[g];
+      return rc[g];
+    }
+  return B200QP_OK;
 }
 
 int32_t b200qp_mpc_set_model(b200qp_mpc *h, const b200qp_seq_model *m) {

@@ -19,6 +19,7 @@ struct MpcParams {
   double dt, alpha, w[12], mu, fmin, fmax;
   double rho0, sigma, relax, eps, kkt_tol;
   int max_iter, check_every, polish_rounds, ipm_max_iter;
+  int precision;  // 0 FP64 (product); 1 / 2: FP32 error study of the condensed kernel (b200qp_mpc_config.precision)
 };
 
 struct MpcBuffers {

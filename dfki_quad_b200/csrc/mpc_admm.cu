@@ -38,6 +38,14 @@ namespace b200qp {
 // rows 3..6 are the reference's D rows 0..3 of that foot.
 constexpr double BIG = 1.0e300;
 
+// FP32 error study (b200qp_mpc_config.precision): every stored intermediate is rounded to binary32, so the data flow has the
+// rounding behaviour of an FP32 build of the same algorithm (storage and every operation result in FP32; the four-term FMA
+// chains accumulate in FP64 before their single rounding, i.e. marginally better than a pure FP32 chain).
+template <bool F32>
+__device__ __forceinline__ double rnd(double v) {
+  return F32 ? (double)(float)v : v;
+}
+
 __device__ __forceinline__ void foot_rows_eval(double fx, double fy, double fz, double mu, double (&ax)[7]) {
   ax[0] = fx;
   ax[1] = fy;
@@ -224,7 +232,7 @@ __device__ __noinline__ void nnls3(const double (*M)[3], int m, const double (&b
 // (the scalar sweep was bound by exactly that per-pivot latency).  The old pivot rows are staged in prow4[j][4]; the new
 // pivot rows are produced column-wise (thread j writes A[P, j]) so that no thread runs a long divergent branch.
 // The last n mod 4 pivots use the scalar step.
-template <int LD>
+template <int LD, bool F32 = false>
 __device__ __noinline__ void gj_invert(double *K, int n, double *prow4) {
   const int i = threadIdx.x;
   double *Ki = K + i;
@@ -270,6 +278,12 @@ __device__ __noinline__ void gj_invert(double *K, int n, double *prow4) {
       E[3][0] = -(j10 * t00 + j11 * t10); E[3][1] = -(j10 * t01 + j11 * t11);
       E[0][0] = i00 - (E[0][2] * t00 + E[0][3] * t10); E[0][1] = i01 - (E[0][2] * t01 + E[0][3] * t11);
       E[1][0] = i10 - (E[1][2] * t00 + E[1][3] * t10); E[1][1] = i11 - (E[1][2] * t01 + E[1][3] * t11);
+      if (F32) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+          for (int q2 = 0; q2 < 4; ++q2) E[q][q2] = rnd<F32>(E[q][q2]);
+      }
       const bool inP = (i >= p0) && (i < p0 + 4);
       // column duty: new pivot-row entries of column i
       {
@@ -278,15 +292,15 @@ __device__ __noinline__ void gj_invert(double *K, int n, double *prow4) {
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const double v = inP ? E[q][i - p0] : (E[q][0] * a.x + E[q][1] * a.y + E[q][2] * b.x + E[q][3] * b.y);
-          K[i * LD + p0 + q] = v;
+          K[i * LD + p0 + q] = rnd<F32>(v);
         }
       }
       if (!inP) {  // row duty
         const double c0 = Ki[p0 * LD], c1 = Ki[(p0 + 1) * LD], c2 = Ki[(p0 + 2) * LD], c3 = Ki[(p0 + 3) * LD];
-        const double w0 = c0 * E[0][0] + c1 * E[1][0] + c2 * E[2][0] + c3 * E[3][0];
-        const double w1 = c0 * E[0][1] + c1 * E[1][1] + c2 * E[2][1] + c3 * E[3][1];
-        const double w2 = c0 * E[0][2] + c1 * E[1][2] + c2 * E[2][2] + c3 * E[3][2];
-        const double w3 = c0 * E[0][3] + c1 * E[1][3] + c2 * E[2][3] + c3 * E[3][3];
+        const double w0 = rnd<F32>(c0 * E[0][0] + c1 * E[1][0] + c2 * E[2][0] + c3 * E[3][0]);
+        const double w1 = rnd<F32>(c0 * E[0][1] + c1 * E[1][1] + c2 * E[2][1] + c3 * E[3][1]);
+        const double w2 = rnd<F32>(c0 * E[0][2] + c1 * E[1][2] + c2 * E[2][2] + c3 * E[3][2]);
+        const double w3 = rnd<F32>(c0 * E[0][3] + c1 * E[1][3] + c2 * E[2][3] + c3 * E[3][3]);
         int j = 0;
         for (; j + 3 < n; j += 4) {  // 4 elements per trip: 8 broadcast LDS.128 + 4 LDS in flight, two half-sums per element
           double2 pa[4], pb[4];
@@ -299,12 +313,12 @@ __device__ __noinline__ void gj_invert(double *K, int n, double *prow4) {
           }
 #pragma unroll
           for (int u = 0; u < 4; ++u)  // four independent chains of four FMAs
-            Ki[(j + u) * LD] = fma(-w3, pb[u].y, fma(-w2, pb[u].x, fma(-w1, pa[u].y, fma(-w0, pa[u].x, kk[u]))));
+            Ki[(j + u) * LD] = rnd<F32>(fma(-w3, pb[u].y, fma(-w2, pb[u].x, fma(-w1, pa[u].y, fma(-w0, pa[u].x, kk[u])))));
         }
         for (; j < n; ++j) {
           const double2 a0 = *reinterpret_cast<const double2 *>(prow4 + 4 * j);
           const double2 b0 = *reinterpret_cast<const double2 *>(prow4 + 4 * j + 2);
-          Ki[j * LD] = fma(-w3, b0.y, fma(-w2, b0.x, fma(-w1, a0.y, fma(-w0, a0.x, Ki[j * LD]))));
+          Ki[j * LD] = rnd<F32>(fma(-w3, b0.y, fma(-w2, b0.x, fma(-w1, a0.y, fma(-w0, a0.x, Ki[j * LD])))));
         }
         Ki[p0 * LD] = -w0;
         Ki[(p0 + 1) * LD] = -w1;
@@ -323,13 +337,13 @@ __device__ __noinline__ void gj_invert(double *K, int n, double *prow4) {
     }
     __syncthreads();
     if (i < n) {
-      const double d = 1.0 / prow[p];
+      const double d = rnd<F32>(1.0 / prow[p]);
       if (i != p) {
-        const double f = Ki[p * LD] * d;
-        for (int j = 0; j < n; ++j) Ki[j * LD] = fma(-f, prow[j], Ki[j * LD]);
+        const double f = rnd<F32>(Ki[p * LD] * d);
+        for (int j = 0; j < n; ++j) Ki[j * LD] = rnd<F32>(fma(-f, prow[j], Ki[j * LD]));
         Ki[p * LD] = -f;
       }
-      K[i * LD + p] = (i == p) ? d : pi * d;  // rescaled pivot row, element (p, i)
+      K[i * LD + p] = (i == p) ? d : rnd<F32>(pi * d);  // rescaled pivot row, element (p, i)
     }
     __syncthreads();
   }
@@ -721,8 +735,11 @@ __device__ __forceinline__ void horizon_sums(int N, int j, int l, double &cnt, d
 
 // ---------------------------------------------------------------------------------------------------------------
 // BS = threads per block (multiple of 32), NV = largest reduced problem the instantiation accepts (even, <= BS)
-template <int BS, int NV>
+// PREC: 0 = FP64 (the product); 1 = FP32 K^-1 and ADMM iterations on FP64 problem data, FP64 polish ("FP32 factor + FP64
+// refinement"); 2 = FP32 everywhere including the assembly, the polish and the outputs (error measurement only: b200qp_mpc_config.precision)
+template <int BS, int NV, int PREC = 0>
 __global__ void __launch_bounds__(BS, (BS == 64 && !B200QP_TC_GJ) ? 6 : 1) mpc_admm_kernel(const MpcParams P, const MpcBuffers B) {
+  constexpr bool R1 = PREC >= 1, R2 = PREC >= 2;
   constexpr int LD = NV + 1;
   constexpr int MAXF = NV / 3 + 1;
   extern __shared__ __align__(16) double smem[];
@@ -1017,10 +1034,11 @@ __global__ void __launch_bounds__(BS, (BS == 64 && !B200QP_TC_GJ) ? 6 : 1) mpc_a
         for (int cc = 0; cc < 3; ++cc) h[cc] = v0 * Bwb[cc] + v1 * Bwb[3 + cc] + v2 * Bwb[6 + cc];
         h[ca] += cnt * lv + S2 * lp;
         if (b == fa) h[ca] += P.alpha;
-        for (int cc = 0; cc < 3; ++cc) Hs[(3 * b + cc) * BS + tid] = h[cc];
+        for (int cc = 0; cc < 3; ++cc) Hs[(3 * b + cc) * BS + tid] = rnd<R2>(h[cc]);
       }
       gi = Bwa[ca] * s_lw[3 * (j + 1)] + Bwa[3 + ca] * s_lw[3 * (j + 1) + 1] + Bwa[6 + ca] * s_lw[3 * (j + 1) + 2] +
            dm * s_lv[3 * (j + 1) + ca];
+      gi = rnd<R2>(gi);
       s_g[tid] = gi;
     }
     for (int e = tid; e < N * 36; e += BS) Bw_park[e] = s_Bw[e];
@@ -1094,13 +1112,13 @@ __global__ void __launch_bounds__(BS, (BS == 64 && !B200QP_TC_GJ) ? 6 : 1) mpc_a
 #pragma unroll
                 for (int u = 0; u < 8; ++u) h[u] = __ldcg(Hs + (size_t)(jx + u) * BS + tid);
 #pragma unroll
-                for (int u = 0; u < 8; ++u) K[(jx + u) * LD + tid] = h[u];
+                for (int u = 0; u < 8; ++u) K[(jx + u) * LD + tid] = rnd<R1>(h[u]);
               }
-              for (; jx < n; ++jx) K[jx * LD + tid] = __ldcg(Hs + (size_t)jx * BS + tid);
-              K[tid * LD + tid] += sigma + rho * Ei;
+              for (; jx < n; ++jx) K[jx * LD + tid] = rnd<R1>(__ldcg(Hs + (size_t)jx * BS + tid));
+              K[tid * LD + tid] = rnd<R1>(K[tid * LD + tid] + (sigma + rho * Ei));
             }
             __syncthreads();
-            gj_invert<LD>(K, n, prow);
+            gj_invert<LD, R1>(K, n, prow);
           }
           need_factor = false;
           PH(2);
@@ -1114,24 +1132,24 @@ __global__ void __launch_bounds__(BS, (BS == 64 && !B200QP_TC_GJ) ? 6 : 1) mpc_a
             double w[7];
 #pragma unroll
             for (int r = 0; r < 7; ++r) w[r] = rho * z[r] - y[r];
-            s_v[tid] = sigma * x - gi + foot_at(ca, w, mu);
+            s_v[tid] = rnd<R1>(sigma * x - gi + foot_at(ca, w, mu));
           }
           __syncthreads();
           double xt = 0.0;
           if (act) {
-            xt = matvec_smem<LD>(K, n, s_v);
+            xt = rnd<R1>(matvec_smem<LD>(K, n, s_v));
             s_xt[tid] = xt;
           }
           __syncthreads();
           if (act) {
             double zt[7];
             foot_rows_eval(s_xt[3 * fa], s_xt[3 * fa + 1], s_xt[3 * fa + 2], mu, zt);
-            x = relax * xt + (1.0 - relax) * x;
+            x = rnd<R1>(relax * xt + (1.0 - relax) * x);
 #pragma unroll
             for (int r = 0; r < 7; ++r) {
-              const double zr = relax * zt[r] + (1.0 - relax) * z[r];
-              const double zn = fmin(fmax(zr + y[r] * rinv, lo[r]), hi[r]);
-              y[r] += rho * (zr - zn);
+              const double zr = rnd<R1>(relax * zt[r] + (1.0 - relax) * z[r]);
+              const double zn = rnd<R1>(fmin(fmax(zr + y[r] * rinv, lo[r]), hi[r]));
+              y[r] = rnd<R1>(y[r] + rho * (zr - zn));
               z[r] = zn;
             }
           }
@@ -1251,7 +1269,7 @@ __global__ void __launch_bounds__(BS, (BS == 64 && !B200QP_TC_GJ) ? 6 : 1) mpc_a
             const int q0 = s_foff[bq];
             for (int kq = 0; kq < nzb; ++kq) {
               const double *vq = s_fZ + 9 * bq + 3 * kq;
-              K[(q0 + kq) * LD + tid] = vq[0] * u0 + vq[1] * u1 + vq[2] * u2;
+              K[(q0 + kq) * LD + tid] = rnd<R2>(vq[0] * u0 + vq[1] * u1 + vq[2] * u2);
             }
           }
         }
@@ -1273,11 +1291,11 @@ __global__ void __launch_bounds__(BS, (BS == 64 && !B200QP_TC_GJ) ? 6 : 1) mpc_a
           PH(7);
           wred = chol_solve<LD>(K, nr, -grp, red);
         } else {
-          gj_invert<LD>(K, nr, prow);
+          gj_invert<LD, R2>(K, nr, prow);
           PH(7);
-          if (tid < nr) s_v[tid] = -grp;
+          if (tid < nr) s_v[tid] = rnd<R2>(-grp);
           __syncthreads();
-          if (tid < nr) wred = matvec_smem<LD>(K, nr, s_v);
+          if (tid < nr) wred = rnd<R2>(matvec_smem<LD>(K, nr, s_v));
         }
         double xn = 0.0;
 #pragma unroll 1
@@ -1289,17 +1307,18 @@ __global__ void __launch_bounds__(BS, (BS == 64 && !B200QP_TC_GJ) ? 6 : 1) mpc_a
             xn = s_c[tid];
             const int o = s_foff[fa];
             for (int q = 0; q < s_fnz[fa]; ++q) xn += s_fZ[9 * fa + 3 * q + ca] * s_w[o + q];
+            xn = rnd<R2>(xn);
             s_xt[tid] = xn;
           }
           __syncthreads();
-          if (act) s_r[tid] = matvec_glob<BS>(Hs, n, s_xt) + gi;  // r = H x + g
+          if (act) s_r[tid] = rnd<R2>(matvec_glob<BS>(Hs, n, s_xt) + gi);  // r = H x + g
           __syncthreads();
           if (refine == 0) {  // one step of iterative refinement on the reduced system
             const double rr = (tid < nr) ? -(vp[0] * s_r[3 * ap] + vp[1] * s_r[3 * ap + 1] + vp[2] * s_r[3 * ap + 2]) : 0.0;
             if constexpr (TC || !B200QP_CHOL_POLISH) {
-              if (tid < nr) s_v[tid] = rr;
+              if (tid < nr) s_v[tid] = rnd<R2>(rr);
               __syncthreads();
-              if (tid < nr) wred += matvec_smem<LD>(K, nr, s_v);
+              if (tid < nr) wred = rnd<R2>(wred + matvec_smem<LD>(K, nr, s_v));
             } else {
               wred += chol_solve<LD>(K, nr, rr, red);
             }
@@ -1575,12 +1594,12 @@ static size_t admm_smem_bytes() {
   return sizeof(double) * ((size_t)NV * (NV + 1) + 6 * BS + 4 * 32);
 }
 
-template <int BS, int NV>
+template <int BS, int NV, int PREC = 0>
 static cudaError_t launch_one(const MpcParams &P, MpcBuffers B, int grid, cudaStream_t st) {
   const size_t sm = admm_smem_bytes<BS, NV>();
-  cudaError_t e = cudaFuncSetAttribute(mpc_admm_kernel<BS, NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+  cudaError_t e = cudaFuncSetAttribute(mpc_admm_kernel<BS, NV, PREC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
   if (e != cudaSuccess) return e;
-  mpc_admm_kernel<BS, NV><<<grid, BS, sm, st>>>(P, B);
+  mpc_admm_kernel<BS, NV, PREC><<<grid, BS, sm, st>>>(P, B);
   return cudaGetLastError();
 }
 
@@ -1610,6 +1629,13 @@ cudaError_t launch_mpc_bin(int n, int N, const uint8_t *contact, int *bin_count,
 }
 
 cudaError_t launch_mpc_admm(int bin, const MpcParams &P, const MpcBuffers &B, int grid, cudaStream_t st) {
+  if (P.precision == 1) {  // FP32 error study (trot-sized and mid-sized bins only)
+    if (bin == 0) return launch_one<64, 60, 1>(P, B, grid, st);
+    if (bin == 1) return launch_one<96, 96, 1>(P, B, grid, st);
+  } else if (P.precision == 2) {
+    if (bin == 0) return launch_one<64, 60, 2>(P, B, grid, st);
+    if (bin == 1) return launch_one<96, 96, 2>(P, B, grid, st);
+  }
   if (bin == 0) return launch_one<64, 60>(P, B, grid, st);
   if (bin == 1) return launch_one<96, 96>(P, B, grid, st);
   if (bin == 2) return launch_one<128, 128>(P, B, grid, st);

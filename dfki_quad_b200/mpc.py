@@ -298,3 +298,54 @@ class BatchedMPC:
         return SolverInformation(success=arr["status"] == 0, return_code=arr["status"], acados_num_iter=arr["iterations"],
                                  polish_rounds=arr["polish_rounds"], n_free=arr["n_free"], kkt=arr["kkt"],
                                  total_solver_time=ms * 1e-3, kernel_launches=nl)
+
+
+class ShardedMPC:
+    """One batch over several GPUs of one box through ONE library call (b200qp_mpc_create_sharded /
+    b200qp_mpc_solve_batch_sharded): contiguous slices, one host thread + stream + staging per GPU, no
+    collective.  Constructor arguments as BatchedMPC plus `devices`; `max_batch` is the size of the whole batch."""
+
+    def __init__(self, alpha, state_weights, mu, fmin, fmax, solver="CONDENSED_ADMM", condensing_N=None, warm_start=0, *,
+                 devices=(0,), horizon=10, dt=0.05, max_batch=4096, **opts):
+        self._lib = _lib.load()
+        cfg = _lib.MpcConfig()
+        cfg.horizon, cfg.solver, cfg.max_batch, cfg.device = int(horizon), _lib.SOLVERS[solver], int(max_batch), 0
+        cfg.dt, cfg.alpha, cfg.mu, cfg.fmin, cfg.fmax = float(dt), float(alpha), float(mu), float(fmin), float(fmax)
+        sw = np.asarray(state_weights, dtype=np.float64).reshape(12)
+        for i in range(12):
+            cfg.state_weights[i] = sw[i]
+        cfg.cond_N = int(condensing_N) if condensing_N else 0
+        cfg.warm_start = int(warm_start)
+        for k, v in opts.items():
+            setattr(cfg, k, v)
+        self.N, self.max_batch, self.devices = int(horizon), int(max_batch), tuple(int(d) for d in devices)
+        devs = (C.c_int32 * len(self.devices))(*self.devices)
+        self._h = C.c_void_p()
+        _lib.check(self._lib.b200qp_mpc_create_sharded(C.byref(cfg), devs, len(self.devices), C.byref(self._h)), "b200qp_mpc_create_sharded")
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._lib.b200qp_mpc_destroy_sharded(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def solve_records(self, rec, contact, forces=None, xpred=None):
+        rec = np.ascontiguousarray(rec, dtype=np.float64)
+        contact = np.ascontiguousarray(contact, dtype=np.uint8)
+        n = rec.shape[0]
+        if rec.shape != (n, in_doubles(self.N)) or contact.shape != (n, self.N, 4):
+            raise ValueError("record / contact shape mismatch")
+        forces = np.zeros((n, self.N, 12)) if forces is None else forces
+        xpred = np.zeros((n, self.N + 1, 13)) if xpred is None else xpred
+        info = (_lib.SolverInfo * max(n, 1))()
+        rc = self._lib.b200qp_mpc_solve_batch_sharded(self._h, n, rec.ctypes.data, contact.ctypes.data, forces.ctypes.data,
+                                                      xpred.ctypes.data, C.addressof(info))
+        _lib.check(rc, "b200qp_mpc_solve_batch_sharded")
+        arr = np.frombuffer(info, dtype=np.dtype([("status", "i4"), ("iterations", "i4"), ("polish_rounds", "i4"), ("n_free", "i4"),
+                                                  ("kkt", "f8", (4,))]), count=n).copy()
+        return forces, xpred, arr

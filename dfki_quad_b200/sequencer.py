@@ -216,6 +216,30 @@ def random_batch(n, horizon, seed, gaits=("TROT",), dt=0.05, device=0, schedule_
                 traj=traj, foot_pos=fp, swing_time=swing, seq_in=seq_in)
 
 
+def random_seq_inputs(n, seed, gaits=("TROT",)):
+    """The same synthetic state / command / gait distribution as random_batch, as sequencer inputs only ([n, 50], the 400 B
+    per robot that b200qp_mpc_sequence_solve_batch takes): no host-side planning, cheap enough for million-problem sweeps."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    roll = rng.uniform(-0.2, 0.2, n)
+    pitch = rng.uniform(-0.2, 0.2, n)
+    yaw = rng.uniform(-np.pi, np.pi, n)
+    quat = euler_to_quaternion(np.stack([roll, pitch, yaw], axis=-1))
+    pos = np.stack([rng.uniform(-1, 1, n), rng.uniform(-1, 1, n), 0.30 + rng.uniform(-0.03, 0.03, n)], axis=-1)
+    omega = rng.uniform(-0.5, 0.5, (n, 3))
+    vel = np.stack([rng.uniform(-0.6, 0.6, n), rng.uniform(-0.6, 0.6, n), rng.uniform(-0.1, 0.1, n)], axis=-1)
+    target = dict(hybrid_x_dot=rng.uniform(-0.5, 0.5, n), hybrid_y_dot=rng.uniform(-0.5, 0.5, n),
+                  wz=rng.uniform(-0.7, 0.7, n), wx=np.zeros(n), wy=np.zeros(n), roll=np.zeros(n), pitch=np.zeros(n),
+                  z=np.full(n, 0.30))
+    phase = rng.uniform(0.0, 1.0, n)
+    gait_ids = np.array([gaitmod.GAIT_NAMES.index(g) for g in gaits])[rng.integers(0, len(gaits), n)]
+    period, duty, offset = gaitmod.gait_arrays(gait_ids)
+    Ryaw = quat_to_rot(_yaw_quat(yaw))
+    feet = pos[:, None, :] + np.einsum("nij,lj->nli", Ryaw, GO2_SHOULDERS)
+    feet[:, :, 0:2] += rng.uniform(-0.05, 0.05, (n, 4, 2))
+    feet[:, :, 2] = 0.0
+    return pack_sequencer_inputs(quat, pos, omega, vel, feet, vel, np.zeros((n, 4)), target, phase, period, duty, offset)
+
+
 SEQ_IN_DOUBLES = 50  # B200QP_SEQ_IN_DOUBLES
 TARGET_FIELDS = ("hybrid_x_dot", "hybrid_y_dot", "wz", "wx", "wy", "roll", "pitch", "z")
 

@@ -85,6 +85,11 @@ typedef struct b200qp_mpc_config {
                               /* `condensing_N` constructor argument (mpc.hpp:125, mpc.cpp:219-225; HPIPM block sizes: N / cond_N,  */
                               /* the first N mod cond_N blocks one longer).  0 => library default (blocks of 4 stages).  Every      */
                               /* value gives the same optimum; blocks with more than 128 stacked stance inputs are split.           */
+  int32_t precision;          /* condensed kernel only.  0: FP64 throughout (the product; the reference computes in double).        */
+                              /* 1, 2: FP32 ERROR STUDY (north star: "with the FP32 error stated separately") - every stored          */
+                              /* intermediate of (1) K^-1 and the ADMM iterations, with assembly and polish still in FP64 ("FP32       */
+                              /* factor + FP64 refinement"), or (2) of everything incl. assembly and polish, is rounded to binary32.  */
+                              /* With 2 and kkt_tol == 0 the acceptance tolerance is 5e-2 (an FP32 polish cannot reach 1e-7).         */
 } b200qp_mpc_config;
 
 /* Input record of one problem = the subset of {StateInterface, ModelInterface, GaitSequence} that
@@ -153,6 +158,24 @@ int32_t b200qp_mpc_get_condensed(b200qp_mpc *h, int32_t index, double *H, int32_
 int32_t b200qp_mpc_last_timing(b200qp_mpc *h, float *kernel_ms, int32_t *kernel_launches);
 /* CUDA stream of the handle as a void* (cudaStream_t), for callers that time with their own events. */
 void *b200qp_mpc_stream(b200qp_mpc *h);
+
+/* ---- one batch, several GPUs ----------------------------------------------------------------
+ * The problems of ONE host array are cut into contiguous slices of ceil(n / G) problems, slice g goes to devices[g]; every
+ * GPU has its own handle, stream, pinned staging buffers and host thread, results land in disjoint ranges of the caller's
+ * output arrays; there is no collective and no inter-GPU traffic on the solve path.  cfg->max_batch is the size of the
+ * whole batch, cfg->device is ignored.  Page-locked caller buffers (cudaHostAlloc / cudaHostRegister with the portable
+ * flag, torch pin_memory) are used in place by all GPUs. */
+typedef struct b200qp_mpc_sharded b200qp_mpc_sharded;
+int32_t b200qp_mpc_create_sharded(const b200qp_mpc_config *cfg, const int32_t *devices, int32_t n_devices, b200qp_mpc_sharded **out);
+void b200qp_mpc_destroy_sharded(b200qp_mpc_sharded *h);
+/* arguments as b200qp_mpc_solve_batch */
+int32_t b200qp_mpc_solve_batch_sharded(b200qp_mpc_sharded *h, int32_t n, const double *in, const uint8_t *contact, double *forces,
+                                       double *xpred, b200qp_solver_info *info);
+/* the per-GPU handle of slice g (for the setters: b200qp_mpc_set_state_weights etc. are applied per handle), or NULL */
+b200qp_mpc *b200qp_mpc_sharded_handle(b200qp_mpc_sharded *h, int32_t g);
+int32_t b200qp_mpc_sharded_devices(const b200qp_mpc_sharded *h);
+/* the slicing rule itself (pure arithmetic, no CUDA): problems [*lo, *hi) of n belong to slice `rank` of `world` */
+int32_t b200qp_shard_range(int32_t n, int32_t rank, int32_t world, int32_t *lo, int32_t *hi);
 
 /* ---- on-device gait sequencer -----------------------------------------------------
  * Replaces, for n robots at once, the caller side of MPC::UpdateGaitSequence: one SimpleGaitSequencer pass

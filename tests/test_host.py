@@ -43,7 +43,7 @@ def test_struct_layout_matches_header():
     from dfki_quad_b200 import _lib
 
     assert ctypes.sizeof(_lib.SolverInfo) == 48
-    assert ctypes.sizeof(_lib.MpcConfig) == 16 + 8 * (2 + 12 + 3 + 5) + 24  # 6 trailing int32 (incl. warm_start, cond_N)
+    assert ctypes.sizeof(_lib.MpcConfig) == 16 + 8 * (2 + 12 + 3 + 5) + 32  # 7 trailing int32 (incl. warm_start, cond_N, precision) + padding
 
 
 def test_no_gpu_fails_loudly():
@@ -319,3 +319,23 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"]
     assert line["cpu_baseline"]["kind"] in ("port", "reference") and line["cpu_baseline"]["cores"] >= 1
     assert "workload" in line["config"]
+
+
+def test_shard_range_of_the_c_abi_equals_the_python_rule():
+    """b200qp_shard_range (pure arithmetic, no CUDA) - the slicing rule of b200qp_mpc_solve_batch_sharded - equals
+    dfki_quad_b200.shard.shard_range, covers [0, n) exactly once and keeps slices contiguous."""
+    from dfki_quad_b200 import _lib
+    from dfki_quad_b200.shard import shard_range
+
+    lib = _lib.load()
+    lo, hi = ctypes.c_int32(), ctypes.c_int32()
+    for n in (0, 1, 7, 8, 9, 4096, 1048576, 1048577, 2**31 - 1):
+        for world in (1, 2, 3, 4, 8):
+            prev = 0
+            for rank in range(world):
+                assert lib.b200qp_shard_range(n, rank, world, ctypes.byref(lo), ctypes.byref(hi)) == 0
+                assert (lo.value, hi.value) == shard_range(n, rank, world)
+                assert lo.value == prev and hi.value >= lo.value
+                prev = hi.value
+            assert prev == n
+    assert lib.b200qp_shard_range(10, 2, 2, ctypes.byref(lo), ctypes.byref(hi)) == _lib.ERR_ARG
