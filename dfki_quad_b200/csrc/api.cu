@@ -30,6 +30,11 @@ cudaError_t launch_mpc_pcond(const MpcParams &P, int n, const double *in, const 
                              b200qp_solver_info *info, double *lam_box, double *lam_g, double *scratch, int *next, int grid,
                              cudaStream_t st, const int *list, const int *list_count, int condN, int nub_limit, long long *dbg);
 int pcond_grid(int num_sms, int N, int condN, int nub_limit);
+cudaError_t launch_mpc_pcw(const MpcParams &P, int n, const double *in, const uint8_t *contact, double *forces, double *xpred,
+                           b200qp_solver_info *info, double *lam_box, double *lam_g, double *scratch, int *next, int grid, cudaStream_t st,
+                           const int *list, const int *list_count, int *rej, int *rej_count, int condN, int fs, long long *dbg);
+int pcw_grid(int num_sms, int N, int fs, int condN);
+size_t pcw_scratch_doubles(int N, int fs);
 size_t pcond_scratch_doubles(int N);
 struct SeqModel {
   double mass, inertia[9], com[3], shoulders[12], raibert_k, raibert_g, max_leg_length, dt;
@@ -92,6 +97,12 @@ struct b200qp_mpc {
   int ric_grid = 0;
   double *d_pc_scratch = nullptr;  // partial-condensing kernel: block constants (+ factors that do not fit shared memory)
   int pc_grid = 0, pc_cond = 0, pc_nub = 0;
+  // warp-per-problem Riccati kernel (solver SPARSE_RICCATI): one launch for problems with <= 32 stance foot-stages, one for <= 64,
+  // the block kernel for the rest
+  double *d_pcw_scratch[2] = {nullptr, nullptr};
+  int pcw_grid[2] = {0, 0}, pcw_cond = 0;
+  int *d_pcw_rej = nullptr;  // [2][max_batch] hand-over lists
+  bool ric_legacy = false;   // B200QP_RICCATI_LEGACY=1: block kernel only (A/B runs)
   // pinned staging
   double *h_in = nullptr, *h_forces = nullptr, *h_xpred = nullptr;
   uint8_t *h_contact = nullptr;
@@ -282,6 +293,20 @@ int32_t b200qp_mpc_create(const b200qp_mpc_config *cfg, b200qp_mpc **out) {
       CK(cudaMalloc(&h->d_hscratch[b], (size_t)g * ((size_t)bs * bs + B200QP_MAX_HORIZON * 36) * sizeof(double)));
     }
   }
+  if (cfg->solver == B200QP_SOLVER_SPARSE_RICCATI) {
+    h->ric_legacy = getenv("B200QP_RICCATI_LEGACY") != nullptr;
+    // blocks of the warp-per-problem kernel: cond_N as given (cond_N = horizon: one stage per block, the sparse formulation proper);
+    // default: two stages per block - same Newton direction, fewer and better filled block factorisations
+    h->pcw_cond = (cfg->cond_N > 0 && cfg->cond_N <= cfg->horizon) ? cfg->cond_N : (cfg->horizon + 1) / 2;
+    for (int v = 0; v < 1 && !h->ric_legacy; ++v) {  // the two-foot-stages-per-lane instantiation is slower than the block kernel: not used
+      int g = pcw_grid(h->num_sms, cfg->horizon, v + 1, h->pcw_cond);
+      if (const char *e = getenv("B200QP_BLOCKS_PER_SM")) g = h->num_sms * (atoi(e) > 0 ? atoi(e) : 1);
+      if ((size_t)g > nb) g = (int)nb;
+      h->pcw_grid[v] = g;
+      CK(cudaMalloc(&h->d_pcw_scratch[v], (size_t)g * pcw_scratch_doubles(cfg->horizon, v + 1) * sizeof(double)));
+    }
+    CK(cudaMalloc(&h->d_pcw_rej, 2 * nb * sizeof(int)));
+  }
   if (cfg->solver == B200QP_SOLVER_SPARSE_RICCATI || cfg->solver == B200QP_SOLVER_AUTO) {
     int g = riccati_grid(h->num_sms, cfg->horizon);
     if ((size_t)g > nb) g = (int)nb;
@@ -330,6 +355,9 @@ void b200qp_mpc_destroy(b200qp_mpc *h) {
   for (int b = 0; b < 4; ++b) cudaFree(h->d_hscratch[b]);
   cudaFree(h->d_ric_scratch);
   cudaFree(h->d_pc_scratch);
+  cudaFree(h->d_pcw_scratch[0]);
+  cudaFree(h->d_pcw_scratch[1]);
+  cudaFree(h->d_pcw_rej);
   cudaFreeHost(h->h_in);
   cudaFreeHost(h->h_contact);
   cudaFreeHost(h->h_forces);
@@ -464,7 +492,18 @@ static int32_t solve_device_impl(b200qp_mpc *h, int32_t n, const double *d_in, c
       ++launches;
     }
   }
-  if (h->cfg.solver == B200QP_SOLVER_SPARSE_RICCATI || autosel) {  // whole batch, or (AUTO) the problems too large for the condensed kernel
+  if (h->cfg.solver == B200QP_SOLVER_SPARSE_RICCATI && !h->ric_legacy) {
+    // warp-per-problem kernel: <= 32 stance foot-stages first, what does not fit is handed on to the two-per-lane instantiation and
+    // from there to the block kernel (d_bin_count[12], [13] = lengths of the hand-over lists, [14], [15], [9] = work counters)
+    double *lb = h->want_duals ? h->d_lam_box : nullptr, *lg = h->want_duals ? h->d_lam_g : nullptr;
+    int *rej0 = h->d_pcw_rej, *rej1 = h->d_pcw_rej + n;
+    CK(launch_mpc_pcw(h->P, n, d_in, d_contact, d_forces, d_xpred, d_info, lb, lg, h->d_pcw_scratch[0], h->d_bin_count + 14, h->pcw_grid[0],
+                      h->stream, nullptr, nullptr, rej0, h->d_bin_count + 12, h->pcw_cond, 1, h->d_dbg_cycles));
+    (void)rej1;
+    CK(launch_mpc_riccati(h->P, n, d_in, d_contact, d_forces, d_xpred, d_info, lb, lg, h->d_ric_scratch, h->d_bin_count + 9, h->ric_grid,
+                          h->stream, nullptr, rej0, h->d_bin_count + 12));
+    launches += 2;
+  } else if (h->cfg.solver == B200QP_SOLVER_SPARSE_RICCATI || autosel) {  // whole batch, or (AUTO) the problems too large for the condensed kernel
     cudaStream_t st = h->stream;
     if (autosel) {
       st = h->bin_stream[3];

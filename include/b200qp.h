@@ -46,7 +46,9 @@ extern "C" {
 
 /* solver selection, named after the reference's acados plans (mit_controller_node.cpp:502-519) */
 #define B200QP_SOLVER_CONDENSED_ADMM 0 /* replaces PARTIAL_CONDENSING_OSQP with small cond_N / FULL_CONDENSING_* */
-#define B200QP_SOLVER_SPARSE_RICCATI 1 /* replaces PARTIAL_CONDENSING_HPIPM with cond_N == N                     */
+#define B200QP_SOLVER_SPARSE_RICCATI 1 /* replaces PARTIAL_CONDENSING_HPIPM near the sparse end: Riccati interior-point     */
+                                       /* method, one warp per problem; cond_N = N is the sparse formulation proper, the   */
+                                       /* default (cond_N = 0) condenses pairs of stages; blocks are capped at 12 inputs   */
 #define B200QP_SOLVER_PARTIAL_CONDENSING 3 /* replaces PARTIAL_CONDENSING_HPIPM for ANY cond_N in 1..N (mpc.cpp:219-225):  */
                                        /* block-condensed Riccati interior-point kernel, b200qp_mpc_config.cond_N blocks;  */
                                        /* cond_N = N is the sparse formulation, cond_N = 1 the fully condensed one          */
