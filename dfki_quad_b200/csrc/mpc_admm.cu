@@ -257,7 +257,7 @@ __device__ __noinline__ void gj_invert(double *K, int n, double *prow4) {
         const double2 b = *reinterpret_cast<const double2 *>(prow4 + 4 * (p0 + c) + 2);
         D[0][c] = a.x; D[1][c] = a.y; D[2][c] = b.x; D[3][c] = b.y;
       }
-      const double r1 = 1.0 / (D[0][0] * D[1][1] - D[0][1] * D[1][0]);
+      const double r1 = fast_rcp(D[0][0] * D[1][1] - D[0][1] * D[1][0]);
       const double i00 = D[1][1] * r1, i01 = -D[0][1] * r1, i10 = -D[1][0] * r1, i11 = D[0][0] * r1;  // A11^-1
       // T = A21 A11^-1
       const double t00 = D[2][0] * i00 + D[2][1] * i10, t01 = D[2][0] * i01 + D[2][1] * i11;
@@ -265,7 +265,7 @@ __device__ __noinline__ void gj_invert(double *K, int n, double *prow4) {
       // S = A22 - T A12
       const double s00 = D[2][2] - (t00 * D[0][2] + t01 * D[1][2]), s01 = D[2][3] - (t00 * D[0][3] + t01 * D[1][3]);
       const double s10 = D[3][2] - (t10 * D[0][2] + t11 * D[1][2]), s11 = D[3][3] - (t10 * D[0][3] + t11 * D[1][3]);
-      const double r2 = 1.0 / (s00 * s11 - s01 * s10);
+      const double r2 = fast_rcp(s00 * s11 - s01 * s10);
       const double j00 = s11 * r2, j01 = -s01 * r2, j10 = -s10 * r2, j11 = s00 * r2;  // S^-1
       // U = A11^-1 A12 ; E12 = -U S^-1 ; E21 = -S^-1 T ; E11 = A11^-1 + U S^-1 T
       const double u00 = i00 * D[0][2] + i01 * D[1][2], u01 = i00 * D[0][3] + i01 * D[1][3];
