@@ -43,6 +43,17 @@ class WbcConfig(C.Structure):
                 ("max_iter", C.c_int32), ("kkt_tol", C.c_double)]
 
 
+class SeqOptions(C.Structure):
+    _fields_ = [("mode", C.c_int32), ("raibert_filtersize", C.c_int32), ("fix_standing_position", C.c_int32),
+                ("early_contact_detection", C.c_int32), ("fix_position_distance_threshold", C.c_double),
+                ("fix_position_angular_threshold", C.c_double), ("fix_position_velocity_threshold", C.c_double),
+                ("swing_time", C.c_double), ("zero_velocity_threshold", C.c_double), ("standing_foot_position_threshold", C.c_double),
+                ("min_v_cmd_factor", C.c_double), ("max_correction_cycles", C.c_double), ("correction_period", C.c_double),
+                ("disturbance_correction", C.c_double), ("min_v", C.c_double), ("offset_delay", C.c_double),
+                ("max_stride_length", C.c_double), ("phase_offset", C.c_double * 4), ("control_dt", C.c_double),
+                ("filter_size", C.c_int32), ("switch_offsets", C.c_int32), ("correct_all", C.c_int32)]
+
+
 class SeqModel(C.Structure):
     _fields_ = [("mass", C.c_double), ("inertia", C.c_double * 9), ("com", C.c_double * 3), ("shoulders", C.c_double * 12),
                 ("raibert_k", C.c_double), ("raibert_g", C.c_double), ("max_leg_length", C.c_double)]
@@ -54,6 +65,7 @@ EXPORTS = [
     "b200qp_mpc_solve_batch", "b200qp_mpc_solve_batch_device", "b200qp_mpc_get_duals", "b200qp_mpc_get_condensed",
     "b200qp_mpc_last_timing", "b200qp_mpc_stream", "b200qp_mpc_set_model", "b200qp_mpc_sequence_batch",
     "b200qp_mpc_sequence_solve_batch", "b200qp_mpc_sequence_solve_batch_device", "b200qp_gait_schedule", "b200qp_gait_schedule_device",
+    "b200qp_mpc_sequencer_configure", "b200qp_mpc_sequencer_reset", "b200qp_mpc_sequencer_step", "b200qp_mpc_sequencer_step_solve",
     "b200qp_mpc_create_sharded", "b200qp_mpc_destroy_sharded", "b200qp_mpc_solve_batch_sharded", "b200qp_mpc_sharded_handle",
     "b200qp_mpc_sharded_devices", "b200qp_shard_range",
     "b200qp_wbc_create", "b200qp_wbc_destroy", "b200qp_wbc_solve_batch", "b200qp_wbc_solve_batch_device", "b200qp_wbc_stream",
@@ -96,6 +108,10 @@ def load() -> C.CDLL:
     lib.b200qp_mpc_sequence_solve_batch.argtypes = [vp, i32, vp, vp, vp, vp, vp]
     lib.b200qp_mpc_sequence_solve_batch_device.argtypes = [vp, i32, vp, vp, vp, vp, vp, i32]
     lib.b200qp_mpc_stream.restype = vp
+    lib.b200qp_mpc_sequencer_configure.argtypes = [vp, p(SeqOptions)]
+    lib.b200qp_mpc_sequencer_reset.argtypes = [vp]
+    lib.b200qp_mpc_sequencer_step.argtypes = [vp, i32, vp, vp, vp, vp]
+    lib.b200qp_mpc_sequencer_step_solve.argtypes = [vp, i32, vp, vp, vp, vp, vp]
     lib.b200qp_mpc_create_sharded.argtypes = [p(MpcConfig), p(i32), i32, p(vp)]
     lib.b200qp_mpc_destroy_sharded.argtypes = [vp]
     lib.b200qp_mpc_destroy_sharded.restype = None

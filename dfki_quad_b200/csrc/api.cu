@@ -36,12 +36,10 @@ cudaError_t launch_mpc_pcw(const MpcParams &P, int n, const double *in, const ui
 int pcw_grid(int num_sms, int N, int fs, int condN);
 size_t pcw_scratch_doubles(int N, int fs);
 size_t pcond_scratch_doubles(int N);
-struct SeqModel {
-  double mass, inertia[9], com[3], shoulders[12], raibert_k, raibert_g, max_leg_length, dt;
-  int N;
-};
 cudaError_t launch_sequencer(int n, const SeqModel &M, const double *seq_in, const uint8_t *measured, double *rec_out,
                              uint8_t *contact_out, int in_stride, cudaStream_t st);
+cudaError_t launch_sequencer_full(int n, const SeqModel &M, const SeqOptions &O, const double *seq_in, const uint8_t *measured,
+                                  double *state, double *rec_out, uint8_t *contact_out, int in_stride, cudaStream_t st);
 struct WbcParams {
   int nq, neq, nin;
   double kkt_tol;
@@ -121,6 +119,10 @@ struct b200qp_mpc {
   bool no_zero_copy = false;  // B200QP_NO_ZERO_COPY=1: always stage outputs through device buffers + DMA
   double *d_seq = nullptr, *h_seq = nullptr;
   uint8_t *d_measured = nullptr;
+  // stateful sequencers (b200qp_mpc_sequencer_*)
+  SeqOptions seq_opt;
+  bool have_seq_opt = false;
+  double *d_seq_state = nullptr, *d_seq2 = nullptr, *h_seq2 = nullptr;
 };
 
 static bool is_pinned(const void *p) {
@@ -364,6 +366,9 @@ void b200qp_mpc_destroy(b200qp_mpc *h) {
   cudaFreeHost(h->h_xpred);
   cudaFreeHost(h->h_info);
   cudaFree(h->d_seq);
+  cudaFree(h->d_seq_state);
+  cudaFree(h->d_seq2);
+  cudaFreeHost(h->h_seq2);
   cudaFree(h->d_measured);
   cudaFree(h->d_warm_x);
   cudaFree(h->d_warm_y);
@@ -792,6 +797,105 @@ static int32_t sequence_impl(b200qp_mpc *h, int32_t n, const double *seq_in, con
   }
   CK(launch_sequencer(n, h->model, d_seq, d_meas, h->d_in, h->d_contact, h->P.in_stride, h->stream));
   return B200QP_OK;
+}
+
+// ---- stateful sequencers --------------------------------------------------------------------------------------------------
+int32_t b200qp_mpc_sequencer_configure(b200qp_mpc *h, const b200qp_seq_options *o) {
+  if (!h || !o || (o->mode != 0 && o->mode != 1) || o->raibert_filtersize < 1 || o->raibert_filtersize > 32) return B200QP_ERR_ARG;
+  if (o->mode == 1 && (o->filter_size < 1 || o->filter_size > 24 || !(o->swing_time > 0) || !(o->correction_period > 0) || !(o->control_dt > 0)))
+    return B200QP_ERR_ARG;
+  if (!h->have_model) {
+    g_err = "b200qp_mpc_sequencer_configure: call b200qp_mpc_set_model first";
+    return B200QP_ERR_ARG;
+  }
+  CK(cudaSetDevice(h->cfg.device));
+  SeqOptions &O = h->seq_opt;
+  O.mode = o->mode;
+  O.raibert_filtersize = o->raibert_filtersize;
+  O.fix_standing_position = o->fix_standing_position;
+  O.early_contact_detection = o->early_contact_detection;
+  O.dist_thr = o->fix_position_distance_threshold;
+  O.ang_thr = o->fix_position_angular_threshold;
+  O.vel_thr = o->fix_position_velocity_threshold;
+  O.swing_time = o->swing_time;
+  O.zero_velocity_threshold = o->zero_velocity_threshold;
+  O.standing_foot_position_threshold = o->standing_foot_position_threshold;
+  O.min_v_cmd_factor = o->min_v_cmd_factor;
+  O.max_correction_cycles = o->max_correction_cycles;
+  O.correction_period = o->correction_period;
+  O.disturbance_correction = o->disturbance_correction;
+  O.min_v = o->min_v;
+  O.offset_delay = o->offset_delay;
+  O.max_stride_length = o->max_stride_length;
+  for (int l = 0; l < 4; ++l) O.phase_offset[l] = o->phase_offset[l];
+  O.control_dt = o->control_dt;
+  O.filter_size = o->filter_size;
+  O.switch_offsets = o->switch_offsets;
+  O.correct_all = o->correct_all;
+  const size_t nb = (size_t)h->cfg.max_batch;
+  if (!h->d_seq_state) {
+    CK(cudaMalloc(&h->d_seq_state, nb * 192 * sizeof(double)));
+    CK(cudaMalloc(&h->d_seq2, nb * B200QP_SEQ2_IN_DOUBLES * sizeof(double)));
+    CK(cudaMallocHost(&h->h_seq2, nb * B200QP_SEQ2_IN_DOUBLES * sizeof(double) + nb * 4));
+  }
+  h->have_seq_opt = true;
+  return b200qp_mpc_sequencer_reset(h);
+}
+int32_t b200qp_mpc_sequencer_reset(b200qp_mpc *h) {
+  if (!h || !h->d_seq_state) return B200QP_ERR_ARG;
+  CK(cudaSetDevice(h->cfg.device));
+  CK(cudaMemsetAsync(h->d_seq_state, 0, (size_t)h->cfg.max_batch * 192 * sizeof(double), h->stream));
+  return B200QP_OK;
+}
+static int32_t sequencer_step_impl(b200qp_mpc *h, int32_t n, const double *seq2_in, const uint8_t *measured) {
+  if (!h->have_seq_opt) {
+    g_err = "b200qp_mpc_sequencer_step: call b200qp_mpc_sequencer_configure first";
+    return B200QP_ERR_ARG;
+  }
+  h->model.dt = h->cfg.dt;
+  h->model.N = h->cfg.horizon;
+  const size_t sb = (size_t)n * B200QP_SEQ2_IN_DOUBLES * sizeof(double);
+  const double *src = seq2_in;
+  if (!is_pinned(seq2_in)) {
+    memcpy(h->h_seq2, seq2_in, sb);
+    src = h->h_seq2;
+  }
+  CK(cudaMemcpyAsync(h->d_seq2, src, sb, cudaMemcpyHostToDevice, h->stream));
+  const uint8_t *d_meas = nullptr;
+  if (measured) {
+    uint8_t *stage = reinterpret_cast<uint8_t *>(h->h_seq2 + (size_t)h->cfg.max_batch * B200QP_SEQ2_IN_DOUBLES);
+    memcpy(stage, measured, (size_t)n * 4);
+    CK(cudaMemcpyAsync(h->d_measured, stage, (size_t)n * 4, cudaMemcpyHostToDevice, h->stream));
+    d_meas = h->d_measured;
+  }
+  CK(launch_sequencer_full(n, h->model, h->seq_opt, h->d_seq2, d_meas, h->d_seq_state, h->d_in, h->d_contact, h->P.in_stride, h->stream));
+  return B200QP_OK;
+}
+int32_t b200qp_mpc_sequencer_step(b200qp_mpc *h, int32_t n, const double *seq2_in, const uint8_t *measured_contact, double *records,
+                                  uint8_t *contact) {
+  if (!h || n < 0 || n > h->cfg.max_batch || (n > 0 && (!seq2_in || !records || !contact))) return B200QP_ERR_ARG;
+  if (n == 0) return B200QP_OK;
+  CK(cudaSetDevice(h->cfg.device));
+  const int32_t rc = sequencer_step_impl(h, n, seq2_in, measured_contact);
+  if (rc != B200QP_OK) return rc;
+  const int N = h->cfg.horizon;
+  CK(cudaMemcpyAsync(h->h_in, h->d_in, (size_t)n * h->P.in_stride * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(h->h_contact, h->d_contact, (size_t)n * N * 4, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  memcpy(records, h->h_in, (size_t)n * h->P.in_stride * sizeof(double));
+  memcpy(contact, h->h_contact, (size_t)n * N * 4);
+  return B200QP_OK;
+}
+int32_t b200qp_mpc_sequencer_step_solve(b200qp_mpc *h, int32_t n, const double *seq2_in, const uint8_t *measured_contact, double *forces,
+                                        double *xpred, b200qp_solver_info *info) {
+  if (!h || n < 0 || n > h->cfg.max_batch || (n > 0 && (!seq2_in || !forces || !xpred || !info))) return B200QP_ERR_ARG;
+  if (n == 0) return B200QP_OK;
+  CK(cudaSetDevice(h->cfg.device));
+  int32_t rc = sequencer_step_impl(h, n, seq2_in, measured_contact);
+  if (rc != B200QP_OK) return rc;
+  rc = solve_and_fetch(h, n, forces, xpred, info);
+  h->last_launches += 1;
+  return rc;
 }
 
 int32_t b200qp_mpc_sequence_batch(b200qp_mpc *h, int32_t n, const double *seq_in, const uint8_t *measured_contact,

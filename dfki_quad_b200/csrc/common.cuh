@@ -22,6 +22,21 @@ struct MpcParams {
   int precision;  // 0 FP64 (product); 1 / 2: FP32 error study of the condensed kernel (b200qp_mpc_config.precision)
 };
 
+// model constants of the gait sequencer kernels (b200qp_seq_model + the handle's dt / horizon)
+struct SeqModel {
+  double mass, inertia[9], com[3], shoulders[12], raibert_k, raibert_g, max_leg_length, dt;
+  int N;
+};
+// mirror of b200qp_seq_options (include/b200qp.h)
+struct SeqOptions {
+  int mode, raibert_filtersize, fix_standing_position, early_contact_detection;
+  double dist_thr, ang_thr, vel_thr;
+  // AdaptiveGait constructor arguments (gait.hpp:123-139)
+  double swing_time, zero_velocity_threshold, standing_foot_position_threshold, min_v_cmd_factor, max_correction_cycles,
+      correction_period, disturbance_correction, min_v, offset_delay, max_stride_length, phase_offset[4], control_dt;
+  int filter_size, switch_offsets, correct_all;
+};
+
 struct MpcBuffers {
   const double *in;        // [n][in_stride]
   const uint8_t *contact;  // [n][N][4]

@@ -113,10 +113,6 @@ cudaError_t fp64_peak(int num_sms, double *tflops) {
 //   RaibertFootStepPlanner::get_foot_position_sequence / get_foothold   raibert_foot_step_planner.cpp:43-169
 namespace b200qp {
 
-struct SeqModel {
-  double mass, inertia[9], com[3], shoulders[12], raibert_k, raibert_g, max_leg_length, dt;
-  int N;
-};
 
 namespace {
 __device__ inline double q_yaw(const double *q) {

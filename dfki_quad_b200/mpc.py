@@ -82,6 +82,46 @@ def euler_to_quaternion(e):
     return np.stack([x, yy, z, w], axis=-1)
 
 
+# b200qp_seq_options defaults: config/mit_controller_sim_go2.yaml:40-52, mit_controller_node.cpp:249-264 (AdaptiveGait arguments)
+SEQ_OPTION_DEFAULTS = dict(
+    raibert_filtersize=20, fix_standing_position=1, early_contact_detection=1, fix_position_distance_threshold=0.1,
+    fix_position_angular_threshold=0.26, fix_position_velocity_threshold=0.1, swing_time=0.2, zero_velocity_threshold=0.03,
+    standing_foot_position_threshold=0.08, min_v_cmd_factor=0.5, max_correction_cycles=2.0, correction_period=0.6,
+    disturbance_correction=0.0, min_v=0.0, offset_delay=0.0, max_stride_length=0.0, phase_offset=(0.0, 0.5, 0.5, 0.0),
+    control_dt=0.01, filter_size=10, switch_offsets=1, correct_all=0)
+# Target fields in the order of the value block / activation bits of the stateful sequencer input (target.hpp:8-45)
+TARGET_VALUES = ("x", "y", "z", "roll", "pitch", "yaw", "qx", "qy", "qz", "qw", "x_dot", "y_dot", "z_dot", "hybrid_x_dot",
+                 "hybrid_y_dot", "hybrid_z_dot", "wx", "wy", "wz")
+TARGET_FLAGS = ("x", "y", "z", "roll", "pitch", "yaw", "full_orientation", "x_dot", "y_dot", "z_dot", "hybrid_x_dot", "hybrid_y_dot",
+                "hybrid_z_dot", "wx", "wy", "wz")
+
+
+def pack_seq2(state13, feet, time_ns, target, gait=None):
+    """Input records of the stateful sequencer (b200qp.h, B200QP_SEQ2_IN_DOUBLES).  state13 [n,13], feet [n,4,3], time_ns [n] (integer
+    nanoseconds), target: dict field -> [n] array or scalar (`full_orientation` -> [n,4] xyzw); every given field is activated.
+    gait = (period [n], duty [n,4], offset [n,4]) for the simple sequencer."""
+    state13 = np.asarray(state13, dtype=np.float64)
+    n = state13.shape[0]
+    rec = np.zeros((n, 64))
+    rec[:, 0:13] = state13
+    rec[:, 13:25] = np.asarray(feet, dtype=np.float64).reshape(n, 12)
+    rec[:, 25] = np.asarray(time_ns, dtype=np.float64)
+    rec[:, 26 + 9] = 1.0
+    act = 0
+    for k, v in target.items():
+        if k == "full_orientation":
+            rec[:, 32:36] = v
+        else:
+            rec[:, 26 + TARGET_VALUES.index(k)] = v
+        act |= 1 << TARGET_FLAGS.index(k)
+    rec[:, 45] = float(act)
+    if gait is not None:
+        rec[:, 46] = gait[0]
+        rec[:, 47:51] = gait[1]
+        rec[:, 51:55] = gait[2]
+    return rec
+
+
 class BatchedMPC:
     """Drop-in for `MPC` over a batch.  Constructor arguments follow mpc.hpp:117-127; `solver` accepts the reference's
     acados plan names ("PARTIAL_CONDENSING_HPIPM", "PARTIAL_CONDENSING_OSQP", ...) or the kernel names
@@ -251,6 +291,64 @@ class BatchedMPC:
                                                        mc.ctypes.data if mc is not None else None, forces.ctypes.data,
                                                        xpred.ctypes.data, C.addressof(info))
         _lib.check(rc, "b200qp_mpc_sequence_solve_batch")
+        return forces, xpred, self._info(info, n)
+
+    # -- the sequencers with their state across calls (b200qp_mpc_sequencer_*) ----------------------------------------------
+    def sequencer_configure(self, mode="simple", **options):
+        """b200qp_mpc_sequencer_configure: `mode` "simple" (SimpleGaitSequencer) or "adaptive" (AdaptiveGaitSequencer); options are
+        the fields of b200qp_seq_options, defaults = config/mit_controller_sim_go2.yaml + mit_controller_node.cpp:250-264."""
+        o = _lib.SeqOptions()
+        vals = dict(SEQ_OPTION_DEFAULTS)
+        unknown = set(options) - set(vals)
+        if unknown:
+            raise TypeError(f"unknown sequencer options {sorted(unknown)}")
+        vals.update(options)
+        o.mode = {"simple": 0, "adaptive": 1}[mode]
+        for k, v in vals.items():
+            if k == "phase_offset":
+                o.phase_offset[:] = [float(x) for x in v]
+            elif isinstance(getattr(o, k), int):
+                setattr(o, k, int(v))
+            else:
+                setattr(o, k, float(v))
+        _lib.check(self._lib.b200qp_mpc_sequencer_configure(self._h, C.byref(o)), "b200qp_mpc_sequencer_configure")
+
+    def sequencer_reset(self):
+        _lib.check(self._lib.b200qp_mpc_sequencer_reset(self._h), "b200qp_mpc_sequencer_reset")
+
+    def _seq2_args(self, seq2_in, measured_contact):
+        seq2_in = np.ascontiguousarray(seq2_in, dtype=np.float64)
+        n = seq2_in.shape[0]
+        if seq2_in.shape != (n, 64):
+            raise ValueError("seq2_in must be [n, 64]")
+        mc = None
+        if measured_contact is not None:
+            mc = np.ascontiguousarray(measured_contact, dtype=np.uint8)
+            if mc.shape != (n, 4):
+                raise ValueError("measured_contact must be [n, 4]")
+        return seq2_in, mc, n
+
+    def sequencer_step(self, seq2_in, measured_contact=None):
+        """b200qp_mpc_sequencer_step: UpdateState + UpdateTarget + GetGaitSequence of every robot -> (records, contact)."""
+        seq2_in, mc, n = self._seq2_args(seq2_in, measured_contact)
+        rec = np.zeros((n, in_doubles(self.N)))
+        contact = np.zeros((n, self.N, 4), dtype=np.uint8)
+        rc = self._lib.b200qp_mpc_sequencer_step(self._h, n, seq2_in.ctypes.data, mc.ctypes.data if mc is not None else None,
+                                                 rec.ctypes.data, contact.ctypes.data)
+        _lib.check(rc, "b200qp_mpc_sequencer_step")
+        return rec, contact
+
+    def sequencer_step_solve(self, seq2_in, measured_contact=None, forces=None, xpred=None):
+        """b200qp_mpc_sequencer_step_solve: the stateful sequencer + QP assembly + solve in one call."""
+        seq2_in, mc, n = self._seq2_args(seq2_in, measured_contact)
+        if forces is None:
+            forces = np.zeros((n, self.N, 12))
+        if xpred is None:
+            xpred = np.zeros((n, self.N + 1, 13))
+        info = self._info_buf()
+        rc = self._lib.b200qp_mpc_sequencer_step_solve(self._h, n, seq2_in.ctypes.data, mc.ctypes.data if mc is not None else None,
+                                                       forces.ctypes.data, xpred.ctypes.data, C.addressof(info))
+        _lib.check(rc, "b200qp_mpc_sequencer_step_solve")
         return forces, xpred, self._info(info, n)
 
     def sequence_and_solve_device(self, n, d_seq_in, d_measured, d_forces, d_xpred, d_info, sync=True):

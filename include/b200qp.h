@@ -219,6 +219,49 @@ int32_t b200qp_mpc_sequence_solve_batch_device(b200qp_mpc *h, int32_t n, const d
                                                const uint8_t *d_measured_contact, double *d_forces, double *d_xpred,
                                                b200qp_solver_info *d_info, int32_t sync);
 
+/* ---- the gait sequencers with their state across calls (kernel K5b) ------------------------------------------------------
+ * What b200qp_mpc_sequence_* above does for ONE call of a freshly constructed SimpleGaitSequencer, these entry points do for
+ * the sequencers as the controller node runs them, call after call: the state the reference keeps in its objects lives in
+ * a per-robot record on the device (slot p of the handle <-> robot p) -
+ *   SimpleGaitSequencer::phase_ / time_ (phase = fmod((t - t0) / T, 1), 0 for a standing gait)   simple_gait_sequencer.cpp:62-80
+ *   MPCTrajectoryPlanner::sequence_initialized_, foot_heights_ and the previous desired row 1 (stand-still latch)
+ *                                                                                      mpc_trajectory_planner.cpp:28-264
+ *   RaibertFootStepPlanner::velocity_filter_, last_foot_heights_                          raibert_foot_step_planner.cpp:25-129
+ *   AdaptiveGait: leg phases, period, duty factors, phase offsets, velocity filter       gait.cpp:363-700 (mode 1)
+ * and every field / activation flag of `Target` (target.hpp) is honoured.
+ * Input per robot and call, B200QP_SEQ2_IN_DOUBLES doubles:
+ *   [0:13) quat xyzw, position, angular velocity (world), linear velocity     [13:25) current foot positions, world
+ *   [25]   StateInterface::GetTime() in NANOSECONDS (an integer held in a double)
+ *   [26:45) Target values: x y z roll pitch yaw | full_orientation xyzw | x_dot y_dot z_dot | hybrid_x_dot hybrid_y_dot
+ *           hybrid_z_dot | wx wy wz
+ *   [45]   Target::active as a bit mask (bit i = i-th flag of Target::activateTarget in declaration order, target.hpp:28-45)
+ *   [46] period  [47:51) duty factors  [51:55) phase offsets of the Gait (mode 0; ignored by the adaptive gait)
+ * measured_contact [n][4] = StateInterface::GetFeetContacts() (NULL: all feet in contact). */
+#define B200QP_SEQ2_IN_DOUBLES 64
+typedef struct b200qp_seq_options {
+  int32_t mode;                     /* 0: SimpleGaitSequencer, 1: AdaptiveGaitSequencer                                     */
+  int32_t raibert_filtersize;       /* raibert.filtersize (mit_controller_sim_go2.yaml: 20), <= 32                          */
+  int32_t fix_standing_position;    /* fix_standing_position                                                                */
+  int32_t early_contact_detection;  /* early_contact_detection                                                              */
+  double fix_position_distance_threshold, fix_position_angular_threshold, fix_position_velocity_threshold;
+  /* AdaptiveGait constructor arguments (gait.hpp:123-139; defaults mit_controller_node.cpp:250-264) */
+  double swing_time, zero_velocity_threshold, standing_foot_position_threshold, min_v_cmd_factor, max_correction_cycles,
+      correction_period, disturbance_correction, min_v, offset_delay, max_stride_length, phase_offset[4];
+  double control_dt;                /* MPC_CONTROL_DT, the dt AdaptiveGaitSequencer passes to update_sequence                */
+  int32_t filter_size, switch_offsets, correct_all;
+} b200qp_seq_options;
+/* Sets the options (b200qp_mpc_set_model must have been called) and forgets the state of every slot. */
+int32_t b200qp_mpc_sequencer_configure(b200qp_mpc *h, const b200qp_seq_options *opt);
+/* Forgets the state of every slot (as if the sequencers were constructed anew). */
+int32_t b200qp_mpc_sequencer_reset(b200qp_mpc *h);
+/* One UpdateState + UpdateTarget + GetGaitSequence per robot -> records / contact in the layout b200qp_mpc_solve_batch
+ * consumes (HOST buffers; parity hook). */
+int32_t b200qp_mpc_sequencer_step(b200qp_mpc *h, int32_t n, const double *seq2_in, const uint8_t *measured_contact, double *records,
+                                  uint8_t *contact);
+/* The same followed by QP assembly + solve; outputs and failure semantics as b200qp_mpc_solve_batch. */
+int32_t b200qp_mpc_sequencer_step_solve(b200qp_mpc *h, int32_t n, const double *seq2_in, const uint8_t *measured_contact, double *forces,
+                                        double *xpred, b200qp_solver_info *info);
+
 /* ---- gait schedule -> contact mask -> bound indexing (kernel K4, bit-exact) -------------------------------------
  * Gait::update_sequence (gait.cpp:67-112) for n robots with per-robot gait parameters and phase, followed by
  * MPC::GetUBounds (mpc.cpp:94-115).
