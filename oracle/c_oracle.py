@@ -80,7 +80,7 @@ class WbcInfo(C.Structure):
     _fields_ = [("status", C.c_int), ("iters", C.c_int), ("kkt", C.c_double * 4)]
 
 
-def wbc_batch(H, g, A, lo, hi, neq, tol=1e-8, max_iter=60, threads=0):
+def wbc_batch(H, g, A, lo, hi, neq, tol=1e-6, max_iter=40, threads=0):
     """C dense primal-dual IPM (wbc_ref.c) over a batch of WBC QPs in the C-ABI layout (column-major H [n,nq*nq], A [n,(neq+nin)*nq])."""
     lib = load()
     lib.wbc_ref_batch.restype = C.c_int
