@@ -54,6 +54,17 @@ class SeqOptions(C.Structure):
                 ("filter_size", C.c_int32), ("switch_offsets", C.c_int32), ("correct_all", C.c_int32)]
 
 
+class WbcSceneConfig(C.Structure):
+    _fields_ = [("mu", C.c_double), ("com_pose_weight", C.c_double * 6), ("foot_force_weight", C.c_double * 3),
+                ("foot_pose_weight", C.c_double * 3), ("hessian_regularizer", C.c_double), ("tau_max", C.c_double * 12)]
+
+
+class RolloutOptions(C.Structure):
+    _fields_ = [("substeps", C.c_int32), ("plant_inertia", C.c_int32), ("wbc_per_mpc", C.c_int32), ("reserved", C.c_int32),
+                ("com_pose_Kp", C.c_double * 6), ("com_pose_Kd", C.c_double * 6), ("feet_pose_Kp", C.c_double * 3),
+                ("feet_pose_Kd", C.c_double * 3)]
+
+
 class SeqModel(C.Structure):
     _fields_ = [("mass", C.c_double), ("inertia", C.c_double * 9), ("com", C.c_double * 3), ("shoulders", C.c_double * 12),
                 ("raibert_k", C.c_double), ("raibert_g", C.c_double), ("max_leg_length", C.c_double)]
@@ -66,6 +77,8 @@ EXPORTS = [
     "b200qp_mpc_last_timing", "b200qp_mpc_stream", "b200qp_mpc_set_model", "b200qp_mpc_sequence_batch",
     "b200qp_mpc_sequence_solve_batch", "b200qp_mpc_sequence_solve_batch_device", "b200qp_gait_schedule", "b200qp_gait_schedule_device",
     "b200qp_mpc_sequencer_configure", "b200qp_mpc_sequencer_reset", "b200qp_mpc_sequencer_step", "b200qp_mpc_sequencer_step_solve",
+    "b200qp_wbc_scene_configure", "b200qp_wbc_scene_solve_batch", "b200qp_wbc_scene_assemble", "b200qp_wbc_scene_solve_batch_device",
+    "b200qp_mpc_rollout",
     "b200qp_mpc_create_sharded", "b200qp_mpc_destroy_sharded", "b200qp_mpc_solve_batch_sharded", "b200qp_mpc_sharded_handle",
     "b200qp_mpc_sharded_devices", "b200qp_shard_range",
     "b200qp_wbc_create", "b200qp_wbc_destroy", "b200qp_wbc_solve_batch", "b200qp_wbc_solve_batch_device", "b200qp_wbc_stream",
@@ -112,6 +125,11 @@ def load() -> C.CDLL:
     lib.b200qp_mpc_sequencer_reset.argtypes = [vp]
     lib.b200qp_mpc_sequencer_step.argtypes = [vp, i32, vp, vp, vp, vp]
     lib.b200qp_mpc_sequencer_step_solve.argtypes = [vp, i32, vp, vp, vp, vp, vp]
+    lib.b200qp_wbc_scene_configure.argtypes = [vp, p(WbcSceneConfig)]
+    lib.b200qp_wbc_scene_solve_batch.argtypes = [vp, i32, vp, vp, vp, vp]
+    lib.b200qp_wbc_scene_assemble.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, vp]
+    lib.b200qp_wbc_scene_solve_batch_device.argtypes = [vp, i32, vp, vp, vp, vp, i32]
+    lib.b200qp_mpc_rollout.argtypes = [vp, vp, i32, i32, vp, p(RolloutOptions), vp]
     lib.b200qp_mpc_create_sharded.argtypes = [p(MpcConfig), p(i32), i32, p(vp)]
     lib.b200qp_mpc_destroy_sharded.argtypes = [vp]
     lib.b200qp_mpc_destroy_sharded.restype = None

@@ -45,6 +45,24 @@ struct WbcParams {
   double kkt_tol;
   int max_iter;
 };
+struct WbcSceneConfig {
+  double mu, com_pose_weight[6], foot_force_weight[3], foot_pose_weight[3], hessian_regularizer, tau_max[12];
+};
+cudaError_t launch_wbc_scene(int n, const WbcSceneConfig &C, const double *scene_in, double *H, double *g, double *A, double *lo, double *hi,
+                             double *feet, cudaStream_t st);
+cudaError_t launch_wbc_torque(int n, const double *A, const double *lo, const double *hi, const double *x, double *tau, cudaStream_t st);
+struct RolloutOptions {
+  int substeps, plant_inertia, wbc_per_mpc, reserved;
+  double com_pose_Kp[6], com_pose_Kd[6], feet_pose_Kp[3], feet_pose_Kd[3];
+};
+cudaError_t launch_rollout_feet(int n, int N, int in_stride, const double *rec, const uint8_t *contact, const double *forces,
+                                const b200qp_solver_info *info, double *seq2, uint8_t *measured, double *f0, cudaStream_t st);
+cudaError_t launch_rollout_plant(int n, const SeqModel &M, int plant_inertia, double h_total, int substeps, const double *f_app, int f_stride,
+                                 int f_off, const b200qp_solver_info *f_info, const double *f_fallback, double *seq2, cudaStream_t st);
+cudaError_t launch_rollout_finish(int n, double dt_ns, const double *f0, const b200qp_solver_info *info, const b200qp_solver_info *winfo,
+                                  double *seq2, double *hist, cudaStream_t st);
+cudaError_t launch_rollout_wbc_target(int n, int N, const RolloutOptions &O, const double *seq2, const double *xpred, const double *f0,
+                                      double *scene, cudaStream_t st);
 size_t wbc_smem_bytes(const WbcParams &P);
 int wbc_grid(const WbcParams &P, int num_sms);
 cudaError_t launch_wbc_qp(const WbcParams &P, int n, const double *H, const double *g, const double *A, const double *lo,
@@ -1130,6 +1148,10 @@ struct b200qp_wbc {
   double *d_H = nullptr, *d_g = nullptr, *d_A = nullptr, *d_lo = nullptr, *d_hi = nullptr, *d_x = nullptr;
   b200qp_solver_info *d_info = nullptr, *h_info = nullptr;
   int *d_next = nullptr;
+  // on-device scene assembly (b200qp_wbc_scene_*)
+  WbcSceneConfig scene;
+  bool have_scene = false;
+  double *d_scene = nullptr, *d_tau = nullptr, *d_feet = nullptr, *h_stage = nullptr;
 };
 
 extern "C" {
@@ -1193,6 +1215,10 @@ void b200qp_wbc_destroy(b200qp_wbc *h) {
   cudaFree(h->d_x);
   cudaFree(h->d_info);
   cudaFree(h->d_next);
+  cudaFree(h->d_scene);
+  cudaFree(h->d_tau);
+  cudaFree(h->d_feet);
+  cudaFreeHost(h->h_stage);
   cudaFreeHost(h->h_info);
   for (int c = 0; c < 8; ++c)
     if (h->ev[c]) cudaEventDestroy(h->ev[c]);
@@ -1251,5 +1277,186 @@ int32_t b200qp_wbc_solve_batch(b200qp_wbc *h, int32_t n, const double *H, const 
 }
 
 void *b200qp_wbc_stream(b200qp_wbc *h) { return h ? (void *)h->stream : nullptr; }
+
+// ---- scene assembled on the device ----------------------------------------------------------------------------------------
+int32_t b200qp_wbc_scene_configure(b200qp_wbc *h, const b200qp_wbc_scene_config *c) {
+  if (!h || !c) return B200QP_ERR_ARG;
+  if (h->cfg.nq != 30 || h->cfg.neq != 18 || h->cfg.nin != 28) {
+    g_err = "b200qp_wbc_scene_configure: the Go2 reduced-TSID scene needs a handle with nq = 30, neq = 18, nin = 28";
+    return B200QP_ERR_ARG;
+  }
+  if (!(c->mu > 0) || !(c->hessian_regularizer >= 0)) return B200QP_ERR_ARG;
+  CK(cudaSetDevice(h->cfg.device));
+  h->scene.mu = c->mu;
+  for (int i = 0; i < 6; ++i) h->scene.com_pose_weight[i] = c->com_pose_weight[i];
+  for (int i = 0; i < 3; ++i) {
+    h->scene.foot_force_weight[i] = c->foot_force_weight[i];
+    h->scene.foot_pose_weight[i] = c->foot_pose_weight[i];
+  }
+  h->scene.hessian_regularizer = c->hessian_regularizer;
+  for (int i = 0; i < 12; ++i) h->scene.tau_max[i] = c->tau_max[i];
+  const size_t nb = (size_t)h->cfg.max_batch;
+  if (!h->d_scene) {
+    CK(cudaMalloc(&h->d_scene, nb * B200QP_WBC_SCENE_IN_DOUBLES * sizeof(double)));
+    CK(cudaMalloc(&h->d_tau, nb * 12 * sizeof(double)));
+    CK(cudaMalloc(&h->d_feet, nb * 24 * sizeof(double)));
+    CK(cudaMallocHost(&h->h_stage, nb * (B200QP_WBC_SCENE_IN_DOUBLES + 30 + 12) * sizeof(double)));
+  }
+  h->have_scene = true;
+  return B200QP_OK;
+}
+
+static int32_t wbc_scene_queue(b200qp_wbc *h, int32_t n, const double *d_scene, double *d_x, double *d_tau, b200qp_solver_info *d_info) {
+  CK(launch_wbc_scene(n, h->scene, d_scene, h->d_H, h->d_g, h->d_A, h->d_lo, h->d_hi, h->d_feet, h->stream));
+  CK(cudaMemsetAsync(h->d_next, 0, sizeof(int), h->stream));
+  CK(launch_wbc_qp(h->P, n, h->d_H, h->d_g, h->d_A, h->d_lo, h->d_hi, d_x, d_info, h->d_next, h->grid, h->stream));
+  if (d_tau) CK(launch_wbc_torque(n, h->d_A, h->d_lo, h->d_hi, d_x, d_tau, h->stream));
+  return B200QP_OK;
+}
+
+int32_t b200qp_wbc_scene_solve_batch_device(b200qp_wbc *h, int32_t n, const double *d_scene_in, double *d_x, double *d_tau,
+                                            b200qp_solver_info *d_info, int32_t sync) {
+  if (!h || n < 0 || n > h->cfg.max_batch || (n > 0 && (!d_scene_in || !d_x || !d_info))) return B200QP_ERR_ARG;
+  if (!h->have_scene) {
+    g_err = "b200qp_wbc_scene_solve_batch_device: call b200qp_wbc_scene_configure first";
+    return B200QP_ERR_ARG;
+  }
+  if (n == 0) return B200QP_OK;
+  CK(cudaSetDevice(h->cfg.device));
+  const int32_t rc = wbc_scene_queue(h, n, d_scene_in, d_x, d_tau, d_info);
+  if (rc != B200QP_OK) return rc;
+  if (sync) CK(cudaStreamSynchronize(h->stream));
+  return B200QP_OK;
+}
+
+int32_t b200qp_wbc_scene_solve_batch(b200qp_wbc *h, int32_t n, const double *scene_in, double *x, double *tau, b200qp_solver_info *info) {
+  if (!h || n < 0 || n > h->cfg.max_batch || (n > 0 && (!scene_in || !x || !info))) return B200QP_ERR_ARG;
+  if (!h->have_scene) {
+    g_err = "b200qp_wbc_scene_solve_batch: call b200qp_wbc_scene_configure first";
+    return B200QP_ERR_ARG;
+  }
+  if (n == 0) return B200QP_OK;
+  CK(cudaSetDevice(h->cfg.device));
+  const size_t nn = n, sb = nn * B200QP_WBC_SCENE_IN_DOUBLES * sizeof(double);
+  double *st_in = h->h_stage, *st_x = h->h_stage + (size_t)h->cfg.max_batch * B200QP_WBC_SCENE_IN_DOUBLES;
+  double *st_tau = st_x + (size_t)h->cfg.max_batch * 30;
+  memcpy(st_in, scene_in, sb);
+  memcpy(st_x, x, nn * 30 * sizeof(double));  // a failed QP keeps the caller's row
+  if (tau) memcpy(st_tau, tau, nn * 12 * sizeof(double));
+  CK(cudaMemcpyAsync(h->d_scene, st_in, sb, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->d_x, st_x, nn * 30 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  const int32_t rc = wbc_scene_queue(h, n, h->d_scene, h->d_x, tau ? h->d_tau : nullptr, h->d_info);
+  if (rc != B200QP_OK) return rc;
+  CK(cudaMemcpyAsync(st_x, h->d_x, nn * 30 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(h->h_info, h->d_info, nn * sizeof(b200qp_solver_info), cudaMemcpyDeviceToHost, h->stream));
+  double *st_tau_new = nullptr;
+  if (tau) {
+    st_tau_new = st_in;  // the input staging area is free again once the kernels are queued behind its copy
+    CK(cudaMemcpyAsync(st_tau_new, h->d_tau, nn * 12 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  }
+  CK(cudaStreamSynchronize(h->stream));
+  memcpy(x, st_x, nn * 30 * sizeof(double));
+  memcpy(info, h->h_info, nn * sizeof(b200qp_solver_info));
+  if (tau)
+    for (size_t p = 0; p < nn; ++p)
+      if (h->h_info[p].status == B200QP_ACADOS_SUCCESS) memcpy(tau + 12 * p, st_tau_new + 12 * p, 12 * sizeof(double));
+  return B200QP_OK;
+}
+
+int32_t b200qp_wbc_scene_assemble(b200qp_wbc *h, int32_t n, const double *scene_in, double *H, double *g, double *A, double *lower_y,
+                                  double *upper_y, double *feet) {
+  if (!h || n < 0 || n > h->cfg.max_batch || (n > 0 && (!scene_in || !H || !g || !A || !lower_y || !upper_y))) return B200QP_ERR_ARG;
+  if (!h->have_scene) {
+    g_err = "b200qp_wbc_scene_assemble: call b200qp_wbc_scene_configure first";
+    return B200QP_ERR_ARG;
+  }
+  if (n == 0) return B200QP_OK;
+  CK(cudaSetDevice(h->cfg.device));
+  const size_t nn = n;
+  CK(cudaMemcpyAsync(h->d_scene, scene_in, nn * B200QP_WBC_SCENE_IN_DOUBLES * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  CK(launch_wbc_scene(n, h->scene, h->d_scene, h->d_H, h->d_g, h->d_A, h->d_lo, h->d_hi, h->d_feet, h->stream));
+  CK(cudaMemcpyAsync(H, h->d_H, nn * 900 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(g, h->d_g, nn * 30 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(A, h->d_A, nn * 1380 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(lower_y, h->d_lo, nn * 46 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(upper_y, h->d_hi, nn * 46 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  if (feet) CK(cudaMemcpyAsync(feet, h->d_feet, nn * 24 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return B200QP_OK;
+}
+
+// ---- closed loop on the device ---------------------------------------------------------------------------------------------
+int32_t b200qp_mpc_rollout(b200qp_mpc *h, b200qp_wbc *w, int32_t n, int32_t periods, double *seq2_inout, const b200qp_rollout_options *opt,
+                           double *history) {
+  if (!h || !opt || n < 0 || periods < 0 || n > h->cfg.max_batch || (n > 0 && !seq2_inout) || opt->substeps < 1 ||
+      (opt->plant_inertia != 0 && opt->plant_inertia != 1))
+    return B200QP_ERR_ARG;
+  if (!h->have_seq_opt) {
+    g_err = "b200qp_mpc_rollout: call b200qp_mpc_set_model and b200qp_mpc_sequencer_configure first";
+    return B200QP_ERR_ARG;
+  }
+  if (w && (!w->have_scene || w->cfg.device != h->cfg.device || w->cfg.max_batch < n || opt->wbc_per_mpc < 1 || opt->substeps % opt->wbc_per_mpc)) {
+    g_err = "b200qp_mpc_rollout: the WBC handle needs a configured scene on the same device, max_batch >= n, and wbc_per_mpc must divide substeps";
+    return B200QP_ERR_ARG;
+  }
+  if (n == 0 || periods == 0) return B200QP_OK;
+  CK(cudaSetDevice(h->cfg.device));
+  RolloutOptions O;
+  O.substeps = opt->substeps;
+  O.plant_inertia = opt->plant_inertia;
+  O.wbc_per_mpc = opt->wbc_per_mpc;
+  O.reserved = 0;
+  for (int c = 0; c < 6; ++c) {
+    O.com_pose_Kp[c] = opt->com_pose_Kp[c];
+    O.com_pose_Kd[c] = opt->com_pose_Kd[c];
+  }
+  for (int c = 0; c < 3; ++c) {
+    O.feet_pose_Kp[c] = opt->feet_pose_Kp[c];
+    O.feet_pose_Kd[c] = opt->feet_pose_Kd[c];
+  }
+  const int N = h->cfg.horizon;
+  h->model.dt = h->cfg.dt;
+  h->model.N = N;
+  const size_t nn = n, sb = nn * B200QP_SEQ2_IN_DOUBLES * sizeof(double);
+  DevTmp tmp;
+  double *d_f0 = nullptr, *d_hist = nullptr;
+  CK(tmp.alloc(&d_f0, nn * 12 * sizeof(double)));
+  CK(tmp.alloc(&d_hist, history ? (size_t)periods * nn * B200QP_ROLLOUT_HIST_DOUBLES * sizeof(double) : 8));
+  cudaStream_t st = h->stream;
+  CK(cudaMemcpyAsync(h->d_seq2, seq2_inout, sb, cudaMemcpyHostToDevice, st));
+  CK(cudaMemsetAsync(h->d_measured, 1, nn * 4, st));  // first period: every foot measured in contact
+  const double dt = h->cfg.dt, dt_ns = (double)llround(dt * 1e9);
+  int launches = 0;
+  for (int k = 0; k < periods; ++k) {
+    CK(launch_sequencer_full(n, h->model, h->seq_opt, h->d_seq2, h->d_measured, h->d_seq_state, h->d_in, h->d_contact, h->P.in_stride, st));
+    const int32_t rc = solve_device_impl(h, n, h->d_in, h->d_contact, h->d_forces, h->d_xpred, h->d_info, -1, nullptr, nullptr);
+    if (rc != B200QP_OK) return rc;
+    launches += 1 + h->last_launches;
+    CK(launch_rollout_feet(n, N, h->P.in_stride, h->d_in, h->d_contact, h->d_forces, h->d_info, h->d_seq2, h->d_measured, d_f0, st));
+    if (!w) {
+      CK(launch_rollout_plant(n, h->model, O.plant_inertia, dt, O.substeps, d_f0, 12, 0, nullptr, d_f0, h->d_seq2, st));
+      launches += 3;
+    } else {
+      for (int s = 0; s < O.wbc_per_mpc; ++s) {
+        CK(launch_rollout_wbc_target(n, N, O, h->d_seq2, h->d_xpred, d_f0, w->d_scene, st));
+        CK(launch_wbc_scene(n, w->scene, w->d_scene, w->d_H, w->d_g, w->d_A, w->d_lo, w->d_hi, w->d_feet, st));
+        CK(cudaMemsetAsync(w->d_next, 0, sizeof(int), st));
+        CK(launch_wbc_qp(w->P, n, w->d_H, w->d_g, w->d_A, w->d_lo, w->d_hi, w->d_x, w->d_info, w->d_next, w->grid, st));
+        // the WBC's contact forces (x[18:30]) drive the plant; a robot whose WBC QP failed keeps the MPC's forces for this slice
+        CK(launch_rollout_plant(n, h->model, O.plant_inertia, dt / O.wbc_per_mpc, O.substeps / O.wbc_per_mpc, w->d_x, 30, 18, w->d_info, d_f0,
+                                h->d_seq2, st));
+        launches += 4;
+      }
+      launches += 2;
+    }
+    CK(launch_rollout_finish(n, dt_ns, d_f0, h->d_info, w ? w->d_info : nullptr, h->d_seq2,
+                             history ? d_hist + (size_t)k * nn * B200QP_ROLLOUT_HIST_DOUBLES : nullptr, st));
+  }
+  CK(cudaMemcpyAsync(seq2_inout, h->d_seq2, sb, cudaMemcpyDeviceToHost, st));
+  if (history) CK(cudaMemcpyAsync(history, d_hist, (size_t)periods * nn * B200QP_ROLLOUT_HIST_DOUBLES * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  h->last_launches = launches;
+  return B200QP_OK;
+}
 
 }  // extern "C"

@@ -66,14 +66,9 @@ __global__ void __launch_bounds__(32) mpc_pcw_kernel(const MpcParams P, int npro
   __shared__ double sP[144], sPA[144], sDst[20], sYst[8], sVec[64];
   __shared__ double sIn[NUBW * 8];  // per input of the current block: bw[3], rb[3], kd
   __shared__ unsigned char sTriR[80], sTriC[80], sCc[NUBW];  // lower-triangle enumeration (12 rows + 2 spare), component of an input
-  __shared__ double sBwc[MAXFS * 9];                    // Bw of the stance foot-stages, row-major 3x3
-  __shared__ double sU[MAXA], sDU[MAXA], sRt[MAXA], sYv[MAXA], sDul[NUBW];
-  __shared__ double sX[(NH + 1) * 12];
+  __shared__ double sU[MAXA], sDul[NUBW];
   double *sQe = sK;  // [(NH + 1) * 12] weighted state error: only alive in the roll-out / adjoint phase, before any block is assembled
   static_assert((NH + 1) * 12 <= NAW * LDW, "sQe alias");
-  __shared__ double sLw[(NH + 2) * 3], sLv[(NH + 2) * 3];
-  __shared__ double sRb[MAXFS * 5];
-  __shared__ double sBwsum[NH * 6];
   __shared__ double sYaw[NH + 1], sX0[13], sRot[9];
   __shared__ unsigned char sOn[NH * 4], sFs[MAXFS];
   __shared__ short sSt[NH + 2];      // first stance foot-stage of stage k (prefix counts), sSt[N] = nfs
@@ -87,6 +82,13 @@ __global__ void __launch_bounds__(32) mpc_pcw_kernel(const MpcParams P, int npro
   double *Cs = scratch + (size_t)blockIdx.x * scratch_stride;
   double *Bk = Cs + scratch_stride - (20 * MAXFS + MAXA);  // best-iterate backup: (s, z) of every lane's foot-stages, forces
   double *gXref = Bk - (NH + 1) * 12;                      // reference states (read once per iteration)
+  // Per-problem tables that are written once (set-up) or once per iteration and read through L1: keeping them out of shared memory
+  // is what lets a seventh block reside on the SM (36.2 KB -> 31 KB per block); the latency-bound kernel scales with resident warps.
+  double *const sBwc = gXref - MAXFS * 9;   // Bw of the stance foot-stages, row-major 3x3
+  double *const sRb = sBwc - MAXFS * 5;
+  double *const sBwsum = sRb - NH * 6;
+  double *const sLw = sBwsum - (NH + 2) * 3, *const sLv = sLw - (NH + 2) * 3;
+  double *const sX = sLv - (NH + 1) * 12, *const sDU = sX - MAXA, *const sRt = sDU - MAXA, *const sYv = sRt - MAXA;
 
   for (int e = lane; e < 80; e += 32) {  // constant memory serialises lane-dependent indices: keep the tables in shared memory
     sTriR[e] = TRI_R[e];
@@ -905,7 +907,7 @@ static int pcw_fcap(int fs, int N, int condN) {
 }
 size_t pcw_scratch_doubles(int N, int fs) {
   const size_t half = (size_t)16 * 15 * (size_t)N + 288 * (size_t)N + 1024;  // block constants / factors that do not fit shared memory
-  return 2 * half + 23 * (size_t)(32 * fs) + 21 * 12;
+  return 2 * half + 23 * (size_t)(32 * fs) + 21 * 12 + 14 * (size_t)(32 * fs) + 12 * 22 + 64 + 12 * 21 + 9 * (size_t)(32 * fs);
 }
 
 template <int NH, int FS>

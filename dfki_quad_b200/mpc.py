@@ -351,6 +351,26 @@ class BatchedMPC:
         _lib.check(rc, "b200qp_mpc_sequencer_step_solve")
         return forces, xpred, self._info(info, n)
 
+    # -- closed loop on the device (b200qp_mpc_rollout) -------------------------------------------------------------------
+    def rollout(self, seq2, periods, wbc=None, substeps=10, plant_inertia="physical", wbc_per_mpc=5, gains=None, history=True):
+        """b200qp_mpc_rollout: `periods` control periods of n single-rigid-body robots with the sequencer + MPC (+ the WBC of the
+        BatchedWBCSolver `wbc`, scene configured) in the loop, all on the device.  seq2 [n,64] is updated in place to the final
+        state; returns the history [periods, n, 16] (pos, vel, quat, sum f_z, MPC status, iterations, polish rounds, WBC status)."""
+        if not (isinstance(seq2, np.ndarray) and seq2.dtype == np.float64 and seq2.flags.c_contiguous and seq2.ndim == 2 and seq2.shape[1] == 64):
+            raise ValueError("seq2 must be a C-contiguous float64 [n, 64] array (it is updated in place)")
+        n = seq2.shape[0]
+        o = _lib.RolloutOptions()
+        o.substeps, o.wbc_per_mpc = int(substeps), int(wbc_per_mpc)
+        o.plant_inertia = {"physical": 0, "reference_model": 1}[plant_inertia]
+        g = gains or dict(com_pose_Kp=[300.0] * 3 + [200.0] * 3, com_pose_Kd=[100.0] * 6, feet_pose_Kp=[1200.0] * 3, feet_pose_Kd=[500.0, 500.0, 400.0])
+        for k in ("com_pose_Kp", "com_pose_Kd", "feet_pose_Kp", "feet_pose_Kd"):
+            getattr(o, k)[:] = [float(v) for v in g[k]]
+        hist = np.zeros((periods, n, 16)) if history else None
+        rc = self._lib.b200qp_mpc_rollout(self._h, wbc._h if wbc is not None else None, n, int(periods), seq2.ctypes.data, C.byref(o),
+                                          hist.ctypes.data if hist is not None else None)
+        _lib.check(rc, "b200qp_mpc_rollout")
+        return hist
+
     def sequence_and_solve_device(self, n, d_seq_in, d_measured, d_forces, d_xpred, d_info, sync=True):
         rc = self._lib.b200qp_mpc_sequence_solve_batch_device(self._h, n, d_seq_in, d_measured, d_forces, d_xpred, d_info,
                                                               1 if sync else 0)

@@ -104,3 +104,104 @@ def closed_loop(mpc, n, steps, target, gait="TROT", seed=0, dt=0.05, v_filter_le
         hist["ok"].append(ok.copy()); hist["fz"].append(f0[:, :, 2].sum(axis=1)); hist["iters"].append(info.acados_num_iter.copy())
         hist["rounds"].append(info.polish_rounds.copy()); hist["kernel_ms"].append(info.total_solver_time * 1e3)
     return {k: np.array(v) for k, v in hist.items()}
+
+
+# ---- host-stepped mirror of the device loop (b200qp_mpc_rollout) --------------------------------------------------------------
+ABAD = np.array([0.1934, 0.0465])
+HIP_Y, L1, L2 = 0.0955, 0.213, 0.213
+
+
+def leg_ik(quat, pos, feet):
+    """Closed-form inverse kinematics of the Go2 legs: foot positions (world) -> joint angles [n,12] and leg Jacobians (world) [n,4,3,3]
+    (what rollout_wbc_target_kernel computes; checked against go2_model.dynamics' forward kinematics in the tests)."""
+    n = pos.shape[0]
+    R = sq.quat_to_rot(quat)
+    q = np.zeros((n, 12))
+    J = np.zeros((n, 4, 3, 3))
+    for leg in range(4):
+        sx, sy = (1.0 if leg < 2 else -1.0), (1.0 if leg % 2 == 0 else -1.0)
+        rw = feet[:, leg] - pos
+        b = np.einsum("nji,nj->ni", R, rw) - np.array([sx * ABAD[0], sy * ABAD[1], 0.0])
+        bx, by, bz = b[:, 0], b[:, 1], b[:, 2]
+        l0 = sy * HIP_Y
+        hh = np.sqrt(np.maximum(by * by + bz * bz - l0 * l0, 1e-12))
+        q0 = np.arctan2(hh * by + l0 * bz, l0 * by - hh * bz)
+        d2 = np.clip(bx * bx + hh * hh, 1e-6, (L1 + L2) ** 2 * (1.0 - 1e-9))
+        ck = np.clip((d2 - L1 * L1 - L2 * L2) / (2.0 * L1 * L2), -1.0, 1.0)
+        q2 = -np.arccos(ck)
+        q1 = np.arctan2(-bx, hh) - np.arctan2(L2 * np.sin(q2), L1 + L2 * np.cos(q2))
+        q[:, 3 * leg], q[:, 3 * leg + 1], q[:, 3 * leg + 2] = q0, q1, q2
+        c0, s0, s1, c1, s12, c12 = np.cos(q0), np.sin(q0), np.sin(q1), np.cos(q1), np.sin(q1 + q2), np.cos(q1 + q2)
+        tx, tz, kx, kz = -L1 * s1 - L2 * s12, -L1 * c1 - L2 * c12, -L2 * s12, -L2 * c12
+        z = np.zeros(n)
+        a_foot = np.stack([tx, l0 * c0 - tz * s0, l0 * s0 + tz * c0], axis=1)
+        h_foot = np.stack([tx, -tz * s0, tz * c0], axis=1)
+        k_foot = np.stack([kx, -kz * s0, kz * c0], axis=1)
+        ax0 = np.stack([z + 1.0, z, z], axis=1)
+        ax1 = np.stack([z, c0, s0], axis=1)
+        jb = np.stack([np.cross(ax0, a_foot), np.cross(ax1, h_foot), np.cross(ax1, k_foot)], axis=2)
+        J[:, leg] = R @ jb
+    return q, J
+
+
+def wbc_target(quat, pos, omega, vel, feet, mask, x1, f0, gains):
+    """The scene input rows rollout_wbc_target_kernel builds: joints from the leg IK with the feet at rest, body PD on the stage-1
+    prediction, wrench references f0, contacts `mask` [n,4] bool."""
+    from . import wbc
+    from .mpc import euler_to_quaternion
+
+    n = pos.shape[0]
+    q, J = leg_ik(quat, pos, feet)
+    rhs = -(vel[:, None, :] + np.cross(omega[:, None, :], feet - pos[:, None, :]))
+    qd = np.linalg.solve(J, rhs[..., None])[..., 0].reshape(n, 12)
+    kp, kd = np.asarray(gains["com_pose_Kp"], float), np.asarray(gains["com_pose_Kd"], float)
+    a_body = np.concatenate([kd[:3] * (x1[:, 9:12] - vel) + kp[:3] * (x1[:, 3:6] - pos),
+                             kd[3:] * (x1[:, 6:9] - omega) + kp[3:] * wbc._quat_err_rotvec(euler_to_quaternion(x1[:, 0:3]), quat)], axis=1)
+    return wbc.pack_scene(pos, quat, vel, omega, q, qd, mask, a_body, np.zeros((n, 4, 3)), f0.reshape(n, 4, 3))
+
+
+def closed_loop_stateful(mpc, seq2, periods, wbc_solver=None, substeps=10, plant_inertia="physical", wbc_per_mpc=5, gains=None):
+    """What b200qp_mpc_rollout does, with the plant, the foot bookkeeping and the MPC -> WBC coupling stepped on the HOST in numpy and one
+    library call per solve (mpc.sequencer_step / solve_records, wbc_solver.scene_solve) - the reference the device loop is tested
+    against.  seq2 [n,64] is updated in place; returns the same history array."""
+    n, N, dt = seq2.shape[0], mpc.N, 0.05
+    g = gains or dict(com_pose_Kp=[300.0] * 3 + [200.0] * 3, com_pose_Kd=[100.0] * 6, feet_pose_Kp=[1200.0] * 3, feet_pose_Kd=[500.0, 500.0, 400.0])
+    hist = np.zeros((periods, n, 16))
+    meas = np.ones((n, 4), dtype=np.uint8)
+    forces_prev = np.zeros((n, N, 12))
+    xpred_prev = np.zeros((n, N + 1, 13))
+    for k in range(periods):
+        rec, contact = mpc.sequencer_step(seq2, meas)
+        forces, xpred, info = mpc.solve_records(rec, contact, forces_prev, xpred_prev)
+        ok = info.success
+        c0 = contact[:, 0].astype(bool)
+        fp = rec[:, 26 + 13 * (N + 1):].reshape(n, N, 4, 3)
+        has = contact.astype(bool).any(axis=1)
+        first = np.argmax(contact.astype(bool), axis=1)
+        nxt = np.take_along_axis(fp, first[:, None, :, None], axis=1)[:, 0]
+        feet = seq2[:, 13:25].reshape(n, 4, 3)
+        feet = np.where(has[:, :, None], nxt, feet)
+        f0 = np.where((ok[:, None] & c0)[:, :, None], forces[:, 0].reshape(n, 4, 3), 0.0)
+        seq2[:, 13:25] = feet.reshape(n, 12)
+        meas = c0.astype(np.uint8)
+        seq2[:, 55] = 16 + (c0 * np.array([1, 2, 4, 8])).sum(axis=1)
+        quat, pos, omega, vel = seq2[:, 0:4].copy(), seq2[:, 4:7].copy(), seq2[:, 7:10].copy(), seq2[:, 10:13].copy()
+        wst = np.full(n, -1.0)
+        if wbc_solver is None:
+            quat, pos, omega, vel = srbd_step(quat, pos, omega, vel, feet, f0, dt, substeps=substeps, plant_inertia=plant_inertia)
+        else:
+            for _ in range(wbc_per_mpc):
+                scene = wbc_target(quat, pos, omega, vel, feet, c0, xpred[:, 1], f0.reshape(n, 12), g)
+                x, _, winfo = wbc_solver.scene_solve(scene)
+                wok = winfo["status"] == 0
+                fw = np.where(wok[:, None, None], x[:, 18:].reshape(n, 4, 3), f0)
+                quat, pos, omega, vel = srbd_step(quat, pos, omega, vel, feet, fw, dt / wbc_per_mpc, substeps=substeps // wbc_per_mpc,
+                                                  plant_inertia=plant_inertia)
+                wst = winfo["status"].astype(float)
+        seq2[:, 0:4], seq2[:, 4:7], seq2[:, 7:10], seq2[:, 10:13] = quat, pos, omega, vel
+        seq2[:, 25] += round(dt * 1e9)
+        hist[k, :, 0:3], hist[k, :, 3:6], hist[k, :, 6:10] = pos, vel, quat
+        hist[k, :, 10] = f0[:, :, 2].sum(axis=1)
+        hist[k, :, 11], hist[k, :, 12], hist[k, :, 13], hist[k, :, 14] = info.return_code, info.acados_num_iter, info.polish_rounds, wst
+        forces_prev, xpred_prev = forces, xpred
+    return hist

@@ -98,6 +98,22 @@ def reduced_tsid_qp(dyn, contacts, a_body_des, a_foot_des, f_ref, tau_max, cfg=G
     return QuadraticProgram(H=H, g=g, A=A, lower_y=lo, upper_y=hi, neq=NEQ)
 
 
+SCENE_IN_DOUBLES = 72  # B200QP_WBC_SCENE_IN_DOUBLES
+
+
+def pack_scene(pos, quat, v_lin, omega, q, qd, contacts, a_body_des, a_foot_des, f_ref):
+    """Input records of the on-device scene assembly (kernel K6, b200qp_wbc_scene_*): [n, 72] doubles = quat xyzw 0:4, pos 4:7,
+    v 7:10, omega 10:13, q 13:25, qd 25:37, a_body_des 37:43, a_foot_des 43:55, f_ref 55:67, contact bit mask 67."""
+    n = pos.shape[0]
+    rec = np.zeros((n, SCENE_IN_DOUBLES))
+    rec[:, 0:4], rec[:, 4:7], rec[:, 7:10], rec[:, 10:13] = quat, pos, v_lin, omega
+    rec[:, 13:25], rec[:, 25:37], rec[:, 37:43] = q, qd, a_body_des
+    rec[:, 43:55] = np.asarray(a_foot_des).reshape(n, 12)
+    rec[:, 55:67] = np.asarray(f_ref).reshape(n, 12)
+    rec[:, 67] = (np.asarray(contacts).astype(np.int64) * np.array([1, 2, 4, 8])).sum(axis=1)
+    return rec
+
+
 def joint_torques(dyn, x):
     """tau = M_j nud + h_j - sum_f J_f[:, 6:]' f_f  (the scene's solver_output -> effort mapping)."""
     nud, f = x[:, :18], x[:, 18:].reshape(-1, 4, 3)
@@ -162,6 +178,47 @@ class BatchedWBCSolver:
         dt = np.dtype([("status", "i4"), ("iterations", "i4"), ("polish_rounds", "i4"), ("n_free", "i4"), ("kkt", "f8", (4,))])
         arr = np.frombuffer(info, dtype=np.uint8, count=48 * n).copy().view(dt)  # bytes copy + view: 10x faster than a structured copy
         return x, arr
+
+    # -- scene assembled on the device (kernel K6) ----------------------------------------------------------------------
+    def scene_configure(self, cfg=GO2_WBC, tau_max=None):
+        """b200qp_wbc_scene_configure: weights / friction of the reduced-TSID scene (mit_controller_sim_go2.yaml:62-72)."""
+        from . import go2_model as gm
+
+        c = _lib.WbcSceneConfig()
+        c.mu = float(cfg["mu"])
+        c.com_pose_weight[:] = [float(v) for v in cfg["com_pose_weight"]]
+        c.foot_force_weight[:] = [float(v) for v in cfg["foot_force_weight"]]
+        c.foot_pose_weight[:] = [float(v) for v in cfg["foot_pose_weight"]]
+        c.hessian_regularizer = float(cfg["hessian_regularizer"])
+        c.tau_max[:] = [float(v) for v in (gm.TAU_MAX if tau_max is None else tau_max)]
+        _lib.check(self._lib.b200qp_wbc_scene_configure(self._h, C.byref(c)), "b200qp_wbc_scene_configure")
+
+    def scene_assemble(self, scene_in):
+        """b200qp_wbc_scene_assemble (parity hook) -> H [n,900], g, A [n,1380], lower_y, upper_y (ABI layout), feet [n,24]."""
+        scene_in = np.ascontiguousarray(scene_in, dtype=np.float64)
+        n = scene_in.shape[0]
+        out = [np.zeros((n, k)) for k in (900, 30, 1380, 46, 46, 24)]
+        rc = self._lib.b200qp_wbc_scene_assemble(self._h, n, scene_in.ctypes.data, *[o.ctypes.data for o in out])
+        _lib.check(rc, "b200qp_wbc_scene_assemble")
+        return out
+
+    def scene_solve(self, scene_in, x=None, tau=None):
+        """b200qp_wbc_scene_solve_batch: robot states -> (x [n,30], tau [n,12], info)."""
+        scene_in = np.ascontiguousarray(scene_in, dtype=np.float64)
+        n = scene_in.shape[0]
+        if scene_in.shape != (n, SCENE_IN_DOUBLES):
+            raise ValueError("scene_in must be [n, 72]")
+        x = np.zeros((n, 30)) if x is None else x
+        tau = np.zeros((n, 12)) if tau is None else tau
+        info = (_lib.SolverInfo * max(n, 1))()
+        rc = self._lib.b200qp_wbc_scene_solve_batch(self._h, n, scene_in.ctypes.data, x.ctypes.data, tau.ctypes.data, C.addressof(info))
+        _lib.check(rc, "b200qp_wbc_scene_solve_batch")
+        dt = np.dtype([("status", "i4"), ("iterations", "i4"), ("polish_rounds", "i4"), ("n_free", "i4"), ("kkt", "f8", (4,))])
+        return x, tau, np.frombuffer(info, dtype=np.uint8, count=48 * n).copy().view(dt)
+
+    def scene_solve_device(self, n, d_scene_in, d_x, d_tau, d_info, sync=True):
+        rc = self._lib.b200qp_wbc_scene_solve_batch_device(self._h, n, d_scene_in, d_x, d_tau, d_info, 1 if sync else 0)
+        _lib.check(rc, "b200qp_wbc_scene_solve_batch_device")
 
     def solve_device(self, n, d_H, d_g, d_A, d_lo, d_hi, d_x, d_info, sync=True):
         rc = self._lib.b200qp_wbc_solve_batch_device(self._h, n, d_H, d_g, d_A, d_lo, d_hi, d_x, d_info, 1 if sync else 0)

@@ -309,6 +309,62 @@ int32_t b200qp_wbc_solve_batch_device(b200qp_wbc *h, int32_t n, const double *d_
                                       b200qp_solver_info *d_info, int32_t sync);
 void *b200qp_wbc_stream(b200qp_wbc *h);
 
+/* ---- the WBC scene assembled on the device (kernel K6) -------------------------------------------------------------------
+ * What `scene->update()` computes on the host in the reference before `scene->solve()` (wbc_arc_opt.cpp:292-297) - Pinocchio's
+ * M(q), h(q, nu), foot Jacobians and Jdot nu for the Go2 (wbc_arc_opt.cpp:30-47,236-241; URDF go2_description.urdf) and the
+ * reduced-TSID QP (task set / weights wbc_arc_opt.cpp:78-123, mit_controller_sim_go2.yaml:62-72) - runs on the GPU, so a solve
+ * takes the robot's state (576 B) instead of the assembled QP (19.5 KB).  Handle must be created with nq = 30, neq = 18, nin = 28.
+ * scene_in per robot, B200QP_WBC_SCENE_IN_DOUBLES doubles:
+ *   [0:4) base quaternion xyzw  [4:7) base position  [7:10) base linear velocity (world)  [10:13) base angular velocity (world)
+ *   [13:25) joint positions (fl, fr, bl, br x abad, hip, knee)  [25:37) joint velocities
+ *   [37:43) desired base acceleration (linear, angular; CartesianPosPDController output, wbc_arc_opt.cpp:256-289)
+ *   [43:55) desired foot accelerations  [55:67) wrench references = MPC GRFs of stage 0 (mit_controller_node.cpp:1006)
+ *   [67] feet in contact, bit f = foot f (UpdateFootContact) */
+#define B200QP_WBC_SCENE_IN_DOUBLES 72
+typedef struct b200qp_wbc_scene_config {
+  double mu;                      /* wbc.friction_coefficient (0.45)                */
+  double com_pose_weight[6];      /* wbc.com_pose_weight: linear xyz, angular xyz   */
+  double foot_force_weight[3];    /* wbc.feet_force_weight                          */
+  double foot_pose_weight[3];     /* wbc.feet_pose_weight                           */
+  double hessian_regularizer;     /* ARC-OPT scene regulariser (1e-8)               */
+  double tau_max[12];             /* joint effort limits of the URDF                */
+} b200qp_wbc_scene_config;
+int32_t b200qp_wbc_scene_configure(b200qp_wbc *h, const b200qp_wbc_scene_config *cfg);
+/* HOST scene_in[n][72] -> x[n][30] = [nu_dot(18), f(12)], tau[n][12] = joint torques of the solution (may be NULL), info[n].
+ * A QP whose solve fails leaves its x / tau rows untouched. */
+int32_t b200qp_wbc_scene_solve_batch(b200qp_wbc *h, int32_t n, const double *scene_in, double *x, double *tau, b200qp_solver_info *info);
+/* Assembly only (parity hook): HOST scene_in -> HOST H[n][900], g[n][30], A[n][1380], lower_y / upper_y[n][46] in the layout of
+ * b200qp_wbc_solve_batch, feet[n][24] = foot positions and velocities (world; may be NULL). */
+int32_t b200qp_wbc_scene_assemble(b200qp_wbc *h, int32_t n, const double *scene_in, double *H, double *g, double *A, double *lower_y,
+                                  double *upper_y, double *feet);
+/* Device-resident variant: d_scene_in[n][72] -> d_x, d_tau (may be NULL), d_info; work is queued on the handle's stream. */
+int32_t b200qp_wbc_scene_solve_batch_device(b200qp_wbc *h, int32_t n, const double *d_scene_in, double *d_x, double *d_tau,
+                                            b200qp_solver_info *d_info, int32_t sync);
+
+/* ---- the closed loop on the device (kernels K7) -----------------------------------------------------------
+ * n single-rigid-body robots (the plant of potato_sim.cpp:92-140: stage-0 GRFs applied at the foot positions + gravity) stepped for
+ * `periods` control periods of length dt (the MPC stage length) with the controller in the loop the way mit_controller_node.cpp
+ * drives one robot: UpdateState -> GetGaitSequence (stateful sequencer, K5b) -> GetWrenchSequence (QP solve) -> and, when a WBC
+ * handle is given, `wbc_per_mpc` times per period: stage-1 prediction / stage-0 GRFs / stage-0 contacts -> WBC target
+ * (mit_controller_node.cpp:1000-1006) -> scene (K6) -> WBC QP (K3) -> the WBC's contact forces drive the plant for dt / wbc_per_mpc.
+ * Nothing is copied to or from the host inside the loop.  b200qp_mpc_set_model and b200qp_mpc_sequencer_configure must have been
+ * called (and b200qp_wbc_scene_configure on the WBC handle, same device, max_batch >= n).
+ * seq2_inout [n][B200QP_SEQ2_IN_DOUBLES]: initial state, feet, clock, Target and gait of every robot; on return the final ones
+ * (column 55 is used by the loop: contact mask of the last period + 16).
+ * history (may be NULL) [periods][n][B200QP_ROLLOUT_HIST_DOUBLES]: pos 0:3, vel 3:6, quat 6:10, sum of applied f_z 10 (MPC stage-0
+ * forces), MPC status 11, iterations 12, polish rounds 13, status of the period's last WBC solve 14 (-1 without WBC). */
+#define B200QP_ROLLOUT_HIST_DOUBLES 16
+typedef struct b200qp_rollout_options {
+  int32_t substeps;       /* plant integration steps per control period (10)                                            */
+  int32_t plant_inertia;  /* 0: Iw = R Ib R' (physical), 1: the reference MPC model's own world inertia (mpc.cpp:60-64)  */
+  int32_t wbc_per_mpc;    /* WBC solves per MPC period when a WBC handle is given (5 = 500 Hz under a 100 Hz MPC)        */
+  int32_t reserved;
+  double com_pose_Kp[6], com_pose_Kd[6];    /* wbc.com_pose_Kp / Kd (linear xyz, angular xyz)  mit_controller_sim_go2.yaml:66-67 */
+  double feet_pose_Kp[3], feet_pose_Kd[3];  /* wbc.feet_pose_Kp / Kd                                                    */
+} b200qp_rollout_options;
+int32_t b200qp_mpc_rollout(b200qp_mpc *h, b200qp_wbc *wbc, int32_t n, int32_t periods, double *seq2_inout,
+                           const b200qp_rollout_options *opt, double *history);
+
 /* library / device info */
 const char *b200qp_version(void);
 int32_t b200qp_device_count(void);

@@ -17,14 +17,15 @@ def available():
     return os.path.exists(os.path.join(CUDA_INC, "cuda_runtime.h")) and os.path.exists("/usr/bin/g++")
 
 
-def build():
-    src = [os.path.join(HERE, "seq_full_host.cpp"), os.path.join(HERE, "emu_preamble.h"),
-           os.path.join(ROOT, "dfki_quad_b200", "csrc", "sequencer_full.cu"), os.path.join(ROOT, "dfki_quad_b200", "csrc", "common.cuh")]
-    if os.path.exists(SO) and all(os.path.getmtime(SO) >= os.path.getmtime(s) for s in src):
-        return SO
-    os.makedirs(os.path.dirname(SO), exist_ok=True)
-    subprocess.check_call(["/usr/bin/g++", "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-w", "-I" + CUDA_INC, "-o", SO, src[0]])
-    return SO
+def build(host="seq_full_host.cpp", kernel="sequencer_full.cu", so=None):
+    so = so or SO
+    src = [os.path.join(HERE, host), os.path.join(HERE, "emu_preamble.h"),
+           os.path.join(ROOT, "dfki_quad_b200", "csrc", kernel), os.path.join(ROOT, "dfki_quad_b200", "csrc", "common.cuh")]
+    if os.path.exists(so) and all(os.path.getmtime(so) >= os.path.getmtime(s) for s in src):
+        return so
+    os.makedirs(os.path.dirname(so), exist_ok=True)
+    subprocess.check_call(["/usr/bin/g++", "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-w", "-I" + CUDA_INC, "-o", so, src[0]])
+    return so
 
 
 class _Model(C.Structure):  # b200qp::SeqModel (common.cuh)
@@ -77,3 +78,25 @@ class HostSequencer:
                                    None if mc is None else mc.ctypes.data_as(C.c_void_p), self.state.ctypes.data_as(C.c_void_p),
                                    rec.ctypes.data_as(C.c_void_p), ct.ctypes.data_as(C.c_void_p), self.stride)
         return rec, ct
+
+
+class _SceneConfig(C.Structure):  # b200qp::WbcSceneConfig (wbc_scene.cu)
+    _fields_ = [("mu", C.c_double), ("com_pose_weight", C.c_double * 6), ("foot_force_weight", C.c_double * 3),
+                ("foot_pose_weight", C.c_double * 3), ("hessian_regularizer", C.c_double), ("tau_max", C.c_double * 12)]
+
+
+def host_wbc_scene(scene_in, cfg, tau_max):
+    """Host build of wbc_scene_kernel: scene_in [n,72] -> (H [n,900], g [n,30], A [n,1380], lo [n,46], hi [n,46], feet [n,24])."""
+    lib = C.CDLL(build("wbc_scene_host.cpp", "wbc_scene.cu", os.path.join(HERE, "_build", "libwbc_scene_host.so")))
+    c = _SceneConfig()
+    c.mu = float(cfg["mu"])
+    c.com_pose_weight[:] = [float(v) for v in cfg["com_pose_weight"]]
+    c.foot_force_weight[:] = [float(v) for v in cfg["foot_force_weight"]]
+    c.foot_pose_weight[:] = [float(v) for v in cfg["foot_pose_weight"]]
+    c.hessian_regularizer = float(cfg["hessian_regularizer"])
+    c.tau_max[:] = [float(v) for v in tau_max]
+    scene_in = np.ascontiguousarray(scene_in, dtype=np.float64)
+    n = scene_in.shape[0]
+    out = [np.zeros((n, k)) for k in (900, 30, 1380, 46, 46, 24)]
+    lib.wbc_scene_host(n, C.byref(c), scene_in.ctypes.data_as(C.c_void_p), *[o.ctypes.data_as(C.c_void_p) for o in out])
+    return out

@@ -96,3 +96,32 @@ def test_host_build_of_the_kernel_option_variants(adaptive, variant):
             rec, ct = seq.sequencer_step(rows, meas)
             assert np.array_equal(ct[0], want_ct[i][r]), (r, i, rob["calls"][i]["cmd"])
             np.testing.assert_allclose(rec[0], want_rec[i][r], rtol=0, atol=1e-11, err_msg=f"robot {r} call {i} {rob['calls'][i]['cmd']}")
+
+
+@needs_emu
+def test_host_build_of_the_wbc_scene_kernel_equals_the_numpy_assembly():
+    """Kernel K6 (wbc_scene.cu: Go2 rigid-body terms + reduced-TSID scene) against go2_model.dynamics + wbc.reduced_tsid_qp."""
+    from dfki_quad_b200 import go2_model as gm
+    from dfki_quad_b200 import wbc
+    from test_host import _oracle_schedule
+
+    n, N = 64, 10
+    zf = np.zeros((n, N, 12))
+    zf[:, :, 2::3] = 40.0
+    xp = np.zeros((n, N + 1, 13))
+    xp[:, :, 5] = 0.3
+    b = wbc.random_wbc_batch(n, seed=11, schedule_fn=_oracle_schedule, mpc_solution=(zf, xp))
+    mb = b["mpc_batch"]
+    scene = wbc.pack_scene(mb["pos"], mb["quat"], mb["vel"], mb["omega"], b["q"], b["qd"], b["contacts"], b["a_body"], b["a_foot"], b["f_ref"])
+    H, g, A, lo, hi, feet = emu.host_wbc_scene(scene, wbc.GO2_WBC, gm.TAU_MAX)
+    qp = b["qp"]
+    Hn = np.transpose(qp.H, (0, 2, 1)).reshape(n, -1)
+    An = np.transpose(qp.A, (0, 2, 1)).reshape(n, -1)
+    assert len({tuple(c) for c in b["contacts"]}) >= 2
+    np.testing.assert_allclose(H, Hn, rtol=0, atol=1e-10)
+    np.testing.assert_allclose(g, qp.g, rtol=0, atol=1e-9)
+    np.testing.assert_allclose(A, An, rtol=0, atol=1e-11)
+    np.testing.assert_allclose(lo, np.clip(qp.lower_y, -1e20, 1e20), rtol=0, atol=1e-10)
+    np.testing.assert_allclose(hi, np.clip(qp.upper_y, -1e20, 1e20), rtol=0, atol=1e-10)
+    np.testing.assert_allclose(feet[:, :12], b["dyn"]["foot_pos"].reshape(n, 12), rtol=0, atol=1e-13)
+    np.testing.assert_allclose(feet[:, 12:], b["dyn"]["foot_vel"].reshape(n, 12), rtol=0, atol=1e-12)
