@@ -28,9 +28,9 @@ WORKLOADS = {
     "config2": dict(name="go2_trot_condensed_mpc_h10_admm", horizon=10, batch=4096, gaits=("TROT",), solver="CONDENSED_ADMM",
                     seed=20261019 + 2, kernel="mpc_admm_kernel<64,60>"),
     "config3": dict(name="go2_mixed_sparse_mpc_h16_riccati", horizon=16, batch=16384, gaits=("TROT", "PACE", "BOUND"),
-                    solver="SPARSE_RICCATI", seed=20261019 + 3, kernel="mpc_riccati_kernel<64>"),
+                    solver="SPARSE_RICCATI", seed=20261019 + 3, kernel="mpc_pcw_kernel<16,1>"),
     "config5": dict(name="go2_1M_mixed_sweep_sharded", horizon=0, batch=1048576, gaits=(), solver="ADMM(N=10 trot) + AUTO(N=16 mixed: condensed kernel where n <= 156, Riccati otherwise)",
-                    seed=20261019 + 5, kernel="mpc_admm_kernel<64,60> + mpc_riccati_kernel<64>"),
+                    seed=20261019 + 5, kernel="mpc_admm_kernel<64,60> + mpc_pcw_kernel<16,1>"),
     "config4": dict(name="go2_wbc_reduced_tsid_qp", horizon=10, batch=16384, gaits=("TROT",), solver="WBC_DENSE_IPM",
                     seed=20261019 + 4, kernel="wbc_qp_kernel"),
 }
@@ -419,7 +419,8 @@ def run_b200(args):
     extras = None
     if args.workload == "config2" and not args.no_extras:
         extras = {}
-        for name, fn in (("config3", extra_config3), ("config4", extra_config4), ("config5_strong", extra_config5), ("fp32", extra_fp32)):
+        for name, fn in (("config3", extra_config3), ("config4", extra_config4), ("config5_strong", extra_config5), ("fp32", extra_fp32),
+                         ("closed_loop_on_device", extra_closed_loop_device)):
             try:
                 extras[name] = fn(args, dev, rank, world)
             except Exception as e:  # an extra never costs the headline line
@@ -542,8 +543,10 @@ def extra_config3(args, dev, rank, world, steps=3):
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
     out = {}
     raw = {}
-    for key, solver, kw in (("riccati_kernel", "SPARSE_RICCATI", {}), ("partial_condensing_cond_N_4", "PARTIAL_CONDENSING", dict(condensing_N=4)),
-                            ("auto", "AUTO", {})):
+    # riccati_kernel: the warp-per-problem Riccati IPM (mpc_pcw.cu), its default pairs stages (cond_N = N / 2); the cond_N = N run is the
+    # same kernel with single-stage blocks (the fully sparse end of the reference's cond_N axis, mpc.cpp:219-225)
+    for key, solver, kw in (("riccati_kernel", "SPARSE_RICCATI", {}), ("riccati_kernel_cond_N_16", "SPARSE_RICCATI", dict(condensing_N=16)),
+                            ("partial_condensing_cond_N_4", "PARTIAL_CONDENSING", dict(condensing_N=4)), ("auto", "AUTO", {})):
         mpc = BatchedMPC(cfg["alpha"], cfg["state_weights_move"], cfg["mu"], cfg["fmin"], cfg["fmax"], solver, horizon=N, dt=cfg["dt"],
                          max_batch=B, device=dev, **kw)
         ext = torch.cuda.ExternalStream(mpc.stream(), device=dev)
@@ -587,6 +590,52 @@ def extra_config3(args, dev, rank, world, steps=3):
                                            "at the GPU kernels' tolerance; SPEED / BALANCE-like caps beside it"}
     out["config"] = {"workload": wl["name"], "horizon": N, "batch_per_gpu": B, "gaits": "/".join(wl["gaits"]), "steps": steps,
                      "l2": "256 MiB flush between timed iterations"}
+    return out
+
+
+def extra_closed_loop_device(args, dev, rank, world, n=4096, periods=20):
+    """n robots x `periods` control periods with sequencer + MPC (+ 5 WBC solves per period) in the loop, everything
+    device-resident (b200qp_mpc_rollout); wall clock of the call, i.e. including the one H2D of the initial and D2H of the final states."""
+    from dfki_quad_b200 import BatchedMPC, gait as gaitmod, pack_seq2, sequencer as sq, wbc
+
+    rng = np.random.Generator(np.random.PCG64(20261019 + 40 + rank))
+    c = sq.GO2_MPC
+    m = BatchedMPC(c["alpha"], c["state_weights_move"], c["mu"], c["fmin"], c["fmax"], "CONDENSED_ADMM", horizon=10, dt=c["dt"], max_batch=n, device=dev,
+                   warm_start=1)
+    m.set_model(sq.GO2_MASS, sq.GO2_INERTIA, sq.GO2_COM, sq.GO2_SHOULDERS, sq.RAIBERT_K, sq.RAIBERT_G, sq.MAX_LEG_LENGTH)
+    w = wbc.BatchedWBCSolver(max_batch=n, device=dev)
+    w.scene_configure()
+    yaw = rng.uniform(-np.pi, np.pi, n)
+    quat = sq._yaw_quat(yaw)
+    pos = np.stack([rng.uniform(-1, 1, n), rng.uniform(-1, 1, n), np.full(n, 0.30)], axis=-1)
+    feet = pos[:, None, :] + np.einsum("nij,lj->nli", sq.quat_to_rot(quat), sq.GO2_SHOULDERS)
+    feet[:, :, 2] = 0.0
+    period, duty, offset = gaitmod.gait_arrays(np.full(n, gaitmod.GAIT_NAMES.index("TROT")))
+    target = dict(hybrid_x_dot=0.4, hybrid_y_dot=0.1, wz=0.3, wx=0.0, wy=0.0, roll=0.0, pitch=0.0, z=0.30)
+    seq0 = pack_seq2(np.concatenate([quat, pos, np.zeros((n, 6))], axis=1), feet, rng.integers(0, 500_000_000, n).astype(np.float64), target,
+                     (period, duty, offset))
+    out = {}
+    for name, wb, cdt, sub in (("mpc_only_period_50ms", None, 0.0, 10), ("mpc_100hz_wbc_500hz", w, 0.01, 5)):
+        m.sequencer_configure("simple", early_contact_detection=0)
+        m.SetWarmStart(1)
+        m.rollout(seq0.copy(), 2, wbc=wb, plant_inertia="reference_model", history=False, control_dt=cdt, substeps=sub)  # warm-up
+        m.sequencer_configure("simple", early_contact_detection=0)
+        m.SetWarmStart(1)
+        seq = seq0.copy()
+        t0 = time.perf_counter()
+        hist = m.rollout(seq, periods, wbc=wb, plant_inertia="reference_model", control_dt=cdt, substeps=sub)
+        dt_s = time.perf_counter() - t0
+        (t_m,), _ = _reduce(world, dev, [dt_s], [0])
+        ok = float((hist[:, :, 11] == 0).mean())
+        out[name] = {"robot_periods_per_s": world * n * periods / t_m, "mpc_solves_per_s": world * n * periods / t_m,
+                     "wbc_solves_per_s": (world * n * periods * 5 / t_m) if wb is not None else 0.0, "seconds": t_m, "mpc_converged_fraction": ok,
+                     "wbc_converged_fraction": float((hist[:, :, 14] == 0).mean()) if wb is not None else None,
+                     "height_error_max_m": float(np.abs(hist[-1, :, 2] - 0.30).max()), "control_period_s": cdt if cdt > 0 else 0.05,
+                     "real_time_factor": (n * periods * (cdt if cdt > 0 else 0.05)) / t_m / n}
+    out["config"] = {"robots_per_gpu": n, "control_periods": periods, "gait": "TROT", "horizon": 10, "warm_start": 1,
+                     "note": "real_time_factor = simulated seconds per wall second for the whole batch; host work inside the loop: none (kernel launches only)"}
+    m.close()
+    w.close()
     return out
 
 
@@ -636,11 +685,25 @@ def extra_config4(args, dev, rank, world, steps=3):
         _, inf = solver.solve_abi(Hp, gp, Ap, lop, hip, xh)
     e2e_s = time.perf_counter() - t0
     conv_e2e = int(((inf["status"] == 0) & (inf["kkt"].max(axis=1) <= KKT_TOL)).sum())
-    (ms_m, e2e_m), (c1, c2) = _reduce(world, dev, [ms, e2e_s], [conv * steps, conv_e2e * steps])
+    # the same QPs entered as robot states (576 B each): scene assembled on the device (kernel K6), then the same QP kernel
+    mb = b["mpc_batch"]
+    scene = torch.from_numpy(wbc.pack_scene(mb["pos"], mb["quat"], mb["vel"], mb["omega"], b["q"], b["qd"], b["contacts"], b["a_body"], b["a_foot"],
+                                            b["f_ref"])).pin_memory().numpy()
+    solver.scene_configure()
+    tau_h = np.zeros((B, 12))
+    solver.scene_solve(scene, xh, tau_h)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        _, _, inf_s = solver.scene_solve(scene, xh, tau_h)
+    scene_s = time.perf_counter() - t0
+    conv_scene = int(((inf_s["status"] == 0) & (inf_s["kkt"].max(axis=1) <= KKT_TOL)).sum())
+    (ms_m, e2e_m, scene_m), (c1, c2, c3) = _reduce(world, dev, [ms, e2e_s, scene_s], [conv * steps, conv_e2e * steps, conv_scene * steps])
     out = {"metric": "WBC task-space QP solves/sec (Go2 reduced TSID, 30 vars, 18 eq, 28 ineq)", "value": c1 / (ms_m * 1e-3), "unit": "solves/s",
            "ms_per_step": ms_m / steps, "e2e": {"value": c2 / e2e_m, "unit": "solves/s", "h2d_bytes_per_step": int(B * 19512), "d2h_bytes_per_step": int(B * 288)},
            "converged_fraction": c1 / (B * steps * world), "mean_iterations": float(info["iterations"].mean()),
            "kkt_max_converged": float(info["kkt"][(info["status"] == 0)].max()),
+           "e2e_scene_on_device": {"value": c3 / scene_m, "unit": "solves/s", "h2d_bytes_per_step": int(B * (576 + 240)), "d2h_bytes_per_step": int(B * (240 + 96 + 48)),
+                                   "note": "b200qp_wbc_scene_solve_batch: robot state in (576 B), rigid-body terms + TSID scene assembled by kernel K6, x + joint torques out"},
            "config": {"workload": wl["name"], "batch_per_gpu": B, "steps": steps, "l2": "256 MiB flush between timed iterations"}}
     if rank == 0 and not args.no_cpu_baseline:
         from oracle import c_oracle

@@ -62,7 +62,7 @@ class WbcSceneConfig(C.Structure):
 class RolloutOptions(C.Structure):
     _fields_ = [("substeps", C.c_int32), ("plant_inertia", C.c_int32), ("wbc_per_mpc", C.c_int32), ("reserved", C.c_int32),
                 ("com_pose_Kp", C.c_double * 6), ("com_pose_Kd", C.c_double * 6), ("feet_pose_Kp", C.c_double * 3),
-                ("feet_pose_Kd", C.c_double * 3)]
+                ("feet_pose_Kd", C.c_double * 3), ("control_dt", C.c_double)]
 
 
 class SeqModel(C.Structure):

@@ -95,6 +95,7 @@ struct b200qp_mpc {
   int stream_chunk = 0;                      // problems per chunk while a streamed solve is being issued, else 0
   // warm / hot start: previous solution per problem slot
   double *d_warm_x = nullptr, *d_warm_y = nullptr;
+  double ipm_warm_mu = 0.1;  // B200QP_IPM_WARM_MU overrides (experiments)
   uint8_t *d_warm_valid = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join[4] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -174,6 +175,9 @@ static void fill_params(b200qp_mpc *h) {
   P.polish_rounds = c.polish_max_rounds > 0 ? c.polish_max_rounds : 8;
   P.ipm_max_iter = c.ipm_max_iter > 0 ? c.ipm_max_iter : 40;
   P.precision = c.precision;
+  P.ipm_warm_x = nullptr;
+  P.ipm_warm_valid = nullptr;
+  P.ipm_warm_mu = 1.0;
   if (c.precision == 2 && !(c.kkt_tol > 0)) P.kkt_tol = 5e-2;  // FP32 polish: stationarity of O(1e-3) is all there is
 }
 
@@ -315,6 +319,7 @@ int32_t b200qp_mpc_create(const b200qp_mpc_config *cfg, b200qp_mpc **out) {
   }
   if (cfg->solver == B200QP_SOLVER_SPARSE_RICCATI) {
     h->ric_legacy = getenv("B200QP_RICCATI_LEGACY") != nullptr;
+    if (const char *wm = getenv("B200QP_IPM_WARM_MU")) h->ipm_warm_mu = atof(wm) > 0 ? atof(wm) : h->ipm_warm_mu;
     // blocks of the warp-per-problem kernel: cond_N as given (cond_N = horizon: one stage per block, the sparse formulation proper);
     // default: two stages per block - same Newton direction, fewer and better filled block factorisations
     h->pcw_cond = (cfg->cond_N > 0 && cfg->cond_N <= cfg->horizon) ? cfg->cond_N : (cfg->horizon + 1) / 2;
@@ -520,7 +525,13 @@ static int32_t solve_device_impl(b200qp_mpc *h, int32_t n, const double *d_in, c
     // from there to the block kernel (d_bin_count[12], [13] = lengths of the hand-over lists, [14], [15], [9] = work counters)
     double *lb = h->want_duals ? h->d_lam_box : nullptr, *lg = h->want_duals ? h->d_lam_g : nullptr;
     int *rej0 = h->d_pcw_rej, *rej1 = h->d_pcw_rej + n;
-    CK(launch_mpc_pcw(h->P, n, d_in, d_contact, d_forces, d_xpred, d_info, lb, lg, h->d_pcw_scratch[0], h->d_bin_count + 14, h->pcw_grid[0],
+    MpcParams Pw = h->P;
+    if (h->cfg.warm_start > 0 && h->d_warm_x != nullptr && dbg_index < 0) {  // IPM warm start: previous forces of the slot
+      Pw.ipm_warm_x = h->d_warm_x;
+      Pw.ipm_warm_valid = h->d_warm_valid;
+      Pw.ipm_warm_mu = h->ipm_warm_mu;
+    }
+    CK(launch_mpc_pcw(Pw, n, d_in, d_contact, d_forces, d_xpred, d_info, lb, lg, h->d_pcw_scratch[0], h->d_bin_count + 14, h->pcw_grid[0],
                       h->stream, nullptr, nullptr, rej0, h->d_bin_count + 12, h->pcw_cond, 1, h->d_dbg_cycles));
     (void)rej1;
     CK(launch_mpc_riccati(h->P, n, d_in, d_contact, d_forces, d_xpred, d_info, lb, lg, h->d_ric_scratch, h->d_bin_count + 9, h->ric_grid,
@@ -1425,7 +1436,7 @@ int32_t b200qp_mpc_rollout(b200qp_mpc *h, b200qp_wbc *w, int32_t n, int32_t peri
   cudaStream_t st = h->stream;
   CK(cudaMemcpyAsync(h->d_seq2, seq2_inout, sb, cudaMemcpyHostToDevice, st));
   CK(cudaMemsetAsync(h->d_measured, 1, nn * 4, st));  // first period: every foot measured in contact
-  const double dt = h->cfg.dt, dt_ns = (double)llround(dt * 1e9);
+  const double dt = opt->control_dt > 0 ? opt->control_dt : h->cfg.dt, dt_ns = (double)llround(dt * 1e9);
   int launches = 0;
   for (int k = 0; k < periods; ++k) {
     CK(launch_sequencer_full(n, h->model, h->seq_opt, h->d_seq2, h->d_measured, h->d_seq_state, h->d_in, h->d_contact, h->P.in_stride, st));

@@ -20,6 +20,10 @@ struct MpcParams {
   double rho0, sigma, relax, eps, kkt_tol;
   int max_iter, check_every, polish_rounds, ipm_max_iter;
   int precision;  // 0 FP64 (product); 1 / 2: FP32 error study of the condensed kernel (b200qp_mpc_config.precision)
+  // warm start of the interior-point kernel (b200qp_mpc_config.warm_start, mpc.cpp:236-237): previous forces per problem slot
+  double *ipm_warm_x;        // [max_batch][N][12] or nullptr
+  uint8_t *ipm_warm_valid;   // [max_batch]
+  double ipm_warm_mu;        // complementarity the warm-started slack / multiplier pairs begin at
 };
 
 // model constants of the gait sequencer kernels (b200qp_seq_model + the handle's dt / horizon)

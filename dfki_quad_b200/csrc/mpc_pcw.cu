@@ -243,14 +243,30 @@ __global__ void __launch_bounds__(32) mpc_pcw_kernel(const MpcParams P, int npro
         gXref[12 * k + 9 + c] = st[10 + c];
       }
     }
-    // starting point: every stance foot carries its share of the weight (strictly inside the pyramid and the box)
+    // starting point: every stance foot carries its share of the weight (strictly inside the pyramid and the box).  Warm start
+    // (mpc.cpp:236-237): 0.9 x the slot's previous solution + 0.1 x that point - a convex combination of a feasible and a strictly
+    // interior point is strictly interior; a foot-stage that was in swing before (zero force) starts cold.
+    const bool warm = P.ipm_warm_x != nullptr && P.ipm_warm_valid[prob] != 0;
     for (int j = lane; j < nfs; j += 32) {
       const int k = sFs[j] >> 2;
       const int ns = sSt[k + 1] - sSt[k];
       const double span = P.fmax - P.fmin;
-      sU[3 * j] = 0.0;
-      sU[3 * j + 1] = 0.0;
-      sU[3 * j + 2] = fmin(fmax(mass * GRAVITY_CONSTANT / (double)ns, P.fmin + 0.05 * span), P.fmax - 0.05 * span);
+      const double fz0 = fmin(fmax(mass * GRAVITY_CONSTANT / (double)ns, P.fmin + 0.05 * span), P.fmax - 0.05 * span);
+      double u0 = 0.0, u1 = 0.0, u2 = fz0;
+      if (warm) {
+        const double *wp = P.ipm_warm_x + (size_t)prob * N * 12 + 3 * sFs[j];
+        const double w0 = wp[0], w1 = wp[1], w2 = wp[2];
+        const bool usable = w2 > 0.0 && w2 <= P.fmax && fabs(w0) <= mu_f * w2 * (1.0 + 1e-9) && fabs(w1) <= mu_f * w2 * (1.0 + 1e-9) &&
+                            fabs(w0) <= P.fmax && fabs(w1) <= P.fmax && w2 >= P.fmin;
+        if (usable) {
+          u0 = 0.9 * w0;
+          u1 = 0.9 * w1;
+          u2 = 0.9 * w2 + 0.1 * fz0;
+        }
+      }
+      sU[3 * j] = u0;
+      sU[3 * j + 1] = u1;
+      sU[3 * j + 2] = u2;
     }
     __syncwarp();
     const int nb = sNb;
@@ -355,7 +371,7 @@ __global__ void __launch_bounds__(32) mpc_pcw_kernel(const MpcParams P, int npro
 #pragma unroll
       for (int r = 0; r < 10; ++r) {
         s[q][r] = fmax(hh[r] - g0[r], 1e-2);
-        z[q][r] = 1.0 / s[q][r];
+        z[q][r] = (warm ? P.ipm_warm_mu : 1.0) / s[q][r];
         inv_s[q][r] = 1.0;
       }
     }
@@ -854,6 +870,15 @@ __global__ void __launch_bounds__(32) mpc_pcw_kernel(const MpcParams P, int npro
         double *f3 = fo + 3 * sFs[j];
         f3[0] = sU[3 * j]; f3[1] = sU[3 * j + 1]; f3[2] = sU[3 * j + 2];
       }
+      if (P.ipm_warm_x != nullptr) {  // remember this solution for the next call on the same slot
+        double *wo = P.ipm_warm_x + (size_t)prob * N * 12;
+        for (int e = lane; e < N * 12; e += 32) wo[e] = 0.0;
+        __syncwarp();
+        for (int j = lane; j < nfs; j += 32) {
+          double *f3 = wo + 3 * sFs[j];
+          f3[0] = sU[3 * j]; f3[1] = sU[3 * j + 1]; f3[2] = sU[3 * j + 2];
+        }
+      }
       double *xo = xpred + (size_t)prob * (N + 1) * 13;
       for (int e = lane; e < (N + 1) * 13; e += 32) {
         const int k = e / 13, c = e - 13 * k;
@@ -876,6 +901,7 @@ __global__ void __launch_bounds__(32) mpc_pcw_kernel(const MpcParams P, int npro
       }
     }
     if (lane == 0) {
+      if (P.ipm_warm_x != nullptr) P.ipm_warm_valid[prob] = (status == B200QP_ACADOS_SUCCESS) ? 1 : 0;
       b200qp_solver_info inf;
       inf.status = status;
       inf.iterations = iter;

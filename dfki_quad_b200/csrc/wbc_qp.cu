@@ -34,6 +34,28 @@ __device__ __forceinline__ double wblock_reduce(double v, double *red, Op op) {
   for (int w = 1; w < nw; ++w) m = op(m, red[w]);
   return m;
 }
+// min over the block of two values at once (one pair of barriers instead of two); red must hold 16 doubles
+__device__ __forceinline__ void wblock_min2(double &a, double &b, double *red) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a = fmin(a, __shfl_xor_sync(0xffffffffu, a, o));
+    b = fmin(b, __shfl_xor_sync(0xffffffffu, b, o));
+  }
+  __syncthreads();
+  if (lane == 0) {
+    red[warp] = a;
+    red[8 + warp] = b;
+  }
+  __syncthreads();
+  double ma = red[0], mb = red[8];
+  for (int w = 1; w < nw; ++w) {
+    ma = fmin(ma, red[w]);
+    mb = fmin(mb, red[8 + w]);
+  }
+  a = ma;
+  b = mb;
+}
 struct WMax { __device__ double operator()(double a, double b) const { return fmax(a, b); } };
 struct WMin { __device__ double operator()(double a, double b) const { return fmin(a, b); } };
 struct WSum { __device__ double operator()(double a, double b) const { return a + b; } };
@@ -153,7 +175,7 @@ __global__ void __launch_bounds__(64, 5) wbc_qp_kernel(const WbcParams P, int np
   double *sdx2 = sbx + nq;          // [nq] refinement step
   double *sdnu2 = sdx2 + nq;        // [me]
   double *sre2 = sdnu2 + me;        // [me]
-  double *red = sre2 + me;          // [8]
+  double *red = sre2 + me;          // [16]
   __shared__ int sSlot;
   const int tid = threadIdx.x, BS = blockDim.x;
 
@@ -394,8 +416,7 @@ __global__ void __launch_bounds__(64, 5) wbc_qp_kernel(const WbcParams P, int np
           if (nsu < 0.0) stp = fmin(stp, -su / nsu);
           if (nzu < 0.0) stq = fmin(stq, -zu / nzu);
         }
-        stp = wblock_reduce(stp, red, WMin());
-        stq = wblock_reduce(stq, red, WMin());
+        wblock_min2(stp, stq, red);
         if (pass == 0) {
           const double g2 = wblock_reduce((hasl ? (sl + stp * nsl) * (zl + stq * nzl) : 0.0) + (hasu ? (su + stp * nsu) * (zu + stq * nzu) : 0.0), red, WSum());
           const double ratio = (g2 / mtot) / fmax(mu_c, 1e-300);
@@ -435,7 +456,7 @@ __global__ void __launch_bounds__(64, 5) wbc_qp_kernel(const WbcParams P, int np
 
 size_t wbc_smem_bytes(const WbcParams &P) {
   const size_t nq = P.nq, me = P.neq, mi = P.nin;
-  const size_t d = nq * nq * 2 + me * nq + mi * nq + nq * me + me * me + 10 * nq + 7 * me + (nq > me ? nq : me) + mi + 8;
+  const size_t d = nq * nq * 2 + me * nq + mi * nq + nq * me + me * me + 10 * nq + 7 * me + (nq > me ? nq : me) + mi + 16;
   return d * sizeof(double) + 64;
 }
 

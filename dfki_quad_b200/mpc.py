@@ -352,7 +352,7 @@ class BatchedMPC:
         return forces, xpred, self._info(info, n)
 
     # -- closed loop on the device (b200qp_mpc_rollout) -------------------------------------------------------------------
-    def rollout(self, seq2, periods, wbc=None, substeps=10, plant_inertia="physical", wbc_per_mpc=5, gains=None, history=True):
+    def rollout(self, seq2, periods, wbc=None, substeps=10, plant_inertia="physical", wbc_per_mpc=5, gains=None, history=True, control_dt=0.0):
         """b200qp_mpc_rollout: `periods` control periods of n single-rigid-body robots with the sequencer + MPC (+ the WBC of the
         BatchedWBCSolver `wbc`, scene configured) in the loop, all on the device.  seq2 [n,64] is updated in place to the final
         state; returns the history [periods, n, 16] (pos, vel, quat, sum f_z, MPC status, iterations, polish rounds, WBC status)."""
@@ -360,7 +360,7 @@ class BatchedMPC:
             raise ValueError("seq2 must be a C-contiguous float64 [n, 64] array (it is updated in place)")
         n = seq2.shape[0]
         o = _lib.RolloutOptions()
-        o.substeps, o.wbc_per_mpc = int(substeps), int(wbc_per_mpc)
+        o.substeps, o.wbc_per_mpc, o.control_dt = int(substeps), int(wbc_per_mpc), float(control_dt)
         o.plant_inertia = {"physical": 0, "reference_model": 1}[plant_inertia]
         g = gains or dict(com_pose_Kp=[300.0] * 3 + [200.0] * 3, com_pose_Kd=[100.0] * 6, feet_pose_Kp=[1200.0] * 3, feet_pose_Kd=[500.0, 500.0, 400.0])
         for k in ("com_pose_Kp", "com_pose_Kd", "feet_pose_Kp", "feet_pose_Kd"):

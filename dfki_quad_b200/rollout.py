@@ -160,11 +160,11 @@ def wbc_target(quat, pos, omega, vel, feet, mask, x1, f0, gains):
     return wbc.pack_scene(pos, quat, vel, omega, q, qd, mask, a_body, np.zeros((n, 4, 3)), f0.reshape(n, 4, 3))
 
 
-def closed_loop_stateful(mpc, seq2, periods, wbc_solver=None, substeps=10, plant_inertia="physical", wbc_per_mpc=5, gains=None):
+def closed_loop_stateful(mpc, seq2, periods, wbc_solver=None, substeps=10, plant_inertia="physical", wbc_per_mpc=5, gains=None, control_dt=0.0):
     """What b200qp_mpc_rollout does, with the plant, the foot bookkeeping and the MPC -> WBC coupling stepped on the HOST in numpy and one
     library call per solve (mpc.sequencer_step / solve_records, wbc_solver.scene_solve) - the reference the device loop is tested
     against.  seq2 [n,64] is updated in place; returns the same history array."""
-    n, N, dt = seq2.shape[0], mpc.N, 0.05
+    n, N, dt = seq2.shape[0], mpc.N, (control_dt if control_dt > 0 else 0.05)
     g = gains or dict(com_pose_Kp=[300.0] * 3 + [200.0] * 3, com_pose_Kd=[100.0] * 6, feet_pose_Kp=[1200.0] * 3, feet_pose_Kd=[500.0, 500.0, 400.0])
     hist = np.zeros((periods, n, 16))
     meas = np.ones((n, 4), dtype=np.uint8)

@@ -343,10 +343,10 @@ int32_t b200qp_wbc_scene_solve_batch_device(b200qp_wbc *h, int32_t n, const doub
 
 /* ---- the closed loop on the device (kernels K7) -----------------------------------------------------------
  * n single-rigid-body robots (the plant of potato_sim.cpp:92-140: stage-0 GRFs applied at the foot positions + gravity) stepped for
- * `periods` control periods of length dt (the MPC stage length) with the controller in the loop the way mit_controller_node.cpp
+ * `periods` control periods (length control_dt, default the MPC stage length) with the controller in the loop the way mit_controller_node.cpp
  * drives one robot: UpdateState -> GetGaitSequence (stateful sequencer, K5b) -> GetWrenchSequence (QP solve) -> and, when a WBC
  * handle is given, `wbc_per_mpc` times per period: stage-1 prediction / stage-0 GRFs / stage-0 contacts -> WBC target
- * (mit_controller_node.cpp:1000-1006) -> scene (K6) -> WBC QP (K3) -> the WBC's contact forces drive the plant for dt / wbc_per_mpc.
+ * (mit_controller_node.cpp:1000-1006) -> scene (K6) -> WBC QP (K3) -> the WBC's contact forces drive the plant for control_dt / wbc_per_mpc.
  * Nothing is copied to or from the host inside the loop.  b200qp_mpc_set_model and b200qp_mpc_sequencer_configure must have been
  * called (and b200qp_wbc_scene_configure on the WBC handle, same device, max_batch >= n).
  * seq2_inout [n][B200QP_SEQ2_IN_DOUBLES]: initial state, feet, clock, Target and gait of every robot; on return the final ones
@@ -361,6 +361,8 @@ typedef struct b200qp_rollout_options {
   int32_t reserved;
   double com_pose_Kp[6], com_pose_Kd[6];    /* wbc.com_pose_Kp / Kd (linear xyz, angular xyz)  mit_controller_sim_go2.yaml:66-67 */
   double feet_pose_Kp[3], feet_pose_Kd[3];  /* wbc.feet_pose_Kp / Kd                                                    */
+  double control_dt;      /* length of a control period = time between MPC solves (MPC_CONTROL_DT = 0.01 in the reference,
+                             mit_controller_params.hpp:8); 0: the MPC stage length dt                                   */
 } b200qp_rollout_options;
 int32_t b200qp_mpc_rollout(b200qp_mpc *h, b200qp_wbc *wbc, int32_t n, int32_t periods, double *seq2_inout,
                            const b200qp_rollout_options *opt, double *history);

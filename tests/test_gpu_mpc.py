@@ -776,3 +776,35 @@ def test_riccati_two_cycle_regression():
     assert ir.acados_num_iter.max() <= 25
     scale = np.maximum(1.0, np.abs(fa).reshape(64, -1).max(axis=1))
     assert (np.abs(fr - fa).reshape(64, -1).max(axis=1) / scale).max() <= 1e-5
+
+
+def test_interior_point_warm_start_saves_iterations_and_keeps_the_optimum():
+    """warm_start = 1 with solver SPARSE_RICCATI (MPC::MPC(..., warm_start), mpc.cpp:236-237): the warp kernel starts from 0.9 x the slot's
+    previous forces + 0.1 x the cold interior point with complementarity 0.1; same optimum as the cold solve, fewer iterations."""
+    from dfki_quad_b200 import BatchedMPC, sequencer
+
+    N, n = 16, 2048
+    c = sequencer.GO2_MPC
+    b = sequencer.random_batch(n, N, seed=5, gaits=("TROT", "PACE", "BOUND"))
+    rng = np.random.default_rng(1)
+    rec2 = b["rec"].copy()
+    rec2[:, 4:7] += rng.normal(0, 3e-3, (n, 3))
+    rec2[:, 7:13] += rng.normal(0, 2e-2, (n, 6))
+    args = (c["alpha"], c["state_weights_move"], c["mu"], c["fmin"], c["fmax"], "SPARSE_RICCATI")
+    cold = BatchedMPC(*args, horizon=N, dt=c["dt"], max_batch=n)
+    fc, xc, ic = cold.solve_records(rec2, b["contact"])
+    warm = BatchedMPC(*args, horizon=N, dt=c["dt"], max_batch=n, warm_start=1)
+    f0, _, i0 = warm.solve_records(b["rec"], b["contact"])       # nothing stored yet: a cold solve
+    assert abs(i0.acados_num_iter.mean() - ic.acados_num_iter.mean()) < 0.5
+    f1, x1, i1 = warm.solve_records(rec2, b["contact"])
+    ok = i1.success & ic.success
+    assert ok.mean() > 0.999
+    assert i1.acados_num_iter[ok].mean() < ic.acados_num_iter[ok].mean() - 1.0
+    sc = np.maximum(1.0, np.abs(fc).reshape(n, -1).max(axis=1))
+    err = np.abs(f1 - fc).reshape(n, -1).max(axis=1) / sc
+    assert err[ok].max() <= 5e-5 and np.quantile(err[ok], 0.999) <= 1e-5
+    warm.SetWarmStart(0)
+    f2, _, i2 = warm.solve_records(rec2, b["contact"])
+    assert np.array_equal(f2[ok], fc[ok])  # warm start off again: the cold solve, bit for bit
+    cold.close()
+    warm.close()

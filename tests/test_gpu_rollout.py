@@ -58,15 +58,16 @@ def test_device_loop_equals_the_host_stepped_loop(plant_inertia, yaw_range):
 def test_device_loop_with_the_wbc_in_it_equals_the_host_stepped_loop():
     from dfki_quad_b200 import rollout, wbc
 
-    n, periods = 48, 6
+    n, periods = 48, 12
     m1, seq = _setup(n, seed=2, yaw_range=0.03)
     m2, _ = _setup(n, seed=2, yaw_range=0.03)
     w1, w2 = wbc.BatchedWBCSolver(max_batch=n), wbc.BatchedWBCSolver(max_batch=n)
     w1.scene_configure()
     w2.scene_configure()
     s1, s2 = seq.copy(), seq.copy()
-    h_dev = m1.rollout(s1, periods, wbc=w1, substeps=10, wbc_per_mpc=5)
-    h_host = rollout.closed_loop_stateful(m2, s2, periods, wbc_solver=w2, substeps=10, wbc_per_mpc=5)
+    # the reference's rates: MPC every 10 ms (MPC_CONTROL_DT), WBC every 2 ms
+    h_dev = m1.rollout(s1, periods, wbc=w1, substeps=5, wbc_per_mpc=5, control_dt=0.01)
+    h_host = rollout.closed_loop_stateful(m2, s2, periods, wbc_solver=w2, substeps=5, wbc_per_mpc=5, control_dt=0.01)
     assert (h_dev[:, :, 14] == 0).mean() > 0.98 and (h_dev[:, :, 11] == 0).mean() > 0.98
     assert np.array_equal(h_dev[:, :, 11], h_host[:, :, 11]) and np.array_equal(h_dev[:, :, 14], h_host[:, :, 14])
     np.testing.assert_allclose(h_dev[:, :, 0:10], h_host[:, :, 0:10], rtol=0, atol=1e-6)

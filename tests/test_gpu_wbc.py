@@ -130,3 +130,21 @@ def test_every_config4_qp_converges():
     assert info["kkt"].max() <= 1e-6
     assert info["iterations"].max() <= 30
     s.close()
+
+
+def test_hard_wbc_qps_regression():
+    """tests/golden/wbc_hard.npz: ten config-4 QPs on which the earlier step rule (one step length for s and z, sigma -> 0) stalled
+    or cycled; x there is the active-set oracle's solution (KKT <= 3e-9)."""
+    import os
+
+    from dfki_quad_b200 import wbc
+
+    d = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "wbc_hard.npz"))
+    n = d["g"].shape[0]
+    s = wbc.BatchedWBCSolver(max_batch=n)
+    x, info = s.solve_abi(d["H"], d["g"], d["A"], d["lo"], d["hi"])
+    assert (info["status"] == 0).all(), info["status"]
+    assert info["iterations"].max() <= 30
+    scale = np.abs(d["x"]).max(axis=1, keepdims=True)
+    assert (np.abs(x - d["x"]) / scale).max() <= 1e-7
+    s.close()

@@ -152,3 +152,17 @@ def test_scalar_sequencer_invariants(go2_params):
     assert np.all(d["foot_pos"][contact == 0] == 0.0)  # swing feet get the zero vector (raibert_foot_step_planner.cpp:125)
     assert np.allclose(np.linalg.norm(d["des_quat"], axis=1), 1.0)
     assert np.allclose(d["des_pos"][1:, 2], 0.30)
+
+
+def test_c_wbc_restatement_solves_the_hard_fixture():
+    """oracle/wbc_ref.c (same method as the device kernel) on tests/golden/wbc_hard.npz against the active-set oracle's solutions."""
+    import os
+
+    from oracle import c_oracle
+
+    if not c_oracle.available():
+        pytest.skip("C oracle not built")
+    d = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "wbc_hard.npz"))
+    x, info, solved = c_oracle.wbc_batch(d["H"], d["g"], d["A"], d["lo"], d["hi"], 18)
+    assert solved == d["g"].shape[0]
+    assert np.abs(x - d["x"]).max() <= 1e-8 * np.abs(d["x"]).max()
