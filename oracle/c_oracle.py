@@ -1,5 +1,5 @@
 """ctypes binding of oracle/_build/libmpc_oracle.so (C restatement of the reference CPU path).
-TEST / MEASUREMENT INFRASTRUCTURE ONLY.  PARITY UNPINNED (see mpc_ref.c header)."""
+TEST / MEASUREMENT INFRASTRUCTURE ONLY.  Pinning status: see the mpc_ref.c header (QP data pinned on oracle/_ref, solver restated)."""
 from __future__ import annotations
 
 import ctypes as C

@@ -1,5 +1,5 @@
 """Timing harness for the restated reference CPU path (bench.py `cpu_baseline` leg and `--impl reference`).
-TEST / MEASUREMENT INFRASTRUCTURE ONLY - never on the product path.  PARITY UNPINNED (see mpc_oracle.py).
+TEST / MEASUREMENT INFRASTRUCTURE ONLY - never on the product path.  Pinning status: see mpc_oracle.py.
 
 Uses the C port (oracle/_build/libmpc_oracle.so: OSQP-style ADMM + polish on the condensed QP, OpenMP over the
 batch) when it has been built, else the numpy port (one core)."""

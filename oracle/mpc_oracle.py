@@ -3,12 +3,15 @@
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg may import
 this module.  The product path (dfki_quad_b200/) never does.
 
-PARITY UNPINNED: the reference (/root/reference) ships no golden vectors, unit tests or fixtures for
-this path and its arithmetic lives in un-vendored third-party code (acados v0.3.6 ->
-HPIPM / OSQP 0.6.3; docker/Dockerfile:74-76).  This file therefore restates (a) the QP *data* exactly as
-ws/src/controllers/src/mit_controller/mpc.cpp builds it and (b) solves the resulting strictly convex QP to
-1e-10 with two independent methods; correctness is anchored on uniqueness of the optimum plus an independent
-KKT checker, and on the hand-derived known answers in tests/test_oracle.py.
+PINNING: the reference ships no golden vectors, unit tests or fixtures for this path, so the
+anchor is the reference's own code compiled here: oracle/_ref (oracle/build_ref.sh builds gait.cpp, mpc.cpp, the planner
+and the sequencers from /root/reference against stand-in Eigen / ROS / acados-interface headers).  tests/test_ref.py
+holds this file to it: (a) the gait schedule bit-exact, (b) the QP *data* (A, x0, bounds, D byte-equal, B <= 4e-17, q)
+equal to what the compiled MPC::GetWrenchSequence hands to acados; tests/golden/ref_golden.npz carries the same
+comparison to the GPU box.  What stays "parity unpinned" is the QP SOLVE: it lives in un-vendored third-party code
+(acados v0.3.6 -> HPIPM / OSQP 0.6.3; docker/Dockerfile:74-76); this file solves the strictly convex QP to 1e-10 with two
+independent methods, anchored on uniqueness of the optimum plus an independent KKT checker and the hand-derived known
+answers in tests/test_oracle.py.
 
 Conventions: quaternions are stored (x, y, z, w) = Eigen's coeffs() order; matrices handed to the C ABI are
 column-major like the reference's acados pointers (mpc.hpp:39-47); in numpy they are ordinary 2-D arrays.

@@ -1,9 +1,12 @@
 /*
  * mpc_ref.c - C restatement of the reference's CPU path for the MPC QP (TEST / MEASUREMENT INFRASTRUCTURE ONLY).
  *
- * PARITY UNPINNED: the reference ships no fixtures for this path and its solver arithmetic is third party
- * (acados v0.3.6 -> HPIPM condensing + OSQP 0.6.3; /root/reference/docker/Dockerfile:74-76), absent from
- * /root/reference and not buildable here.  This file restates
+ * PINNING: the QP DATA this file builds (1) is checked against the compiled reference (oracle/_ref: mpc.cpp built from
+ * /root/reference against stand-in headers; tests/test_ref.py: A, x0, bounds, D byte-equal, B <= 4e-17).  The SOLVER
+ * arithmetic (2)-(3) is third party in the reference (acados v0.3.6 -> HPIPM condensing + OSQP 0.6.3;
+ * /root/reference/docker/Dockerfile:74-76), absent from /root/reference and not buildable here, and the reference ships no
+ * fixtures for it: that part is "parity unpinned" in the strict sense and anchored on uniqueness of the optimum + the
+ * independent KKT checkers.  This file restates
  *   (1) the QP data exactly as ws/src/controllers/src/mit_controller/mpc.cpp:11-115,332-398 builds it,
  *   (2) full condensing (what HPIPM's d_cond_qp computes: X = Phi x0 + Gamma U, H = Gamma'QGamma + R, g),
  *   (3) the published OSQP algorithm (Stellato et al., "OSQP: an operator splitting solver for quadratic programs",

@@ -1,5 +1,6 @@
 """Scalar (one robot at a time) restatement of the reference's gait-sequencer input side.  TEST INFRASTRUCTURE ONLY
-(see oracle/mpc_oracle.py header; PARITY UNPINNED - the reference has no fixtures for this path).
+(see oracle/mpc_oracle.py header).  Pinned on the compiled reference sequencer (oracle/_ref, tests/test_ref.py: records 2e-16 on the
+first call); the multi-call behaviour is checked directly against live reference objects (tests/seq_cases.py).
 
 Follows  SimpleGaitSequencer::GetGaitSequence   simple_gait_sequencer.cpp:43-60
          MPCTrajectoryPlanner::plan_trajectory  mpc_trajectory_planner.cpp:28-140 (+ plan_desired_trajectory :142-264,
