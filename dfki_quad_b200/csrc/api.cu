@@ -34,6 +34,7 @@ cudaError_t launch_mpc_pcw(const MpcParams &P, int n, const double *in, const ui
                            b200qp_solver_info *info, double *lam_box, double *lam_g, double *scratch, int *next, int grid, cudaStream_t st,
                            const int *list, const int *list_count, int *rej, int *rej_count, int condN, int fs, long long *dbg);
 int pcw_grid(int num_sms, int N, int fs, int condN);
+cudaError_t launch_smem_polluter(int num_sms, cudaStream_t st);
 size_t pcw_scratch_doubles(int N, int fs);
 size_t pcond_scratch_doubles(int N);
 cudaError_t launch_sequencer(int n, const SeqModel &M, const double *seq_in, const uint8_t *measured, double *rec_out,
@@ -119,6 +120,7 @@ struct b200qp_mpc {
   double *d_pcw_scratch[2] = {nullptr, nullptr};
   int pcw_grid[2] = {0, 0}, pcw_cond = 0;
   int *d_pcw_rej = nullptr;  // [2][max_batch] hand-over lists
+  bool poison_smem = false;  // B200QP_POISON_SMEM=1 (development)
   bool ric_legacy = false;   // B200QP_RICCATI_LEGACY=1: block kernel only (A/B runs)
   // pinned staging
   double *h_in = nullptr, *h_forces = nullptr, *h_xpred = nullptr;
@@ -178,6 +180,7 @@ static void fill_params(b200qp_mpc *h) {
   P.ipm_warm_x = nullptr;
   P.ipm_warm_valid = nullptr;
   P.ipm_warm_mu = 1.0;
+  P.ipm_flags = getenv("B200QP_IPM_FLAGS") ? atoi(getenv("B200QP_IPM_FLAGS")) : 7;  // separate primal / dual step lengths, two-cycle guard, balance rule
   if (c.precision == 2 && !(c.kkt_tol > 0)) P.kkt_tol = 5e-2;  // FP32 polish: stationarity of O(1e-3) is all there is
 }
 
@@ -319,6 +322,7 @@ int32_t b200qp_mpc_create(const b200qp_mpc_config *cfg, b200qp_mpc **out) {
   }
   if (cfg->solver == B200QP_SOLVER_SPARSE_RICCATI) {
     h->ric_legacy = getenv("B200QP_RICCATI_LEGACY") != nullptr;
+    h->poison_smem = getenv("B200QP_POISON_SMEM") != nullptr;
     if (const char *wm = getenv("B200QP_IPM_WARM_MU")) h->ipm_warm_mu = atof(wm) > 0 ? atof(wm) : h->ipm_warm_mu;
     // blocks of the warp-per-problem kernel: cond_N as given (cond_N = horizon: one stage per block, the sparse formulation proper);
     // default: two stages per block - same Newton direction, fewer and better filled block factorisations
@@ -329,6 +333,14 @@ int32_t b200qp_mpc_create(const b200qp_mpc_config *cfg, b200qp_mpc **out) {
       if ((size_t)g > nb) g = (int)nb;
       h->pcw_grid[v] = g;
       CK(cudaMalloc(&h->d_pcw_scratch[v], (size_t)g * pcw_scratch_doubles(cfg->horizon, v + 1) * sizeof(double)));
+      if (const char *po = getenv("B200QP_POISON_SCRATCH")) {  // development: NaN-fill [lo, hi) doubles counted from the END of every block's scratch
+        const size_t stride = pcw_scratch_doubles(cfg->horizon, v + 1);
+        long lo = 0, hi = (long)stride;
+        sscanf(po, "%ld:%ld", &lo, &hi);
+        if (hi > (long)stride) hi = (long)stride;
+        if (lo < hi)
+          CK(cudaMemset2D(h->d_pcw_scratch[v] + (stride - (size_t)hi), stride * sizeof(double), 0xFF, (size_t)(hi - lo) * sizeof(double), (size_t)g));
+      }
     }
     CK(cudaMalloc(&h->d_pcw_rej, 2 * nb * sizeof(int)));
   }
@@ -525,6 +537,7 @@ static int32_t solve_device_impl(b200qp_mpc *h, int32_t n, const double *d_in, c
     // from there to the block kernel (d_bin_count[12], [13] = lengths of the hand-over lists, [14], [15], [9] = work counters)
     double *lb = h->want_duals ? h->d_lam_box : nullptr, *lg = h->want_duals ? h->d_lam_g : nullptr;
     int *rej0 = h->d_pcw_rej, *rej1 = h->d_pcw_rej + n;
+    if (h->poison_smem) CK(launch_smem_polluter(148, h->stream));
     MpcParams Pw = h->P;
     if (h->cfg.warm_start > 0 && h->d_warm_x != nullptr && dbg_index < 0) {  // IPM warm start: previous forces of the slot
       Pw.ipm_warm_x = h->d_warm_x;

@@ -24,6 +24,7 @@ struct MpcParams {
   double *ipm_warm_x;        // [max_batch][N][12] or nullptr
   uint8_t *ipm_warm_valid;   // [max_batch]
   double ipm_warm_mu;        // complementarity the warm-started slack / multiplier pairs begin at
+  int ipm_flags;             // warp Riccati kernel: bit 0 separate primal / dual step lengths, bit 1 centre two steps when the gap did not fall
 };
 
 // model constants of the gait sequencer kernels (b200qp_seq_model + the handle's dt / horizon)

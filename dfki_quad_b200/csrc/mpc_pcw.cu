@@ -382,6 +382,8 @@ __global__ void __launch_bounds__(32) mpc_pcw_kernel(const MpcParams P, int npro
     double best = BIGP;
     int stall = 0;
     bool final_pass = false;
+    double mu_prev = BIGP, bal0 = -1.0;
+    int damp = 0;
 
     WPH(0);
     for (iter = 0; iter <= P.ipm_max_iter + 1; ++iter) {
@@ -536,6 +538,9 @@ __global__ void __launch_bounds__(32) mpc_pcw_kernel(const MpcParams P, int npro
         break;
       }
       const double mu_c = gap / mtot;
+      if (bal0 < 0.0) bal0 = 1e3 * fmax(r0, 1e-6) / fmax(mu_c, 1e-300);  // allowed stationarity-to-gap ratio: 1000 x the starting one
+      if ((P.ipm_flags & 2) && mu_c > 0.9 * mu_prev) damp = 2;  // the gap did not fall by 10 %: centre the next two steps (two-cycle guard, cf. wbc_qp.cu)
+      mu_prev = mu_c;
 
       WPH(2);
       // (C) barrier weights per foot-stage, predictor right-hand side -------------------------------------------------------
@@ -778,28 +783,32 @@ __global__ void __launch_bounds__(32) mpc_pcw_kernel(const MpcParams P, int npro
         }
         WPH(7);
         // step in (s, z)
-        double stp = 1.0;
+        double stp = 1.0, stq = 1.0;  // step to the boundary in s (primal) and in z (dual)
         double dsn[FS][10], dzn[FS][10];
 #pragma unroll
         for (int q = 0; q < FS; ++q) {
           const int j = lane + 32 * q;
           if (j < nfs) {
-            double Gd[10], tmax = 0.0;
+            double Gd[10], tmax = 0.0, tmaz = 0.0;
             Gf(sDU[3 * j], sDU[3 * j + 1], sDU[3 * j + 2], mu_f, Gd);
 #pragma unroll
             for (int r = 0; r < 10; ++r) {
               const double rc = (pass == 0) ? s[q][r] * z[q][r] : (s[q][r] * z[q][r] + dsdz[q][r] - sigma_mu);
               dsn[q][r] = -rp[q][r] - Gd[r];
               dzn[q][r] = (-rc - z[q][r] * dsn[q][r]) * inv_s[q][r];
-              tmax = fmax(tmax, fmax(-dsn[q][r] * inv_s[q][r], -dzn[q][r] * fast_rcp(z[q][r])));
+              tmax = fmax(tmax, -dsn[q][r] * inv_s[q][r]);
+              tmaz = fmax(tmaz, -dzn[q][r] * fast_rcp(z[q][r]));
             }
             if (tmax > 1.0) stp = fmin(stp, 1.0 / tmax);
+            if (tmaz > 1.0) stq = fmin(stq, 1.0 / tmaz);
           } else {
 #pragma unroll
             for (int r = 0; r < 10; ++r) dsn[q][r] = dzn[q][r] = 0.0;
           }
         }
         stp = wred(stp, PMin());
+        stq = wred(stq, PMin());
+        if (!(P.ipm_flags & 1)) stp = stq = fmin(stp, stq);  // one step length for the whole iterate
         if (pass == 0) {
           double g2 = 0.0;
 #pragma unroll
@@ -807,7 +816,7 @@ __global__ void __launch_bounds__(32) mpc_pcw_kernel(const MpcParams P, int npro
             if (lane + 32 * q < nfs) {
 #pragma unroll
               for (int r = 0; r < 10; ++r) {
-                g2 += (s[q][r] + stp * dsn[q][r]) * (z[q][r] + stp * dzn[q][r]);
+                g2 += (s[q][r] + stp * dsn[q][r]) * (z[q][r] + stq * dzn[q][r]);
                 dsdz[q][r] = dsn[q][r] * dzn[q][r];
               }
             }
@@ -815,8 +824,13 @@ __global__ void __launch_bounds__(32) mpc_pcw_kernel(const MpcParams P, int npro
           const double mu_aff = g2 / mtot;
           const double ratio = mu_aff / fmax(mu_c, 1e-300);
           sigma_mu = ratio * ratio * ratio * mu_c;
+          if (damp > 0) sigma_mu = fmax(sigma_mu, 0.2 * mu_c);
+          // balance rule (bit 2): the gap must not run ahead of the stationarity residual by more than it did at the start, else the
+          // iterate leaves the central path for good (complementarity 1e-18 with stationarity O(1): the other failure kind of the soak)
+          if ((P.ipm_flags & 4) && r0 > bal0 * mu_c) sigma_mu = fmax(sigma_mu, fmin(0.5, 0.1 * r0 / (bal0 * mu_c)) * mu_c);
         } else {
-          double a = fmin(1.0, 0.995 * stp);
+          double a = fmin(1.0, 0.995 * stp), az = fmin(1.0, 0.995 * stq);
+          if (damp > 0) --damp;
           if (r0 < r1) {  // monotone-gap safeguard (see mpc_riccati.cu)
             double c1 = 0.0, c2 = 0.0;
 #pragma unroll
@@ -831,7 +845,10 @@ __global__ void __launch_bounds__(32) mpc_pcw_kernel(const MpcParams P, int npro
             c1 = wred(c1, PSum());
             c2 = wred(c2, PSum());
             const double lin = c1 + 0.1 * gap;
-            if (c2 > 0.0 && lin < 0.0) a = fmin(a, -lin / c2);
+            if (c2 > 0.0 && lin < 0.0) {
+              a = fmin(a, -lin / c2);
+              az = fmin(az, -lin / c2);
+            }
           }
 #pragma unroll
           for (int q = 0; q < FS; ++q) {
@@ -840,7 +857,7 @@ __global__ void __launch_bounds__(32) mpc_pcw_kernel(const MpcParams P, int npro
 #pragma unroll
               for (int r = 0; r < 10; ++r) {
                 s[q][r] += a * dsn[q][r];
-                z[q][r] += a * dzn[q][r];
+                z[q][r] += az * dzn[q][r];
               }
               sU[3 * j] += a * sDU[3 * j];
               sU[3 * j + 1] += a * sDU[3 * j + 1];
@@ -914,6 +931,22 @@ __global__ void __launch_bounds__(32) mpc_pcw_kernel(const MpcParams P, int npro
       info[prob] = inf;
     }
   }
+}
+
+// development aid (B200QP_POISON_SMEM=1): leaves NaN patterns in the shared memory of every SM, so that a read of shared memory the
+// kernel has not written shows up as a changed result instead of depending on which kernel ran before
+__global__ void smem_polluter_kernel(int nd) {
+  extern __shared__ __align__(16) double pdsm[];
+  for (int e = threadIdx.x; e < nd; e += blockDim.x) pdsm[e] = __longlong_as_double(0xFFF8000000000000ULL | (unsigned long long)e);
+  __syncthreads();
+  if (pdsm[(threadIdx.x * 7) % nd] == 1.0) pdsm[0] = 0.0;  // keep the stores
+}
+cudaError_t launch_smem_polluter(int num_sms, cudaStream_t st) {
+  const int bytes = 200 * 1024;
+  cudaError_t e = cudaFuncSetAttribute(smem_polluter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e != cudaSuccess) return e;
+  smem_polluter_kernel<<<num_sms * 2, 256, bytes, st>>>(bytes / 8);
+  return cudaGetLastError();
 }
 
 // ---- host side --------------------------------------------------------------------------------------------------------

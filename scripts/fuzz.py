@@ -21,7 +21,7 @@ for trial in range(int(os.environ.get("TRIALS", "24"))):
     fmax = float(rng.choice([120.0, 250.0, 400.0]))
     solver = str(rng.choice(["CONDENSED_ADMM", "SPARSE_RICCATI", "AUTO"]))
     ws = int(rng.choice([0, 0, 2]))
-    if os.environ.get("ONLY") and int(os.environ["ONLY"]) != trial:
+    if os.environ.get("ONLY") and trial not in {int(t) for t in os.environ["ONLY"].split(",")}:
         continue  # (the random stream above is consumed either way, so ONLY=<trial> reproduces that trial)
     b = sequencer.random_batch(n, N, seed=1000 + trial, gaits=gaits)
     mpc = BatchedMPC(alpha, w, mu, fmin, fmax, solver, warm_start=ws, horizon=N, dt=cfg["dt"], max_batch=n)
