@@ -180,7 +180,7 @@ static void fill_params(b200qp_mpc *h) {
   P.ipm_warm_x = nullptr;
   P.ipm_warm_valid = nullptr;
   P.ipm_warm_mu = 1.0;
-  P.ipm_flags = getenv("B200QP_IPM_FLAGS") ? atoi(getenv("B200QP_IPM_FLAGS")) : 7;  // separate primal / dual step lengths, two-cycle guard, balance rule
+  P.ipm_flags = getenv("B200QP_IPM_FLAGS") ? atoi(getenv("B200QP_IPM_FLAGS")) : 3;  // separate primal / dual step lengths + two-cycle guard
   if (c.precision == 2 && !(c.kkt_tol > 0)) P.kkt_tol = 5e-2;  // FP32 polish: stationarity of O(1e-3) is all there is
 }
 

@@ -382,7 +382,7 @@ __global__ void __launch_bounds__(32) mpc_pcw_kernel(const MpcParams P, int npro
     double best = BIGP;
     int stall = 0;
     bool final_pass = false;
-    double mu_prev = BIGP, bal0 = -1.0;
+    double mu_prev = BIGP;
     int damp = 0;
 
     WPH(0);
@@ -538,7 +538,6 @@ __global__ void __launch_bounds__(32) mpc_pcw_kernel(const MpcParams P, int npro
         break;
       }
       const double mu_c = gap / mtot;
-      if (bal0 < 0.0) bal0 = 1e3 * fmax(r0, 1e-6) / fmax(mu_c, 1e-300);  // allowed stationarity-to-gap ratio: 1000 x the starting one
       if ((P.ipm_flags & 2) && mu_c > 0.9 * mu_prev) damp = 2;  // the gap did not fall by 10 %: centre the next two steps (two-cycle guard, cf. wbc_qp.cu)
       mu_prev = mu_c;
 
@@ -825,9 +824,6 @@ __global__ void __launch_bounds__(32) mpc_pcw_kernel(const MpcParams P, int npro
           const double ratio = mu_aff / fmax(mu_c, 1e-300);
           sigma_mu = ratio * ratio * ratio * mu_c;
           if (damp > 0) sigma_mu = fmax(sigma_mu, 0.2 * mu_c);
-          // balance rule (bit 2): the gap must not run ahead of the stationarity residual by more than it did at the start, else the
-          // iterate leaves the central path for good (complementarity 1e-18 with stationarity O(1): the other failure kind of the soak)
-          if ((P.ipm_flags & 4) && r0 > bal0 * mu_c) sigma_mu = fmax(sigma_mu, fmin(0.5, 0.1 * r0 / (bal0 * mu_c)) * mu_c);
         } else {
           double a = fmin(1.0, 0.995 * stp), az = fmin(1.0, 0.995 * stq);
           if (damp > 0) --damp;
