@@ -44,7 +44,7 @@ constexpr int LDW = 25;         // odd leading dimension
 
 // NH: horizon capacity, FS: stance foot-stages per lane.  Dynamic shared memory per block (= per problem), doubles:
 //   K [NAW * LDW] | PB [12 * NUBW] (aliases the 4 x 32 staging of the elimination) | factors [fcap]
-template <int NH, int FS>
+template <int NH, int FS, bool TM>
 __global__ void __launch_bounds__(32) mpc_pcw_kernel(const MpcParams P, int nprob, const double *__restrict__ in,
                                                      const uint8_t *__restrict__ contact, double *__restrict__ forces,
                                                      double *__restrict__ xpred, b200qp_solver_info *__restrict__ info,
@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(32) mpc_pcw_kernel(const MpcParams P, int npro
     const double *rec = in + (size_t)prob * P.in_stride;
     const uint8_t *ct = contact + (size_t)prob * N * 4;
     const double mass = rec[13], dm = dt / mass;
-    const bool timing = dbg_cycles != nullptr;
+    constexpr bool timing = TM;  // per-phase clock64 accounting: a separate instantiation, so the product kernel carries no counters
     long long cyc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     long long tlast = timing ? clock64() : 0;
 #define WPH(idx) do { if (timing && lane == 0) { const long long t__ = clock64(); cyc[idx] += t__ - tlast; tlast = t__; } } while (0)
@@ -971,10 +971,17 @@ static cudaError_t pcw_launch_t(const MpcParams &P, int n, const double *in, con
                                 const int *list_count, int *rej, int *rej_count, int condN, int grid, cudaStream_t st, long long *dbg) {
   const int fcap = pcw_fcap(FS, P.N, condN);
   const size_t sm = pcw_smem(fcap);
-  cudaError_t e = cudaFuncSetAttribute(mpc_pcw_kernel<NH, FS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-  if (e != cudaSuccess) return e;
   if (grid > n) grid = n;
-  mpc_pcw_kernel<NH, FS><<<grid, 32, sm, st>>>(P, n, in, contact, forces, xpred, info, lam_box, lam_g, scratch, pcw_scratch_doubles(P.N, FS), next,
+  if (dbg != nullptr) {  // phase accounting (scripts/phase_cycles_pcw.py): the instrumented instantiation
+    cudaError_t e = cudaFuncSetAttribute(mpc_pcw_kernel<NH, FS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    if (e != cudaSuccess) return e;
+    mpc_pcw_kernel<NH, FS, true><<<grid, 32, sm, st>>>(P, n, in, contact, forces, xpred, info, lam_box, lam_g, scratch, pcw_scratch_doubles(P.N, FS), next,
+                                               list, list_count, rej, rej_count, condN, fcap, dbg);
+    return cudaGetLastError();
+  }
+  cudaError_t e = cudaFuncSetAttribute(mpc_pcw_kernel<NH, FS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+  if (e != cudaSuccess) return e;
+  mpc_pcw_kernel<NH, FS, false><<<grid, 32, sm, st>>>(P, n, in, contact, forces, xpred, info, lam_box, lam_g, scratch, pcw_scratch_doubles(P.N, FS), next,
                                                list, list_count, rej, rej_count, condN, fcap, dbg);
   return cudaGetLastError();
 }
@@ -982,8 +989,8 @@ template <int NH, int FS>
 static int pcw_occ_t(int N, int condN) {
   const size_t sm = pcw_smem(pcw_fcap(FS, N, condN));
   int occ = 0;
-  if (cudaFuncSetAttribute(mpc_pcw_kernel<NH, FS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm) != cudaSuccess ||
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, mpc_pcw_kernel<NH, FS>, 32, sm) != cudaSuccess) {
+  if (cudaFuncSetAttribute(mpc_pcw_kernel<NH, FS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm) != cudaSuccess ||
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, mpc_pcw_kernel<NH, FS, false>, 32, sm) != cudaSuccess) {
     cudaGetLastError();
     return 0;
   }
