@@ -739,7 +739,8 @@ __device__ __forceinline__ void horizon_sums(int N, int j, int l, double &cnt, d
 // refinement"); 2 = FP32 everywhere including the assembly, the polish and the outputs (error measurement only: b200qp_mpc_config.precision)
 template <int BS, int NV, int PREC = 0>
 __global__ void __launch_bounds__(BS, (BS == 64 && !B200QP_TC_GJ) ? 6 : 1) mpc_admm_kernel(const MpcParams P, const MpcBuffers B) {
-  constexpr bool R1 = PREC >= 1, R2 = PREC >= 2;
+  constexpr bool R1 = PREC == 1 || PREC == 2, R2 = PREC == 2;  // PREC 3: FP64 with the per-phase cycle counters (its own instantiation,
+                                                                // so that the product kernel carries neither the counters nor their branches)
   constexpr int LD = NV + 1;
   constexpr int MAXF = NV / 3 + 1;
   extern __shared__ __align__(16) double smem[];
@@ -835,7 +836,7 @@ __global__ void __launch_bounds__(BS, (BS == 64 && !B200QP_TC_GJ) ? 6 : 1) mpc_a
     const uint8_t *ct = reinterpret_cast<const uint8_t *>(s_rec + P.in_stride);
     const double mass = rec[13];
 
-    const bool timing = B.dbg_cycles != nullptr;
+    constexpr bool timing = PREC == 3;
     long long cyc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     long long tlast = timing ? clock64() : 0;
     // ---- phase 0: per-stage quantities -------------------------------------------------------------------
@@ -1635,6 +1636,12 @@ cudaError_t launch_mpc_admm(int bin, const MpcParams &P, const MpcBuffers &B, in
   } else if (P.precision == 2) {
     if (bin == 0) return launch_one<64, 60, 2>(P, B, grid, st);
     if (bin == 1) return launch_one<96, 96, 2>(P, B, grid, st);
+  }
+  if (B.dbg_cycles != nullptr) {  // phase accounting (scripts/phase_cycles.py)
+    if (bin == 0) return launch_one<64, 60, 3>(P, B, grid, st);
+    if (bin == 1) return launch_one<96, 96, 3>(P, B, grid, st);
+    if (bin == 2) return launch_one<128, 128, 3>(P, B, grid, st);
+    return launch_one<160, 156, 3>(P, B, grid, st);
   }
   if (bin == 0) return launch_one<64, 60>(P, B, grid, st);
   if (bin == 1) return launch_one<96, 96>(P, B, grid, st);
