@@ -621,10 +621,14 @@ def extra_closed_loop_device(args, dev, rank, world, n=4096, periods=20):
         m.rollout(seq0.copy(), 2, wbc=wb, plant_inertia="reference_model", history=False, control_dt=cdt, substeps=sub)  # warm-up
         m.sequencer_configure("simple", early_contact_detection=0)
         m.SetWarmStart(1)
-        seq = seq0.copy()
-        t0 = time.perf_counter()
-        hist = m.rollout(seq, periods, wbc=wb, plant_inertia="reference_model", control_dt=cdt, substeps=sub)
-        dt_s = time.perf_counter() - t0
+        dt_s = 1e30
+        for _ in range(3):  # best of three calls: one call is 40 - 450 ms of wall clock, a host hiccup would dominate it
+            m.sequencer_configure("simple", early_contact_detection=0)
+            m.SetWarmStart(1)
+            seq = seq0.copy()
+            t0 = time.perf_counter()
+            hist = m.rollout(seq, periods, wbc=wb, plant_inertia="reference_model", control_dt=cdt, substeps=sub)
+            dt_s = min(dt_s, time.perf_counter() - t0)
         (t_m,), _ = _reduce(world, dev, [dt_s], [0])
         ok = float((hist[:, :, 11] == 0).mean())
         out[name] = {"robot_periods_per_s": world * n * periods / t_m, "mpc_solves_per_s": world * n * periods / t_m,
