@@ -59,7 +59,7 @@ __device__ __forceinline__ void GT_apply(const double (&v)[10], double mu, doubl
 // NH = horizon capacity of the instantiation (shared-memory stage arrays are sized by it), MINB = resident blocks per SM
 // the register allocation is tuned for: the kernel is a chain of dependent FP64 instructions, so resident warps are what
 // hides its latency.
-template <int BS, int NH, int MINB>
+template <int BS, int NH, int MINB, bool TM = false>
 __global__ void __launch_bounds__(BS, MINB) mpc_riccati_kernel(const MpcParams P, int nprob, const double *__restrict__ in,
                                                          const uint8_t *__restrict__ contact, double *__restrict__ forces,
                                                          double *__restrict__ xpred, b200qp_solver_info *__restrict__ info,
@@ -96,7 +96,7 @@ __global__ void __launch_bounds__(BS, MINB) mpc_riccati_kernel(const MpcParams P
     const double *rec = in + (size_t)prob * P.in_stride;
     const uint8_t *ct = contact + (size_t)prob * N * 4;
     const double mass = rec[13], dm = dt / mass;
-    const bool timing = dbg_cycles != nullptr;
+    constexpr bool timing = TM;  // phase accounting is its own instantiation: the product kernel carries no counters
     long long cyc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     long long tlast = timing ? clock64() : 0;
 #define RPH(idx) do { if (timing && tid == 0) { const long long t__ = clock64(); cyc[idx] += t__ - tlast; tlast = t__; } } while (0)
@@ -761,12 +761,16 @@ cudaError_t launch_mpc_riccati(const MpcParams &P, int n, const double *in, cons
                                double *xpred, b200qp_solver_info *info, double *lam_box, double *lam_g, double *scratch,
                                int *next, int grid, cudaStream_t st, long long *dbg_cycles, const int *list, const int *list_count) {
   if (grid > n) grid = n;
-  if (P.N <= 10)
-    mpc_riccati_kernel<64, 10, 8><<<grid, 64, 0, st>>>(P, n, in, contact, forces, xpred, info, lam_box, lam_g, scratch, next, dbg_cycles, list, list_count);
-  else if (P.N <= 16)
-    mpc_riccati_kernel<64, 16, 6><<<grid, 64, 0, st>>>(P, n, in, contact, forces, xpred, info, lam_box, lam_g, scratch, next, dbg_cycles, list, list_count);
-  else
-    mpc_riccati_kernel<96, 20, 3><<<grid, 96, 0, st>>>(P, n, in, contact, forces, xpred, info, lam_box, lam_g, scratch, next, dbg_cycles, list, list_count);
+  if (P.N <= 10) {
+    if (dbg_cycles != nullptr) mpc_riccati_kernel<64, 10, 8, true><<<grid, 64, 0, st>>>(P, n, in, contact, forces, xpred, info, lam_box, lam_g, scratch, next, dbg_cycles, list, list_count);
+    else mpc_riccati_kernel<64, 10, 8><<<grid, 64, 0, st>>>(P, n, in, contact, forces, xpred, info, lam_box, lam_g, scratch, next, dbg_cycles, list, list_count);
+  } else if (P.N <= 16) {
+    if (dbg_cycles != nullptr) mpc_riccati_kernel<64, 16, 6, true><<<grid, 64, 0, st>>>(P, n, in, contact, forces, xpred, info, lam_box, lam_g, scratch, next, dbg_cycles, list, list_count);
+    else mpc_riccati_kernel<64, 16, 6><<<grid, 64, 0, st>>>(P, n, in, contact, forces, xpred, info, lam_box, lam_g, scratch, next, dbg_cycles, list, list_count);
+  } else {
+    if (dbg_cycles != nullptr) mpc_riccati_kernel<96, 20, 3, true><<<grid, 96, 0, st>>>(P, n, in, contact, forces, xpred, info, lam_box, lam_g, scratch, next, dbg_cycles, list, list_count);
+    else mpc_riccati_kernel<96, 20, 3><<<grid, 96, 0, st>>>(P, n, in, contact, forces, xpred, info, lam_box, lam_g, scratch, next, dbg_cycles, list, list_count);
+  }
   return cudaGetLastError();
 }
 
