@@ -97,6 +97,111 @@ __device__ void chol_and_inverse(double *A, int n, double *diag0) {
   }
 }
 
+// The same for a compile-time size N <= 32.  Two alternatives to the block version, selectable per half for A/B builds:
+//   bit 0  Cholesky by ONE warp (lane i owns row i, the scaled pivot column goes through shared memory, __syncwarp between steps):
+//          measured SLOWER (884 k vs 975 k QPs/s) - the 8 x 8 trailing update of the block version uses both warps;
+//   bit 1  L^-1 with lane j owning COLUMN j: its own forward substitution L x = e_j with x in registers (fully unrolled, the L entries
+//          are warp-uniform broadcast loads), so the columns need no synchronisation at all; written back in place afterwards:
+//          measured faster (1010 k/s), this is what ships.
+// Called by every thread of the block.
+#ifndef B200QP_WBC_VARIANT
+#define B200QP_WBC_VARIANT 2  // bit 0: warp Cholesky (slower: 884 k vs 975 k/s), bit 1: column-parallel inverse (faster: 1010 k/s); A/B builds
+#endif
+template <int N>
+__device__ __noinline__ void chol_and_inverse_warp(double *A, double *dinv) {
+  static_assert(N <= 32, "one lane per row / column");
+  const int tid = threadIdx.x, BS = blockDim.x;
+  if (B200QP_WBC_VARIANT & 1) {
+    if (threadIdx.x < 32) {
+      const int i = threadIdx.x;
+      const double d0 = (i < N) ? A[i * N + i] : 1.0;
+#pragma unroll 1
+      for (int p = 0; p < N; ++p) {
+        const double piv0 = A[p * N + p];
+        const double flo = 1e-13 * __shfl_sync(0xffffffffu, d0, p);
+        const double piv = piv0 > flo ? piv0 : flo;
+        const double rd = fast_rsqrt(piv);
+        __syncwarp();  // every lane has read the pivot before lane p overwrites it
+        double lip = 0.0;
+        if (i >= p && i < N) {
+          lip = (i == p) ? piv * rd : A[i * N + p] * rd;
+          A[i * N + p] = lip;
+        }
+        if (i == p) dinv[p] = rd;
+        __syncwarp();
+        if (i > p && i < N) {
+          double *Ai = A + i * N;
+          int j = p + 1;
+          for (; j + 1 <= i; j += 2) {  // two independent elements per trip
+            const double l0 = A[j * N + p], l1 = A[(j + 1) * N + p];
+            const double a0 = Ai[j], a1 = Ai[j + 1];
+            Ai[j] = fma(-lip, l0, a0);
+            Ai[j + 1] = fma(-lip, l1, a1);
+          }
+          if (j <= i) Ai[j] = fma(-lip, A[j * N + p], Ai[j]);
+        }
+        __syncwarp();
+      }
+    }
+    __syncthreads();
+  } else {  // block Cholesky (as chol_and_inverse)
+    if (tid < N) dinv[tid] = A[tid * N + tid];
+    __syncthreads();
+    for (int p = 0; p < N; ++p) {
+      const double flo = 1e-13 * dinv[p];
+      const double piv0 = A[p * N + p];
+      const double piv = piv0 > flo ? piv0 : flo;
+      const double rd = fast_rsqrt(piv);
+      __syncthreads();
+      for (int i = p + tid; i < N; i += BS) A[i * N + p] = (i == p) ? piv * rd : A[i * N + p] * rd;
+      if (tid == 0) dinv[p] = rd;
+      __syncthreads();
+      for (int i = p + 1 + (tid >> 3); i < N; i += 8) {
+        const double lip = A[i * N + p];
+        for (int j = p + 1 + (tid & 7); j <= i; j += 8) A[i * N + j] -= lip * A[j * N + p];
+      }
+      __syncthreads();
+    }
+  }
+  if (B200QP_WBC_VARIANT & 2) {
+    if (threadIdx.x < 32) {
+      const int j = threadIdx.x;
+      double x[N];
+#pragma unroll
+      for (int r = 0; r < N; ++r) {
+        double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+        for (int k = 0; k + 1 < r; k += 2) {
+          s0 = fma(A[r * N + k], x[k], s0);
+          s1 = fma(A[r * N + k + 1], x[k + 1], s1);
+        }
+        if (r & 1) s0 = fma(A[r * N + r - 1], x[r - 1], s0);
+        const double di = dinv[r];
+        x[r] = (r == j) ? di : ((r > j) ? -(s0 + s1) * di : 0.0);
+      }
+      __syncwarp();  // every lane is done reading L
+      if (j < N) {
+#pragma unroll
+        for (int r = 0; r < N; ++r)
+          if (r >= j) A[r * N + j] = x[r];
+      }
+    }
+    __syncthreads();
+  } else {
+    for (int j = N - 1; j >= 0; --j) {
+      double t = 0.0;
+      if (tid > j && tid < N) {
+        for (int k = j + 1; k <= tid; ++k) t = fma(A[tid * N + k], A[k * N + j], t);
+        t *= -dinv[j];
+      }
+      __syncthreads();
+      if (tid > j && tid < N) A[tid * N + j] = t;
+      else if (tid == j) A[j * N + j] = dinv[j];
+      __syncthreads();
+    }
+  }
+}
+
 // dx, dnu from r~ (srt) and re (sre):  u1 = -L^-1 r~,  dnu = S^-1 (re + Y'u1),  dx = L^-T (u1 - Y dnu)
 __device__ void kkt_solve(int nq, int me, const double *sLi, const double *sY, const double *sSi, const double *srt,
                           const double *sre, double *su1, double *sv, double *sdx, double *sdnu) {
@@ -313,7 +418,8 @@ __global__ void __launch_bounds__(64, 5) wbc_qp_kernel(const WbcParams P, int np
         sPhi[e] = a;
       }
       __syncthreads();
-      chol_and_inverse(sPhi, nq, sd0);
+      if constexpr (NQ_ > 0 && NQ_ <= 32) chol_and_inverse_warp<(NQ_ > 0 ? NQ_ : 1)>(sPhi, sd0);
+      else chol_and_inverse(sPhi, nq, sd0);
       for (int e = tid; e < nq * me; e += BS) {  // Y[i][r] = sum_{k<=i} Li[i][k] Aeq[r][k]
         const int i = e / me, r = e - i * me;
         double a = 0.0;
@@ -329,7 +435,8 @@ __global__ void __launch_bounds__(64, 5) wbc_qp_kernel(const WbcParams P, int np
         sS[e] = a;
       }
       __syncthreads();
-      chol_and_inverse(sS, me, sd0);
+      if constexpr (NQ_ > 0 && ME_ <= 32) chol_and_inverse_warp<(ME_ > 0 ? ME_ : 1)>(sS, sd0);
+      else chol_and_inverse(sS, me, sd0);
 
       if (init) {  // starting point as in CVXOPT's coneqp: solve with W = I, then shift s and z into the interior
         if (row) sw[tid] = (hasu ? hi : 0.0) - (hasl ? lo : 0.0);
