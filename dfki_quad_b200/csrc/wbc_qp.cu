@@ -103,6 +103,8 @@ __device__ void chol_and_inverse(double *A, int n, double *diag0) {
 //   bit 1  L^-1 with lane j owning COLUMN j: its own forward substitution L x = e_j with x in registers (fully unrolled, the L entries
 //          are warp-uniform broadcast loads), so the columns need no synchronisation at all; written back in place afterwards:
 //          measured faster (1010 k/s), this is what ships.
+//   (a third one, the Cholesky with row i in the registers of lane i and the multipliers moved by 64-bit warp shuffles, ran at 565 k/s:
+//   435 dependent shuffle + FMA pairs per factorisation - the same lesson as in the block Riccati kernel - and is not kept.)
 // Called by every thread of the block.
 #ifndef B200QP_WBC_VARIANT
 #define B200QP_WBC_VARIANT 2  // bit 0: warp Cholesky (slower: 884 k vs 975 k/s), bit 1: column-parallel inverse (faster: 1010 k/s); A/B builds
@@ -338,6 +340,13 @@ __global__ void __launch_bounds__(64, 5) wbc_qp_kernel(const WbcParams P, int np
     __syncthreads();
 
     int status = B200QP_ACADOS_MAXITER, iter = 0;
+#ifdef B200QP_WBC_TIMING
+    long long wcyc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, wlast = clock64();
+#define WPHW(idx) do { if (tid == 0) { const long long t__ = clock64(); wcyc[idx] += t__ - wlast; wlast = t__; } } while (0)
+#else
+#define WPHW(idx) do { } while (0)
+#endif
+    WPHW(0);
     double k_stat = 0.0, k_eq = 0.0, k_ineq = 0.0, k_comp = 0.0, bk[4] = {0.0, 0.0, 0.0, 0.0};
     const double target = 1e-4 * P.kkt_tol;
     double best = WBIG;
@@ -407,6 +416,7 @@ __global__ void __launch_bounds__(64, 5) wbc_qp_kernel(const WbcParams P, int np
       mu_prev = mu_c;
       }  // !init
 
+      WPHW(1);
       // Phi = H + Ain' W Ain ------------------------------------------------------------------------------------------
       if (row) sw[tid] = init ? ((hasl ? 1.0 : 0.0) + (hasu ? 1.0 : 0.0)) : ((hasl ? zl / sl : 0.0) + (hasu ? zu / su : 0.0));
       __syncthreads();
@@ -418,8 +428,10 @@ __global__ void __launch_bounds__(64, 5) wbc_qp_kernel(const WbcParams P, int np
         sPhi[e] = a;
       }
       __syncthreads();
+      WPHW(2);
       if constexpr (NQ_ > 0 && NQ_ <= 32) chol_and_inverse_warp<(NQ_ > 0 ? NQ_ : 1)>(sPhi, sd0);
       else chol_and_inverse(sPhi, nq, sd0);
+      WPHW(3);
       for (int e = tid; e < nq * me; e += BS) {  // Y[i][r] = sum_{k<=i} Li[i][k] Aeq[r][k]
         const int i = e / me, r = e - i * me;
         double a = 0.0;
@@ -435,8 +447,10 @@ __global__ void __launch_bounds__(64, 5) wbc_qp_kernel(const WbcParams P, int np
         sS[e] = a;
       }
       __syncthreads();
+      WPHW(4);
       if constexpr (NQ_ > 0 && ME_ <= 32) chol_and_inverse_warp<(ME_ > 0 ? ME_ : 1)>(sS, sd0);
       else chol_and_inverse(sS, me, sd0);
+      WPHW(5);
 
       if (init) {  // starting point as in CVXOPT's coneqp: solve with W = I, then shift s and z into the interior
         if (row) sw[tid] = (hasu ? hi : 0.0) - (hasl ? lo : 0.0);
@@ -466,6 +480,7 @@ __global__ void __launch_bounds__(64, 5) wbc_qp_kernel(const WbcParams P, int np
         __syncthreads();
         continue;
       }
+      WPHW(6);
       // predictor / corrector ---------------------------------------------------------------------------------------------
       double dsl = 0.0, dsu = 0.0, dzl = 0.0, dzu = 0.0, sigma_mu = 0.0;
       for (int pass = 0; pass < 2; ++pass) {
@@ -542,10 +557,14 @@ __global__ void __launch_bounds__(64, 5) wbc_qp_kernel(const WbcParams P, int np
         }
         __syncthreads();
       }
+      WPHW(7);
     }
     __syncthreads();
     if (status == B200QP_ACADOS_SUCCESS)
       for (int i = tid; i < nq; i += BS) xout[(size_t)prob * nq + i] = sbx[i];
+#ifdef B200QP_WBC_TIMING
+    if (tid == 0) for (int q = 0; q < 10; ++q) xout[(size_t)prob * nq + q] = (double)wcyc[q];
+#endif
     if (tid == 0) {
       b200qp_solver_info inf;
       inf.status = status;
