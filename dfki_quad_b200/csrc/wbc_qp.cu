@@ -105,6 +105,8 @@ __device__ void chol_and_inverse(double *A, int n, double *diag0) {
 //          measured faster (1010 k/s), this is what ships.
 //   (a third one, the Cholesky with row i in the registers of lane i and the multipliers moved by 64-bit warp shuffles, ran at 565 k/s:
 //   435 dependent shuffle + FMA pairs per factorisation - the same lesson as in the block Riccati kernel - and is not kept.)
+//   (a blocked Cholesky - four columns per step, the 4 x 4 diagonal block factored redundantly in registers, two barriers per step instead
+//   of three per column - is exactly as fast as the column version, 1005 vs 1014 k/s: the barriers are not what the step waits for.)
 // Called by every thread of the block.
 #ifndef B200QP_WBC_VARIANT
 #define B200QP_WBC_VARIANT 2  // bit 0: warp Cholesky (slower: 884 k vs 975 k/s), bit 1: column-parallel inverse (faster: 1010 k/s); A/B builds
