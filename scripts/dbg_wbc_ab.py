@@ -25,6 +25,6 @@ if len(sys.argv) > 1:
     st = np.frombuffer(di.cpu().numpy().tobytes(), dtype=np.dtype([("status", "i4"), ("it", "i4"), ("a", "i4"), ("b", "i4"), ("kkt", "f8", (4,))]))
     print(sys.argv[1], f"{B / best / 1e3 * 1e3:.0f} solves/s  {best:.2f} ms  ok {(st['status'] == 0).mean():.4f} it {st['it'].mean():.2f}")
 else:
-    for v in ("2", "10"):
+    for v in ("head", "dot4"):
         env = dict(os.environ, B200QP_LIB=f"/root/repo/dfki_quad_b200/libb200qp_wbcv{v}.so")
         subprocess.run([sys.executable, __file__, "variant" + v], env=env)
