@@ -142,6 +142,115 @@ static int test_wbc(void) {
   return 0;
 }
 
+/* The sequencers with their state, the WBC from the robot state and the closed loop on the device, from plain C: a robot standing still on
+ * four feet (STAND gait) carries its weight, keeps its height over 20 control periods with the MPC alone and with the WBC in the loop. */
+static int test_sequencer_scene_rollout(void) {
+  enum { N = 10, NB = 4, PERIODS = 20 };
+  b200qp_mpc_config cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.horizon = N;
+  cfg.solver = B200QP_SOLVER_CONDENSED_ADMM;
+  cfg.max_batch = NB;
+  cfg.dt = 0.05;
+  cfg.alpha = 1e-5;
+  const double w_stand[12] = {30, 30, 30, 30, 30, 30, 1, 1, 1, 1, 1, 1};
+  memcpy(cfg.state_weights, w_stand, sizeof(w_stand));
+  cfg.mu = 0.6;
+  cfg.fmax = 400.0;
+  b200qp_mpc *h = NULL;
+  CHECK(b200qp_mpc_create(&cfg, &h) == B200QP_OK, "rollout: create: %s", b200qp_last_error());
+  b200qp_seq_model model;
+  memset(&model, 0, sizeof(model));
+  model.mass = 15.019;
+  const double inertia[9] = {0.202755, 0.00012166, -0.0143742, 0.00012166, 0.490926, -3.12e-05, -0.0143742, -3.12e-05, 0.52697};
+  memcpy(model.inertia, inertia, sizeof(inertia));
+  const double sh[12] = {0.167, 0.1738, 0.0, 0.167, -0.1738, 0.0, -0.197, 0.1738, 0.0, -0.197, -0.1738, 0.0}; /* mit_controller_sim_go2.yaml:33-38 */
+  memcpy(model.shoulders, sh, sizeof(sh));
+  model.raibert_k = 0.03;
+  model.raibert_g = 9.81;
+  model.max_leg_length = 0.406;
+  static double seq2[NB][B200QP_SEQ2_IN_DOUBLES], hist[PERIODS][NB][B200QP_ROLLOUT_HIST_DOUBLES];
+  static double forces[NB][N * 12], xpred[NB][(N + 1) * 13];
+  b200qp_solver_info info[NB];
+  b200qp_rollout_options ro;
+  memset(&ro, 0, sizeof(ro));
+  ro.substeps = 10;
+  ro.wbc_per_mpc = 5;
+  for (int c = 0; c < 3; ++c) { ro.com_pose_Kp[c] = 300.0; ro.com_pose_Kp[3 + c] = 200.0; ro.feet_pose_Kp[c] = 1200.0; }
+  for (int c = 0; c < 6; ++c) ro.com_pose_Kd[c] = 100.0;
+  ro.feet_pose_Kd[0] = ro.feet_pose_Kd[1] = 500.0; ro.feet_pose_Kd[2] = 400.0;
+  CHECK(b200qp_mpc_rollout(h, NULL, NB, 2, &seq2[0][0], &ro, NULL) == B200QP_ERR_ARG, "rollout before configure must be an argument error");
+  CHECK(b200qp_mpc_set_model(h, &model) == B200QP_OK, "set_model");
+  b200qp_seq_options so;
+  memset(&so, 0, sizeof(so));
+  so.mode = 0;
+  so.raibert_filtersize = 20;
+  so.fix_standing_position = 1;
+  so.fix_position_distance_threshold = 0.1;
+  so.fix_position_angular_threshold = 0.26;
+  so.fix_position_velocity_threshold = 0.1;
+  CHECK(b200qp_mpc_sequencer_configure(h, &so) == B200QP_OK, "sequencer_configure: %s", b200qp_last_error());
+  memset(seq2, 0, sizeof(seq2));
+  for (int p = 0; p < NB; ++p) {
+    double *S = seq2[p];
+    S[3] = 1.0;                      /* identity quaternion */
+    S[4] = 0.5 * p; S[6] = 0.30;     /* position */
+    for (int f = 0; f < 4; ++f) { S[13 + 3 * f] = S[4] + sh[3 * f]; S[13 + 3 * f + 1] = sh[3 * f + 1]; }
+    S[25] = 1.0e6 * p;               /* clock, ns */
+    S[26 + 2] = 0.30; S[26 + 9] = 1.0;                 /* Target: z, full_orientation.w */
+    S[45] = (double)((1u << 2) | (1u << 3) | (1u << 4) | (1u << 10) | (1u << 11) | (1u << 13) | (1u << 14) | (1u << 15)); /* z roll pitch hybrid_x/y_dot wx wy wz */
+    S[46] = 0.5;                                       /* STAND: period, duty 1, offsets 0 (gait.cpp:734-736) */
+    for (int f = 0; f < 4; ++f) S[47 + f] = 1.0;
+  }
+  const double mg = 15.019 * 9.8067;
+  int rc = b200qp_mpc_sequencer_step_solve(h, NB, &seq2[0][0], NULL, &forces[0][0], &xpred[0][0], info);
+  CHECK(rc == B200QP_OK, "sequencer_step_solve: %s", b200qp_last_error());
+  for (int p = 0; p < NB; ++p) {
+    CHECK(info[p].status == B200QP_ACADOS_SUCCESS && info[p].n_free == 120, "sequencer_step_solve: robot %d status %d n_free %d", p, info[p].status, info[p].n_free);
+    double fz = 0.0;
+    for (int f = 0; f < 4; ++f) fz += forces[p][3 * f + 2];
+    CHECK(fabs(fz - mg) <= 2e-3 * mg, "sequencer_step_solve: robot %d carries %g N, m g = %g", p, fz, mg);
+  }
+  CHECK(b200qp_mpc_sequencer_reset(h) == B200QP_OK, "sequencer_reset");
+  rc = b200qp_mpc_rollout(h, NULL, NB, PERIODS, &seq2[0][0], &ro, &hist[0][0][0]);
+  CHECK(rc == B200QP_OK, "rollout: %s", b200qp_last_error());
+  for (int p = 0; p < NB; ++p) {
+    CHECK(hist[PERIODS - 1][p][11] == 0.0, "rollout: robot %d MPC status %g", p, hist[PERIODS - 1][p][11]);
+    CHECK(fabs(hist[PERIODS - 1][p][2] - 0.30) < 5e-3 && fabs(seq2[p][6] - 0.30) < 5e-3, "rollout: robot %d height %g", p, hist[PERIODS - 1][p][2]);
+    CHECK(fabs(hist[PERIODS - 1][p][10] - mg) <= 5e-3 * mg, "rollout: robot %d applied f_z %g", p, hist[PERIODS - 1][p][10]);
+    CHECK(fabs(seq2[p][25] - (1.0e6 * p + PERIODS * 5.0e7)) < 0.5, "rollout: robot %d clock %g", p, seq2[p][25]);
+    CHECK(hist[0][p][14] == -1.0, "rollout without WBC must report WBC status -1");
+  }
+  /* the same with the whole-body controller in the loop: scene assembled on the device from the plant state */
+  b200qp_wbc_config wc;
+  memset(&wc, 0, sizeof(wc));
+  wc.nq = 30; wc.neq = 18; wc.nin = 28; wc.max_batch = NB; wc.kkt_tol = 1e-6; wc.max_iter = 40;
+  b200qp_wbc *w = NULL;
+  CHECK(b200qp_wbc_create(&wc, &w) == B200QP_OK, "wbc create: %s", b200qp_last_error());
+  CHECK(b200qp_mpc_rollout(h, w, NB, 2, &seq2[0][0], &ro, NULL) == B200QP_ERR_ARG, "rollout with an unconfigured scene must be an argument error");
+  b200qp_wbc_scene_config sc;
+  memset(&sc, 0, sizeof(sc));
+  sc.mu = 0.45;
+  sc.hessian_regularizer = 1e-8;
+  for (int c = 0; c < 6; ++c) sc.com_pose_weight[c] = 10.0;
+  for (int c = 0; c < 3; ++c) { sc.foot_force_weight[c] = 30.0; sc.foot_pose_weight[c] = 10.0; }
+  for (int j = 0; j < 12; ++j) sc.tau_max[j] = (j % 3 == 2) ? 45.43 : 23.7;
+  CHECK(b200qp_wbc_scene_configure(w, &sc) == B200QP_OK, "scene_configure: %s", b200qp_last_error());
+  CHECK(b200qp_mpc_sequencer_reset(h) == B200QP_OK, "sequencer_reset");
+  ro.control_dt = 0.01;
+  ro.substeps = 5;
+  rc = b200qp_mpc_rollout(h, w, NB, PERIODS, &seq2[0][0], &ro, &hist[0][0][0]);
+  CHECK(rc == B200QP_OK, "rollout with WBC: %s", b200qp_last_error());
+  for (int p = 0; p < NB; ++p) {
+    CHECK(hist[PERIODS - 1][p][11] == 0.0 && hist[PERIODS - 1][p][14] == 0.0, "rollout with WBC: robot %d status %g / %g", p, hist[PERIODS - 1][p][11], hist[PERIODS - 1][p][14]);
+    CHECK(fabs(hist[PERIODS - 1][p][2] - 0.30) < 2e-2, "rollout with WBC: robot %d height %g", p, hist[PERIODS - 1][p][2]);
+  }
+  b200qp_wbc_destroy(w);
+  b200qp_mpc_destroy(h);
+  printf("sequencer / scene / rollout: ok\n");
+  return 0;
+}
+
 int main(void) {
   printf("%s, %d CUDA device(s)\n", b200qp_version(), b200qp_device_count());
   if (b200qp_device_count() < 1) {
@@ -153,6 +262,7 @@ int main(void) {
   if (test_mpc(B200QP_SOLVER_PARTIAL_CONDENSING, "mpc PARTIAL_CONDENSING")) return 1;
   if (test_mpc(B200QP_SOLVER_AUTO, "mpc AUTO")) return 1;
   if (test_wbc()) return 1;
+  if (test_sequencer_scene_rollout()) return 1;
   printf("all boundary checks passed\n");
   return 0;
 }

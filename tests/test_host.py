@@ -239,7 +239,8 @@ def test_ctypes_structs_match_the_c_header_field_by_field(tmp_path):
     from dfki_quad_b200 import _lib
 
     structs = {"b200qp_mpc_config": _lib.MpcConfig, "b200qp_solver_info": _lib.SolverInfo, "b200qp_wbc_config": _lib.WbcConfig,
-               "b200qp_seq_model": _lib.SeqModel}
+               "b200qp_seq_model": _lib.SeqModel, "b200qp_seq_options": _lib.SeqOptions, "b200qp_wbc_scene_config": _lib.WbcSceneConfig,
+               "b200qp_rollout_options": _lib.RolloutOptions}
     lines = ['#include <stddef.h>', '#include <stdio.h>', '#include "b200qp.h"', "int main(void) {"]
     for cname, cls in structs.items():
         lines.append(f'  printf("{cname} size %zu\\n", sizeof({cname}));')
@@ -267,6 +268,9 @@ def test_ctypes_structs_match_the_c_header_field_by_field(tmp_path):
     from dfki_quad_b200 import sequencer
 
     assert seen[("seq_in_doubles",)] == sequencer.SEQ_IN_DOUBLES == 50
+    # the kernel-side mirrors of the option structs are plain copies field by field (api.cu); their sizes are pinned here through the header
+    assert ctypes.sizeof(_lib.SeqOptions) == 4 * 4 + 3 * 8 + 10 * 8 + 4 * 8 + 8 + 3 * 4 + 4  # 4 ints, 3 + 10 doubles, phase_offset[4], control_dt, 3 ints + tail padding
+    assert ctypes.sizeof(_lib.RolloutOptions) == 4 * 4 + 18 * 8 + 8
 
 
 def test_rollout_plant_conserves_what_it_should():
