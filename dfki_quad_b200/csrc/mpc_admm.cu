@@ -232,24 +232,169 @@ __device__ __noinline__ void nnls3(const double (*M)[3], int m, const double (&b
 // (the scalar sweep was bound by exactly that per-pivot latency).  The old pivot rows are staged in prow4[j][4]; the new
 // pivot rows are produced column-wise (thread j writes A[P, j]) so that no thread runs a long divergent branch.
 // The last n mod 4 pivots use the scalar step.
+#ifndef B200QP_GJ_SYM
+#define B200QP_GJ_SYM 0
+#endif
+// Symmetric variant of the sweep below (-DB200QP_GJ_SYM=1; correct - the whole GPU suite passes with it - but measured SLOWER, 3.04 vs
+// 3.19 M solves/s: halving the multiply-adds and the shared-memory traffic does not shorten a block step, whose length is set by the
+// longest line (line n-1 still has n entries) and by the serial prelude): between block steps the matrix satisfies M(a,b) = M(b,a) when a and b are both
+// already pivoted or both not, and M(a,b) = -M(b,a) when exactly one of them is (A[R,P] carries the minus sign of the sweep).  So only
+// the lower triangle (b <= a) is kept and updated - thread i owns M(i, 0..i), contiguous at K[i * LD] - and an element of the upper
+// triangle is taken from its mirror with that sign: half the multiply-adds and half the shared-memory traffic of the sweep.  The full
+// symmetric inverse is written out at the end.
 template <int LD, bool F32 = false>
-__device__ __noinline__ void gj_invert(double *K, int n, double *prow4) {
+__device__ __noinline__ void gj_invert_sym(double *K, int n, double *prow4) {
+  static_assert((LD % 2) == 0, "128-bit accesses to a thread's run");
   const int i = threadIdx.x;
-  double *Ki = K + i;
+  double *Ki = K + (size_t)i * LD;
   int p0 = 0;
   for (; p0 + 3 < n; p0 += 4) {
-    if (i < n) {  // stage column i of the 4 pivot rows: prow4[i][q] = A[p0+q][i]
+    double st[4] = {0.0, 0.0, 0.0, 0.0};
+    if (i < n) {  // stage M(p0+q, i): stored in the pivot line when i <= p0+q, else the mirror in this thread's own line (both unpivoted: +)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) st[q] = (i <= p0 + q) ? K[(p0 + q) * LD + i] : Ki[p0 + q];
       double2 a, b;
-      a.x = K[i * LD + p0];
-      a.y = K[i * LD + p0 + 1];
-      b.x = K[i * LD + p0 + 2];
-      b.y = K[i * LD + p0 + 3];
+      a.x = st[0]; a.y = st[1]; b.x = st[2]; b.y = st[3];
       *reinterpret_cast<double2 *>(prow4 + 4 * i) = a;
       *reinterpret_cast<double2 *>(prow4 + 4 * i + 2) = b;
     }
     __syncthreads();
     if (i < n) {
-      // D[q][q'] = A[p0+q][p0+q'] = prow4[p0+q'][q]; 4x4 inverse through 2x2 blocks (two reciprocals)
+      double D[4][4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const double2 a = *reinterpret_cast<const double2 *>(prow4 + 4 * (p0 + c));
+        const double2 b = *reinterpret_cast<const double2 *>(prow4 + 4 * (p0 + c) + 2);
+        D[0][c] = a.x; D[1][c] = a.y; D[2][c] = b.x; D[3][c] = b.y;
+      }
+      const double r1 = fast_rcp(D[0][0] * D[1][1] - D[0][1] * D[1][0]);
+      const double i00 = D[1][1] * r1, i01 = -D[0][1] * r1, i10 = -D[1][0] * r1, i11 = D[0][0] * r1;
+      const double t00 = D[2][0] * i00 + D[2][1] * i10, t01 = D[2][0] * i01 + D[2][1] * i11;
+      const double t10 = D[3][0] * i00 + D[3][1] * i10, t11 = D[3][0] * i01 + D[3][1] * i11;
+      const double s00 = D[2][2] - (t00 * D[0][2] + t01 * D[1][2]), s01 = D[2][3] - (t00 * D[0][3] + t01 * D[1][3]);
+      const double s10 = D[3][2] - (t10 * D[0][2] + t11 * D[1][2]), s11 = D[3][3] - (t10 * D[0][3] + t11 * D[1][3]);
+      const double r2 = fast_rcp(s00 * s11 - s01 * s10);
+      const double j00 = s11 * r2, j01 = -s01 * r2, j10 = -s10 * r2, j11 = s00 * r2;
+      const double u00 = i00 * D[0][2] + i01 * D[1][2], u01 = i00 * D[0][3] + i01 * D[1][3];
+      const double u10 = i10 * D[0][2] + i11 * D[1][2], u11 = i10 * D[0][3] + i11 * D[1][3];
+      double E[4][4];
+      E[2][2] = j00; E[2][3] = j01; E[3][2] = j10; E[3][3] = j11;
+      E[0][2] = -(u00 * j00 + u01 * j10); E[0][3] = -(u00 * j01 + u01 * j11);
+      E[1][2] = -(u10 * j00 + u11 * j10); E[1][3] = -(u10 * j01 + u11 * j11);
+      E[2][0] = -(j00 * t00 + j01 * t10); E[2][1] = -(j00 * t01 + j01 * t11);
+      E[3][0] = -(j10 * t00 + j11 * t10); E[3][1] = -(j10 * t01 + j11 * t11);
+      E[0][0] = i00 - (E[0][2] * t00 + E[0][3] * t10); E[0][1] = i01 - (E[0][2] * t01 + E[0][3] * t11);
+      E[1][0] = i10 - (E[1][2] * t00 + E[1][3] * t10); E[1][1] = i11 - (E[1][2] * t01 + E[1][3] * t11);
+      if (F32) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+          for (int q2 = 0; q2 < 4; ++q2) E[q][q2] = rnd<F32>(E[q][q2]);
+      }
+      const bool inP = (i >= p0) && (i < p0 + 4);
+      // new entries of the pivot lines at column i, where they are stored (i <= p0 + q)
+      if (i < p0 + 4) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          if (i <= p0 + q) {
+            const double v = inP ? E[q][i - p0] : (E[q][0] * st[0] + E[q][1] * st[1] + E[q][2] * st[2] + E[q][3] * st[3]);
+            K[(p0 + q) * LD + i] = rnd<F32>(v);
+          }
+        }
+      }
+      if (!inP) {
+        const bool below = i > p0 + 3;  // this line is not pivoted yet: its entries at the pivot columns are stored in the line itself
+        double c0, c1, c2, c3;
+        if (below) {
+          const double2 c01 = *reinterpret_cast<const double2 *>(Ki + p0), c23 = *reinterpret_cast<const double2 *>(Ki + p0 + 2);
+          c0 = c01.x; c1 = c01.y; c2 = c23.x; c3 = c23.y;
+        } else {  // already pivoted line: M(i, p0+q) = -M(p0+q, i)
+          c0 = -st[0]; c1 = -st[1]; c2 = -st[2]; c3 = -st[3];
+        }
+        const double w0 = rnd<F32>(c0 * E[0][0] + c1 * E[1][0] + c2 * E[2][0] + c3 * E[3][0]);
+        const double w1 = rnd<F32>(c0 * E[0][1] + c1 * E[1][1] + c2 * E[2][1] + c3 * E[3][1]);
+        const double w2 = rnd<F32>(c0 * E[0][2] + c1 * E[1][2] + c2 * E[2][2] + c3 * E[3][2]);
+        const double w3 = rnd<F32>(c0 * E[0][3] + c1 * E[1][3] + c2 * E[2][3] + c3 * E[3][3]);
+        int j = 0;
+        for (; j + 3 <= i; j += 4) {  // columns j..j+3 <= i
+          double2 pa[4], pb[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            pa[u] = *reinterpret_cast<const double2 *>(prow4 + 4 * (j + u));
+            pb[u] = *reinterpret_cast<const double2 *>(prow4 + 4 * (j + u) + 2);
+          }
+          double2 k01 = *reinterpret_cast<const double2 *>(Ki + j), k23 = *reinterpret_cast<const double2 *>(Ki + j + 2);
+          k01.x = rnd<F32>(fma(-w3, pb[0].y, fma(-w2, pb[0].x, fma(-w1, pa[0].y, fma(-w0, pa[0].x, k01.x)))));
+          k01.y = rnd<F32>(fma(-w3, pb[1].y, fma(-w2, pb[1].x, fma(-w1, pa[1].y, fma(-w0, pa[1].x, k01.y)))));
+          k23.x = rnd<F32>(fma(-w3, pb[2].y, fma(-w2, pb[2].x, fma(-w1, pa[2].y, fma(-w0, pa[2].x, k23.x)))));
+          k23.y = rnd<F32>(fma(-w3, pb[3].y, fma(-w2, pb[3].x, fma(-w1, pa[3].y, fma(-w0, pa[3].x, k23.y)))));
+          *reinterpret_cast<double2 *>(Ki + j) = k01;
+          *reinterpret_cast<double2 *>(Ki + j + 2) = k23;
+        }
+        for (; j <= i; ++j) {
+          const double2 a0 = *reinterpret_cast<const double2 *>(prow4 + 4 * j);
+          const double2 b0 = *reinterpret_cast<const double2 *>(prow4 + 4 * j + 2);
+          Ki[j] = rnd<F32>(fma(-w3, b0.y, fma(-w2, b0.x, fma(-w1, a0.y, fma(-w0, a0.x, Ki[j])))));
+        }
+        if (below) {
+          double2 m01, m23;
+          m01.x = -w0; m01.y = -w1; m23.x = -w2; m23.y = -w3;
+          *reinterpret_cast<double2 *>(Ki + p0) = m01;
+          *reinterpret_cast<double2 *>(Ki + p0 + 2) = m23;
+        }
+      }
+    }
+    __syncthreads();
+  }
+  double *prow = prow4;
+  for (int p = p0; p < n; ++p) {  // scalar tail, same rules with a 1 x 1 pivot block
+    double sp = 0.0;
+    if (i < n) {
+      sp = (i <= p) ? K[p * LD + i] : Ki[p];
+      prow[i] = sp;
+    }
+    __syncthreads();
+    if (i < n) {
+      const double d = rnd<F32>(1.0 / prow[p]);
+      if (i <= p) K[p * LD + i] = (i == p) ? d : rnd<F32>(sp * d);
+      if (i != p) {
+        const double c = (i > p) ? Ki[p] : -sp;
+        const double f = rnd<F32>(c * d);
+        for (int j = 0; j <= i; ++j)
+          if (j != p) Ki[j] = rnd<F32>(fma(-f, prow[j], Ki[j]));
+        if (i > p) Ki[p] = -f;
+      }
+    }
+    __syncthreads();
+  }
+  // the inverse is symmetric: fill the upper triangle (the mat-vecs read whole runs)
+  if (i < n)
+    for (int j = i + 1; j < n; ++j) Ki[j] = K[j * LD + i];
+  __syncthreads();
+}
+
+template <int LD, bool F32 = false>
+__device__ __noinline__ void gj_invert(double *K, int n, double *prow4) {
+  // Access pattern (round 2): the matrix is symmetric before and after, and M(i,j) = +-M(j,i) in between, so the sweep may as well be
+  // run on the transpose: thread i owns the CONTIGUOUS run K[i * LD + 0..n) and reads / writes it with 128-bit accesses (LD is even
+  // and = 14 or 2 mod 16: conflict-free per quarter warp); the pivot rows are gathered with stride LD (lanes adjacent: conflict-free).
+  static_assert((LD % 2) == 0, "128-bit accesses to a thread's run");
+  const int i = threadIdx.x;
+  double *Ki = K + (size_t)i * LD;
+  int p0 = 0;
+  for (; p0 + 3 < n; p0 += 4) {
+    if (i < n) {  // stage entry i of the 4 pivot lines: prow4[i][q] = M[p0+q][i]
+      double2 a, b;
+      a.x = K[p0 * LD + i];
+      a.y = K[(p0 + 1) * LD + i];
+      b.x = K[(p0 + 2) * LD + i];
+      b.y = K[(p0 + 3) * LD + i];
+      *reinterpret_cast<double2 *>(prow4 + 4 * i) = a;
+      *reinterpret_cast<double2 *>(prow4 + 4 * i + 2) = b;
+    }
+    __syncthreads();
+    if (i < n) {
+      // D[q][q'] = M[p0+q][p0+q'] = prow4[p0+q'][q]; 4x4 inverse through 2x2 blocks (two reciprocals)
       double D[4][4];
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
@@ -285,45 +430,48 @@ __device__ __noinline__ void gj_invert(double *K, int n, double *prow4) {
           for (int q2 = 0; q2 < 4; ++q2) E[q][q2] = rnd<F32>(E[q][q2]);
       }
       const bool inP = (i >= p0) && (i < p0 + 4);
-      // column duty: new pivot-row entries of column i
+      // gather duty: new entries i of the four pivot lines
       {
         const double2 a = *reinterpret_cast<const double2 *>(prow4 + 4 * i);
         const double2 b = *reinterpret_cast<const double2 *>(prow4 + 4 * i + 2);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const double v = inP ? E[q][i - p0] : (E[q][0] * a.x + E[q][1] * a.y + E[q][2] * b.x + E[q][3] * b.y);
-          K[i * LD + p0 + q] = rnd<F32>(v);
+          K[(p0 + q) * LD + i] = rnd<F32>(v);
         }
       }
-      if (!inP) {  // row duty
-        const double c0 = Ki[p0 * LD], c1 = Ki[(p0 + 1) * LD], c2 = Ki[(p0 + 2) * LD], c3 = Ki[(p0 + 3) * LD];
+      if (!inP) {  // run duty
+        const double2 c01 = *reinterpret_cast<const double2 *>(Ki + p0), c23 = *reinterpret_cast<const double2 *>(Ki + p0 + 2);
+        const double c0 = c01.x, c1 = c01.y, c2 = c23.x, c3 = c23.y;
         const double w0 = rnd<F32>(c0 * E[0][0] + c1 * E[1][0] + c2 * E[2][0] + c3 * E[3][0]);
         const double w1 = rnd<F32>(c0 * E[0][1] + c1 * E[1][1] + c2 * E[2][1] + c3 * E[3][1]);
         const double w2 = rnd<F32>(c0 * E[0][2] + c1 * E[1][2] + c2 * E[2][2] + c3 * E[3][2]);
         const double w3 = rnd<F32>(c0 * E[0][3] + c1 * E[1][3] + c2 * E[2][3] + c3 * E[3][3]);
         int j = 0;
-        for (; j + 3 < n; j += 4) {  // 4 elements per trip: 8 broadcast LDS.128 + 4 LDS in flight, two half-sums per element
+        for (; j + 3 < n; j += 4) {  // 4 elements per trip: 8 broadcast LDS.128 (pivot lines) + 2 LDS.128 / 2 STS.128 of the thread's own run
           double2 pa[4], pb[4];
-          double kk[4];
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
             pa[u] = *reinterpret_cast<const double2 *>(prow4 + 4 * (j + u));
             pb[u] = *reinterpret_cast<const double2 *>(prow4 + 4 * (j + u) + 2);
-            kk[u] = Ki[(j + u) * LD];
           }
-#pragma unroll
-          for (int u = 0; u < 4; ++u)  // four independent chains of four FMAs
-            Ki[(j + u) * LD] = rnd<F32>(fma(-w3, pb[u].y, fma(-w2, pb[u].x, fma(-w1, pa[u].y, fma(-w0, pa[u].x, kk[u])))));
+          double2 k01 = *reinterpret_cast<const double2 *>(Ki + j), k23 = *reinterpret_cast<const double2 *>(Ki + j + 2);
+          k01.x = rnd<F32>(fma(-w3, pb[0].y, fma(-w2, pb[0].x, fma(-w1, pa[0].y, fma(-w0, pa[0].x, k01.x)))));
+          k01.y = rnd<F32>(fma(-w3, pb[1].y, fma(-w2, pb[1].x, fma(-w1, pa[1].y, fma(-w0, pa[1].x, k01.y)))));
+          k23.x = rnd<F32>(fma(-w3, pb[2].y, fma(-w2, pb[2].x, fma(-w1, pa[2].y, fma(-w0, pa[2].x, k23.x)))));
+          k23.y = rnd<F32>(fma(-w3, pb[3].y, fma(-w2, pb[3].x, fma(-w1, pa[3].y, fma(-w0, pa[3].x, k23.y)))));
+          *reinterpret_cast<double2 *>(Ki + j) = k01;
+          *reinterpret_cast<double2 *>(Ki + j + 2) = k23;
         }
         for (; j < n; ++j) {
           const double2 a0 = *reinterpret_cast<const double2 *>(prow4 + 4 * j);
           const double2 b0 = *reinterpret_cast<const double2 *>(prow4 + 4 * j + 2);
-          Ki[j * LD] = rnd<F32>(fma(-w3, b0.y, fma(-w2, b0.x, fma(-w1, a0.y, fma(-w0, a0.x, Ki[j * LD])))));
+          Ki[j] = rnd<F32>(fma(-w3, b0.y, fma(-w2, b0.x, fma(-w1, a0.y, fma(-w0, a0.x, Ki[j])))));
         }
-        Ki[p0 * LD] = -w0;
-        Ki[(p0 + 1) * LD] = -w1;
-        Ki[(p0 + 2) * LD] = -w2;
-        Ki[(p0 + 3) * LD] = -w3;
+        double2 m01, m23;
+        m01.x = -w0; m01.y = -w1; m23.x = -w2; m23.y = -w3;
+        *reinterpret_cast<double2 *>(Ki + p0) = m01;
+        *reinterpret_cast<double2 *>(Ki + p0 + 2) = m23;
       }
     }
     __syncthreads();
@@ -332,18 +480,18 @@ __device__ __noinline__ void gj_invert(double *K, int n, double *prow4) {
   for (int p = p0; p < n; ++p) {  // scalar tail
     double pi = 0.0;
     if (i < n) {
-      pi = K[i * LD + p];  // pivot row element (p, i)
+      pi = K[p * LD + i];  // pivot line element (p, i)
       prow[i] = pi;
     }
     __syncthreads();
     if (i < n) {
       const double d = rnd<F32>(1.0 / prow[p]);
       if (i != p) {
-        const double f = rnd<F32>(Ki[p * LD] * d);
-        for (int j = 0; j < n; ++j) Ki[j * LD] = rnd<F32>(fma(-f, prow[j], Ki[j * LD]));
-        Ki[p * LD] = -f;
+        const double f = rnd<F32>(Ki[p] * d);
+        for (int j = 0; j < n; ++j) Ki[j] = rnd<F32>(fma(-f, prow[j], Ki[j]));
+        Ki[p] = -f;
       }
-      K[i * LD + p] = (i == p) ? d : rnd<F32>(pi * d);  // rescaled pivot row, element (p, i)
+      K[p * LD + i] = (i == p) ? d : rnd<F32>(pi * d);  // rescaled pivot line, element (p, i)
     }
     __syncthreads();
   }
@@ -675,18 +823,21 @@ __device__ __noinline__ double chol_solve(const double *K, int n, double b, doub
 
 template <int LD>
 __device__ __forceinline__ double matvec_smem(const double *K, int n, const double *v) {
-  const int i = threadIdx.x;
+  // K is symmetric here (an inverse): thread i reads its contiguous run K[i * LD + j] with 128-bit loads instead of the strided column
+  const double *Ki = K + (size_t)threadIdx.x * LD;
   double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
   int j = 0;
   for (; j + 3 < n; j += 4) {
     const double2 v01 = *reinterpret_cast<const double2 *>(v + j);
     const double2 v23 = *reinterpret_cast<const double2 *>(v + j + 2);
-    a0 = fma(K[j * LD + i], v01.x, a0);
-    a1 = fma(K[(j + 1) * LD + i], v01.y, a1);
-    a2 = fma(K[(j + 2) * LD + i], v23.x, a2);
-    a3 = fma(K[(j + 3) * LD + i], v23.y, a3);
+    const double2 k01 = *reinterpret_cast<const double2 *>(Ki + j);
+    const double2 k23 = *reinterpret_cast<const double2 *>(Ki + j + 2);
+    a0 = fma(k01.x, v01.x, a0);
+    a1 = fma(k01.y, v01.y, a1);
+    a2 = fma(k23.x, v23.x, a2);
+    a3 = fma(k23.y, v23.y, a3);
   }
-  for (; j < n; ++j) a0 = fma(K[j * LD + i], v[j], a0);
+  for (; j < n; ++j) a0 = fma(Ki[j], v[j], a0);
   return (a0 + a1) + (a2 + a3);
 }
 
@@ -741,7 +892,7 @@ template <int BS, int NV, int PREC = 0>
 __global__ void __launch_bounds__(BS, (BS == 64 && !B200QP_TC_GJ) ? 6 : 1) mpc_admm_kernel(const MpcParams P, const MpcBuffers B) {
   constexpr bool R1 = PREC == 1 || PREC == 2, R2 = PREC == 2;  // PREC 3: FP64 with the per-phase cycle counters (its own instantiation,
                                                                 // so that the product kernel carries neither the counters nor their branches)
-  constexpr int LD = NV + 1;
+  constexpr int LD = NV + 2;  // even (128-bit accesses to a thread's run) and = 14 or 2 mod 16 for NV = 60, 96, 128, 156 (conflict-free)
   constexpr int MAXF = NV / 3 + 1;
   extern __shared__ __align__(16) double smem[];
   double *K = smem;                 // [NV * LD]
@@ -1119,7 +1270,8 @@ __global__ void __launch_bounds__(BS, (BS == 64 && !B200QP_TC_GJ) ? 6 : 1) mpc_a
               K[tid * LD + tid] = rnd<R1>(K[tid * LD + tid] + (sigma + rho * Ei));
             }
             __syncthreads();
-            gj_invert<LD, R1>(K, n, prow);
+            if (B200QP_GJ_SYM) gj_invert_sym<LD, R1>(K, n, prow);
+            else gj_invert<LD, R1>(K, n, prow);
           }
           need_factor = false;
           PH(2);
@@ -1292,7 +1444,8 @@ __global__ void __launch_bounds__(BS, (BS == 64 && !B200QP_TC_GJ) ? 6 : 1) mpc_a
           PH(7);
           wred = chol_solve<LD>(K, nr, -grp, red);
         } else {
-          gj_invert<LD, R2>(K, nr, prow);
+          if (B200QP_GJ_SYM) gj_invert_sym<LD, R2>(K, nr, prow);
+          else gj_invert<LD, R2>(K, nr, prow);
           PH(7);
           if (tid < nr) s_v[tid] = rnd<R2>(-grp);
           __syncthreads();
@@ -1592,7 +1745,7 @@ __global__ void mpc_bin_kernel(int n, int N, const uint8_t *__restrict__ contact
 
 template <int BS, int NV>
 static size_t admm_smem_bytes() {
-  return sizeof(double) * ((size_t)NV * (NV + 1) + 6 * BS + 4 * 32);
+  return sizeof(double) * ((size_t)NV * (NV + 2) + 6 * BS + 4 * 32);
 }
 
 template <int BS, int NV, int PREC = 0>
