@@ -121,6 +121,7 @@ struct b200qp_mpc {
   int pcw_grid[2] = {0, 0}, pcw_cond = 0;
   int *d_pcw_rej = nullptr;  // [2][max_batch] hand-over lists
   bool poison_smem = false;  // B200QP_POISON_SMEM=1 (development)
+  int in_chunks = 4;         // record chunks of the streamed H2D copy (B200QP_IN_CHUNKS, 1..16)
   bool ric_legacy = false;   // B200QP_RICCATI_LEGACY=1: block kernel only (A/B runs)
   // pinned staging
   double *h_in = nullptr, *h_forces = nullptr, *h_xpred = nullptr;
@@ -323,6 +324,10 @@ int32_t b200qp_mpc_create(const b200qp_mpc_config *cfg, b200qp_mpc **out) {
   if (cfg->solver == B200QP_SOLVER_SPARSE_RICCATI) {
     h->ric_legacy = getenv("B200QP_RICCATI_LEGACY") != nullptr;
     h->poison_smem = getenv("B200QP_POISON_SMEM") != nullptr;
+    if (const char *ic = getenv("B200QP_IN_CHUNKS")) {
+      const int v = atoi(ic);
+      if (v >= 1 && v <= 16) h->in_chunks = v;
+    }
     if (const char *wm = getenv("B200QP_IPM_WARM_MU")) h->ipm_warm_mu = atof(wm) > 0 ? atof(wm) : h->ipm_warm_mu;
     // blocks of the warp-per-problem kernel: cond_N as given (cond_N = horizon: one stage per block, the sparse formulation proper);
     // default: two stages per block - same Newton direction, fewer and better filled block factorisations
@@ -689,7 +694,7 @@ int32_t b200qp_mpc_solve_batch(b200qp_mpc *h, int32_t n, const double *in, const
   // The records (2.3 KB per problem, the bulk of the input) go up in chunks on the copy stream while the condensed kernel is
   // already solving the chunks that have landed: a per-chunk flag, written by a 4-byte copy queued behind the chunk's data,
   // is what the kernel polls before it stages a record.  The Riccati kernel has no such wait, so only CONDENSED_ADMM streams.
-  const int chunks = (h->cfg.solver == B200QP_SOLVER_CONDENSED_ADMM && !h->no_zero_copy && h->async_engines >= 1 && n >= 2048) ? 4 : 1;
+  const int chunks = (h->cfg.solver == B200QP_SOLVER_CONDENSED_ADMM && !h->no_zero_copy && h->async_engines >= 1 && n >= 2048) ? h->in_chunks : 1;
   if (chunks == 1) {
     CK(cudaMemcpyAsync(h->d_in, src_in, in_b, cudaMemcpyHostToDevice, h->stream));
     return solve_and_fetch(h, n, forces, xpred, info);
