@@ -71,6 +71,25 @@ def test_batched_state_slots_follow_live_reference_objects(adaptive, variant):
     m.close()
 
 
+@pytest.mark.parametrize("N", [16, 20])
+@pytest.mark.parametrize("adaptive", [False, True])
+def test_other_horizons_follow_live_reference_objects(adaptive, N):
+    from oracle import ref_binding as rb
+
+    if not rb.available(N):
+        pytest.skip("oracle/_ref not built for this horizon")
+    robots = sc.make_streams(48, 40, seed=900 + adaptive + N, adaptive=adaptive, phase_offset=(0.0, 0.5, 0.5, 0.0), speed=2.0, hold=(4, 12))
+    want_rec, want_ct = sc.reference_records(robots, N, adaptive=adaptive)
+    m = _mpc(N, solver="SPARSE_RICCATI")
+    m.sequencer_configure("adaptive" if adaptive else "simple", phase_offset=(0.0, 0.5, 0.5, 0.0), **sc.OPTIONS, **sc.ADAPTIVE)
+    for i in range(len(robots[0]["calls"])):
+        rows, meas = sc.pack_call(robots, i)
+        rec, ct = m.sequencer_step(rows, meas)
+        assert np.array_equal(ct, want_ct[i]), i
+        np.testing.assert_allclose(rec, want_rec[i], rtol=0, atol=1e-11)
+    m.close()
+
+
 def test_step_solve_is_step_then_solve():
     N = 10
     robots = sc.make_streams(128, 6, seed=9)

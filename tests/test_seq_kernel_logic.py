@@ -47,12 +47,14 @@ def test_host_build_of_the_kernel_reproduces_the_committed_reference_sequences(n
 
 
 @needs_emu
+@pytest.mark.parametrize("N", [10, 16, 20])
 @pytest.mark.parametrize("adaptive", [False, True])
-def test_host_build_of_the_kernel_follows_live_reference_objects(adaptive):
-    if not _have_ref():
-        pytest.skip("oracle/_ref not built")
-    N = 10
-    robots = sc.make_streams(24, 40, seed=5 + adaptive, adaptive=adaptive)
+def test_host_build_of_the_kernel_follows_live_reference_objects(adaptive, N):
+    from oracle import ref_binding as rb
+
+    if not rb.available(N):
+        pytest.skip("oracle/_ref not built for this horizon")
+    robots = sc.make_streams(24 if N == 10 else 10, 40, seed=5 + adaptive + N, adaptive=adaptive)
     want_rec, want_ct = sc.reference_records(robots, N, adaptive=adaptive)
     # one sequencer object per robot in the reference <-> one state slot per robot here; phase offsets are per object
     for r, rob in enumerate(robots):
