@@ -17,6 +17,8 @@ cudaError_t launch_gait_schedule(int n, int steps, double dt, const double *peri
                                  cudaStream_t st);
 cudaError_t launch_mpc_bin(int n, int N, const uint8_t *contact, int *bin_count, int *bin_lists,
                            b200qp_solver_info *info, int overflow_bin, cudaStream_t st);
+cudaError_t launch_mpc_bin_list(const int *src, const int *src_count, int n, int N, const uint8_t *contact, int *bin_count, int *bin_lists,
+                                cudaStream_t st);
 cudaError_t launch_mpc_admm(int bin, const MpcParams &P, const MpcBuffers &B, int grid, cudaStream_t st);
 int admm_block_size(int bin);
 cudaError_t fp64_peak(int num_sms, double *tflops);
@@ -121,6 +123,8 @@ struct b200qp_mpc {
   int pcw_grid[2] = {0, 0}, pcw_cond = 0;
   int *d_pcw_rej = nullptr;  // [2][max_batch] hand-over lists
   bool poison_smem = false;  // B200QP_POISON_SMEM=1 (development)
+  bool ipm_refine = true;    // SPARSE_RICCATI: second opinion by the active-set kernel for stall-accepted problems (B200QP_IPM_REFINE=0: off)
+  int *d_refine = nullptr;   // [max_batch] list + [8] counters (list length, 4 bin counts ... ) at the end
   int in_chunks = 4;         // record chunks of the streamed H2D copy (B200QP_IN_CHUNKS, 1..16)
   bool ric_legacy = false;   // B200QP_RICCATI_LEGACY=1: block kernel only (A/B runs)
   // pinned staging
@@ -181,6 +185,9 @@ static void fill_params(b200qp_mpc *h) {
   P.ipm_warm_x = nullptr;
   P.ipm_warm_valid = nullptr;
   P.ipm_warm_mu = 1.0;
+  P.ipm_refine_list = nullptr;
+  P.ipm_refine_count = nullptr;
+  P.ipm_refine_thr = 1e-10;
   P.ipm_flags = getenv("B200QP_IPM_FLAGS") ? atoi(getenv("B200QP_IPM_FLAGS")) : 3;  // separate primal / dual step lengths + two-cycle guard
   if (c.precision == 2 && !(c.kkt_tol > 0)) P.kkt_tol = 5e-2;  // FP32 polish: stationarity of O(1e-3) is all there is
 }
@@ -311,7 +318,12 @@ int32_t b200qp_mpc_create(const b200qp_mpc_config *cfg, b200qp_mpc **out) {
     h->pc_grid = g;
     CK(cudaMalloc(&h->d_pc_scratch, (size_t)g * pcond_scratch_doubles(cfg->horizon) * sizeof(double)));
   }
-  if (cfg->solver == B200QP_SOLVER_CONDENSED_ADMM || cfg->solver == B200QP_SOLVER_AUTO) {
+  if (cfg->solver == B200QP_SOLVER_SPARSE_RICCATI) {
+    h->ipm_refine = !(getenv("B200QP_IPM_REFINE") && atoi(getenv("B200QP_IPM_REFINE")) == 0) && getenv("B200QP_RICCATI_LEGACY") == nullptr;
+    if (h->ipm_refine) CK(cudaMalloc(&h->d_refine, (nb + 16) * sizeof(int)));
+  }
+  if (cfg->solver == B200QP_SOLVER_CONDENSED_ADMM || cfg->solver == B200QP_SOLVER_AUTO ||
+      (cfg->solver == B200QP_SOLVER_SPARSE_RICCATI && h->ipm_refine)) {
     for (int b = 0; b < 4; ++b) {
       const int bs = admm_block_size(b);
       int g = h->num_sms * admm_occupancy(b);
@@ -399,6 +411,7 @@ void b200qp_mpc_destroy(b200qp_mpc *h) {
   cudaFree(h->d_pc_scratch);
   cudaFree(h->d_pcw_scratch[0]);
   cudaFree(h->d_pcw_scratch[1]);
+  cudaFree(h->d_refine);
   cudaFree(h->d_pcw_rej);
   cudaFreeHost(h->h_in);
   cudaFreeHost(h->h_contact);
@@ -511,6 +524,7 @@ static int32_t solve_device_impl(b200qp_mpc *h, int32_t n, const double *d_in, c
       B.hscratch = h->d_hscratch[b];
       B.retry_list = autosel ? h->d_retry : nullptr;
       B.retry_count = autosel ? h->d_bin_count + 10 : nullptr;
+      B.refine = 0;
       B.warm_mode = (h->cfg.warm_start > 0 && h->d_warm_x != nullptr && dbg_index < 0 && !h->want_duals) ? h->cfg.warm_start : 0;
       B.warm_x = h->d_warm_x;
       B.warm_y = h->d_warm_y;
@@ -549,12 +563,55 @@ static int32_t solve_device_impl(b200qp_mpc *h, int32_t n, const double *d_in, c
       Pw.ipm_warm_valid = h->d_warm_valid;
       Pw.ipm_warm_mu = h->ipm_warm_mu;
     }
+    const bool refine = h->ipm_refine && h->d_refine != nullptr && dbg_index < 0;
+    int *ref_cnt = h->d_refine + h->cfg.max_batch;  // [0] list length, [1..4] bin counts, [5..8] work counters
+    if (refine) {
+      CK(cudaMemsetAsync(ref_cnt, 0, 16 * sizeof(int), h->stream));
+      Pw.ipm_refine_list = h->d_refine;
+      Pw.ipm_refine_count = ref_cnt;
+    }
     CK(launch_mpc_pcw(Pw, n, d_in, d_contact, d_forces, d_xpred, d_info, lb, lg, h->d_pcw_scratch[0], h->d_bin_count + 14, h->pcw_grid[0],
                       h->stream, nullptr, nullptr, rej0, h->d_bin_count + 12, h->pcw_cond, 1, h->d_dbg_cycles));
     (void)rej1;
-    CK(launch_mpc_riccati(h->P, n, d_in, d_contact, d_forces, d_xpred, d_info, lb, lg, h->d_ric_scratch, h->d_bin_count + 9, h->ric_grid,
+    CK(launch_mpc_riccati(Pw, n, d_in, d_contact, d_forces, d_xpred, d_info, lb, lg, h->d_ric_scratch, h->d_bin_count + 9, h->ric_grid,
                           h->stream, nullptr, rej0, h->d_bin_count + 12));
     launches += 2;
+    if (refine) {
+      // second opinion: what the interior-point kernel only solved by its stall rule goes through the condensed ADMM + polish kernel
+      // (where it fits, n <= 156); that kernel overwrites forces / prediction / record only when it succeeds
+      CK(launch_mpc_bin_list(h->d_refine, ref_cnt, n, N, d_contact, ref_cnt + 1, h->d_bin_lists, h->stream));
+      for (int b = 0; b < 4; ++b) {
+        MpcBuffers B;
+        B.in = d_in;
+        B.contact = d_contact;
+        B.forces = d_forces;
+        B.xpred = d_xpred;
+        B.info = d_info;
+        B.lam_box = lb;
+        B.lam_g = lg;
+        B.bin_list = h->d_bin_lists + (size_t)b * n;
+        B.bin_count = ref_cnt + 1 + b;
+        B.bin_next = ref_cnt + 5 + b;
+        B.hscratch = h->d_hscratch[b];
+        B.retry_list = nullptr;
+        B.retry_count = nullptr;
+        B.refine = 1;
+        B.warm_mode = 0;
+        B.warm_x = nullptr;
+        B.warm_y = nullptr;
+        B.warm_valid = nullptr;
+        B.ready = nullptr;
+        B.ready_chunk = 0;
+        B.dbg_index = -1;
+        B.dbg_H = nullptr;
+        B.dbg_g = nullptr;
+        B.dbg_cycles = nullptr;
+        int g = h->grid[b] < 2 * h->num_sms ? h->grid[b] : 2 * h->num_sms;  // a few hundred problems at most
+        if (g > n) g = n;
+        CK(launch_mpc_admm(b, h->P, B, g, h->stream));
+      }
+      launches += 5;
+    }
   } else if (h->cfg.solver == B200QP_SOLVER_SPARSE_RICCATI || autosel) {  // whole batch, or (AUTO) the problems too large for the condensed kernel
     cudaStream_t st = h->stream;
     if (autosel) {

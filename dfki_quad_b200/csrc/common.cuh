@@ -24,6 +24,11 @@ struct MpcParams {
   double *ipm_warm_x;        // [max_batch][N][12] or nullptr
   uint8_t *ipm_warm_valid;   // [max_batch]
   double ipm_warm_mu;        // complementarity the warm-started slack / multiplier pairs begin at
+  // second opinion for the interior-point path (solver SPARSE_RICCATI): solved problems whose final residual is above ipm_refine_thr are
+  // listed here and re-solved by the condensed ADMM + active-set polish kernel, which overwrites the outputs only if it succeeds
+  int *ipm_refine_list;
+  int *ipm_refine_count;
+  double ipm_refine_thr;
   int ipm_flags;             // warp Riccati kernel: bit 0 separate primal / dual step lengths, bit 1 centre two steps when the gap did not fall
 };
 
@@ -59,6 +64,7 @@ struct MpcBuffers {
   // Riccati kernel; nullptr otherwise
   int *retry_list;
   int *retry_count;
+  int refine;  // 1: this launch re-solves problems that already have a solution (second opinion): a failure leaves info untouched
   // chunked input streaming (host-buffer entry point): ready[c] != 0 once the records of chunk c = prob / ready_chunk have
   // landed in device memory; nullptr = everything is resident
   const int *ready;

@@ -1711,7 +1711,7 @@ __global__ void __launch_bounds__(BS, (BS == 64 && !B200QP_TC_GJ) ? 6 : 1) mpc_a
       inf.kkt[1] = 0.0;  // dynamics hold by construction of the roll-out
       inf.kkt[2] = kkt_ineq;
       inf.kkt[3] = kkt_comp;
-      B.info[prob] = inf;
+      if (!(B.refine != 0 && status != B200QP_ACADOS_SUCCESS)) B.info[prob] = inf;  // a failed second opinion leaves the first answer's record
       if (B.retry_list != nullptr && (status == B200QP_ACADOS_MAXITER || status == B200QP_ACADOS_MINSTEP))
         B.retry_list[atomicAdd(B.retry_count, 1)] = prob;
     }
@@ -1741,6 +1741,21 @@ __global__ void mpc_bin_kernel(int n, int N, const uint8_t *__restrict__ contact
   }
   const int pos = atomicAdd(bin_count + bin, 1);
   bin_lists[(size_t)bin * n + pos] = p;
+}
+
+// the same binning for a list of problem indices (second opinion for the interior-point path); sizes the condensed kernel cannot take are dropped
+__global__ void mpc_bin_list_kernel(const int *__restrict__ src, const int *__restrict__ src_count, int n, int N,
+                                    const uint8_t *__restrict__ contact, int *bin_count, int *bin_lists) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= *src_count) return;
+  const int p = src[k];
+  const uint8_t *ct = contact + (size_t)p * N * 4;
+  int cnt = 0;
+  for (int e = 0; e < 4 * N; ++e) cnt += ct[e] != 0;
+  const int nv = 3 * cnt;
+  const int bin = nv <= 60 ? 0 : nv <= 96 ? 1 : nv <= 128 ? 2 : nv <= 156 ? 3 : 4;
+  if (bin == 4) return;
+  bin_lists[(size_t)bin * n + atomicAdd(bin_count + bin, 1)] = p;
 }
 
 template <int BS, int NV>
@@ -1779,6 +1794,12 @@ int admm_block_size(int bin) { return bin == 0 ? 64 : bin == 1 ? 96 : bin == 2 ?
 cudaError_t launch_mpc_bin(int n, int N, const uint8_t *contact, int *bin_count, int *bin_lists,
                            b200qp_solver_info *info, int overflow_bin, cudaStream_t st) {
   mpc_bin_kernel<<<(n + 127) / 128, 128, 0, st>>>(n, N, contact, bin_count, bin_lists, info, overflow_bin);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_mpc_bin_list(const int *src, const int *src_count, int n, int N, const uint8_t *contact, int *bin_count, int *bin_lists,
+                                cudaStream_t st) {
+  mpc_bin_list_kernel<<<(n + 127) / 128, 128, 0, st>>>(src, src_count, n, N, contact, bin_count, bin_lists);
   return cudaGetLastError();
 }
 

@@ -915,6 +915,12 @@ __global__ void __launch_bounds__(32) mpc_pcw_kernel(const MpcParams P, int npro
     }
     if (lane == 0) {
       if (P.ipm_warm_x != nullptr) P.ipm_warm_valid[prob] = (status == B200QP_ACADOS_SUCCESS) ? 1 : 0;
+      // solved, but only by the stall rule (residual between the target and the tolerance): these carry the GRF error tail of the
+      // interior-point path (degenerate vertices, cost flat along directions only alpha penalises) - ask the active-set kernel
+      // ... and so do the problems it gave up on (iteration cap, step collapse): a failure then needs both kernels to fail
+      if (P.ipm_refine_list != nullptr && ((status == B200QP_ACADOS_SUCCESS && fmax(k_stat, k_comp) > P.ipm_refine_thr) ||
+                                           status == B200QP_ACADOS_MAXITER || status == B200QP_ACADOS_MINSTEP))
+        P.ipm_refine_list[atomicAdd(P.ipm_refine_count, 1)] = prob;
       b200qp_solver_info inf;
       inf.status = status;
       inf.iterations = iter;
