@@ -545,10 +545,14 @@ def extra_config3(args, dev, rank, world, steps=3):
     raw = {}
     # riccati_kernel: the warp-per-problem Riccati IPM (mpc_pcw.cu), its default pairs stages (cond_N = N / 2); the cond_N = N run is the
     # same kernel with single-stage blocks (the fully sparse end of the reference's cond_N axis, mpc.cpp:219-225)
-    for key, solver, kw in (("riccati_kernel", "SPARSE_RICCATI", {}), ("riccati_kernel_cond_N_16", "SPARSE_RICCATI", dict(condensing_N=16)),
+    for key, solver, kw in (("riccati_kernel", "SPARSE_RICCATI", {}), ("riccati_kernel_without_second_opinion", "SPARSE_RICCATI", {}),
+                            ("riccati_kernel_cond_N_16", "SPARSE_RICCATI", dict(condensing_N=16)),
                             ("partial_condensing_cond_N_4", "PARTIAL_CONDENSING", dict(condensing_N=4)), ("auto", "AUTO", {})):
+        if key == "riccati_kernel_without_second_opinion":
+            os.environ["B200QP_IPM_REFINE"] = "0"  # read at handle creation: the interior-point kernels alone (error tail of DESIGN 3.3b)
         mpc = BatchedMPC(cfg["alpha"], cfg["state_weights_move"], cfg["mu"], cfg["fmin"], cfg["fmax"], solver, horizon=N, dt=cfg["dt"],
                          max_batch=B, device=dev, **kw)
+        os.environ.pop("B200QP_IPM_REFINE", None)
         ext = torch.cuda.ExternalStream(mpc.stream(), device=dev)
         r = _mpc_pass(mpc, ext, dev, B, N, batch["rec"], batch["contact"], steps, 3, flush)
         mpc.close()
