@@ -124,7 +124,9 @@ struct b200qp_mpc {
   int *d_pcw_rej = nullptr;  // [2][max_batch] hand-over lists
   bool poison_smem = false;  // B200QP_POISON_SMEM=1 (development)
   bool ipm_refine = true;    // SPARSE_RICCATI: second opinion by the active-set kernel for stall-accepted problems (B200QP_IPM_REFINE=0: off)
-  int *d_refine = nullptr;   // [max_batch] list + [8] counters (list length, 4 bin counts ... ) at the end
+  int *d_refine = nullptr;   // [max_batch] list + [16] counters (list length, 4 bin counts, 4 work counters) at the end
+  double *d_refine_x = nullptr, *d_refine_y = nullptr;  // hot start of the second opinion: forces / duals of the interior-point answer
+  uint8_t *d_refine_valid = nullptr;
   int in_chunks = 4;         // record chunks of the streamed H2D copy (B200QP_IN_CHUNKS, 1..16)
   bool ric_legacy = false;   // B200QP_RICCATI_LEGACY=1: block kernel only (A/B runs)
   // pinned staging
@@ -188,6 +190,9 @@ static void fill_params(b200qp_mpc *h) {
   P.ipm_refine_list = nullptr;
   P.ipm_refine_count = nullptr;
   P.ipm_refine_thr = 1e-10;
+  P.ipm_refine_x = nullptr;
+  P.ipm_refine_y = nullptr;
+  P.ipm_refine_valid = nullptr;
   P.ipm_flags = getenv("B200QP_IPM_FLAGS") ? atoi(getenv("B200QP_IPM_FLAGS")) : 3;  // separate primal / dual step lengths + two-cycle guard
   if (c.precision == 2 && !(c.kkt_tol > 0)) P.kkt_tol = 5e-2;  // FP32 polish: stationarity of O(1e-3) is all there is
 }
@@ -320,7 +325,15 @@ int32_t b200qp_mpc_create(const b200qp_mpc_config *cfg, b200qp_mpc **out) {
   }
   if (cfg->solver == B200QP_SOLVER_SPARSE_RICCATI) {
     h->ipm_refine = !(getenv("B200QP_IPM_REFINE") && atoi(getenv("B200QP_IPM_REFINE")) == 0) && getenv("B200QP_RICCATI_LEGACY") == nullptr;
-    if (h->ipm_refine) CK(cudaMalloc(&h->d_refine, (nb + 16) * sizeof(int)));
+    if (h->ipm_refine) {
+      CK(cudaMalloc(&h->d_refine, (nb + 16) * sizeof(int)));
+      if (!(getenv("B200QP_IPM_REFINE_COLD"))) {
+        CK(cudaMalloc(&h->d_refine_x, nb * N * 12 * sizeof(double)));
+        CK(cudaMalloc(&h->d_refine_y, nb * N * 28 * sizeof(double)));
+        CK(cudaMalloc(&h->d_refine_valid, nb));
+        CK(cudaMemset(h->d_refine_valid, 0, nb));
+      }
+    }
   }
   if (cfg->solver == B200QP_SOLVER_CONDENSED_ADMM || cfg->solver == B200QP_SOLVER_AUTO ||
       (cfg->solver == B200QP_SOLVER_SPARSE_RICCATI && h->ipm_refine)) {
@@ -412,6 +425,9 @@ void b200qp_mpc_destroy(b200qp_mpc *h) {
   cudaFree(h->d_pcw_scratch[0]);
   cudaFree(h->d_pcw_scratch[1]);
   cudaFree(h->d_refine);
+  cudaFree(h->d_refine_x);
+  cudaFree(h->d_refine_y);
+  cudaFree(h->d_refine_valid);
   cudaFree(h->d_pcw_rej);
   cudaFreeHost(h->h_in);
   cudaFreeHost(h->h_contact);
@@ -569,6 +585,9 @@ static int32_t solve_device_impl(b200qp_mpc *h, int32_t n, const double *d_in, c
       CK(cudaMemsetAsync(ref_cnt, 0, 16 * sizeof(int), h->stream));
       Pw.ipm_refine_list = h->d_refine;
       Pw.ipm_refine_count = ref_cnt;
+      Pw.ipm_refine_x = h->d_refine_x;
+      Pw.ipm_refine_y = h->d_refine_y;
+      Pw.ipm_refine_valid = h->d_refine_valid;
     }
     CK(launch_mpc_pcw(Pw, n, d_in, d_contact, d_forces, d_xpred, d_info, lb, lg, h->d_pcw_scratch[0], h->d_bin_count + 14, h->pcw_grid[0],
                       h->stream, nullptr, nullptr, rej0, h->d_bin_count + 12, h->pcw_cond, 1, h->d_dbg_cycles));
@@ -596,10 +615,10 @@ static int32_t solve_device_impl(b200qp_mpc *h, int32_t n, const double *d_in, c
         B.retry_list = nullptr;
         B.retry_count = nullptr;
         B.refine = 1;
-        B.warm_mode = 0;
-        B.warm_x = nullptr;
-        B.warm_y = nullptr;
-        B.warm_valid = nullptr;
+        B.warm_mode = h->d_refine_x != nullptr ? 2 : 0;  // hot: the interior-point answer's active set goes straight to the polish
+        B.warm_x = h->d_refine_x;
+        B.warm_y = h->d_refine_y;
+        B.warm_valid = h->d_refine_valid;
         B.ready = nullptr;
         B.ready_chunk = 0;
         B.dbg_index = -1;

@@ -29,6 +29,11 @@ struct MpcParams {
   int *ipm_refine_list;
   int *ipm_refine_count;
   double ipm_refine_thr;
+  // ... which starts from the interior-point answer: forces [max_batch][N][12] and duals in its own row layout [max_batch][N][4][7]
+  // (3 box rows, 4 pyramid rows), so that its polish gets the active set directly (hot start) and only the K^-1 / ADMM-free path runs
+  double *ipm_refine_x;
+  double *ipm_refine_y;
+  uint8_t *ipm_refine_valid;
   int ipm_flags;             // warp Riccati kernel: bit 0 separate primal / dual step lengths, bit 1 centre two steps when the gap did not fall
 };
 

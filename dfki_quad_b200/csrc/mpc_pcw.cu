@@ -897,6 +897,23 @@ __global__ void __launch_bounds__(32) mpc_pcw_kernel(const MpcParams P, int npro
         const int k = e / 13, c = e - 13 * k;
         xo[e] = (c < 12) ? sX[12 * k + c] : sX0[12];
       }
+      if (P.ipm_refine_x != nullptr && fmax(k_stat, k_comp) > P.ipm_refine_thr) {  // hand the answer to the second opinion (hot start)
+        double *rx = P.ipm_refine_x + (size_t)prob * N * 12, *ry = P.ipm_refine_y + (size_t)prob * N * 28;
+        for (int e = lane; e < N * 12; e += 32) rx[e] = 0.0;
+        for (int e = lane; e < N * 28; e += 32) ry[e] = 0.0;
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < FS; ++q) {
+          const int j = lane + 32 * q;
+          if (j < nfs) {
+            double *f3 = rx + 3 * sFs[j], *y7 = ry + 7 * sFs[j];
+            f3[0] = sU[3 * j]; f3[1] = sU[3 * j + 1]; f3[2] = sU[3 * j + 2];
+            y7[0] = z[q][0] - z[q][1]; y7[1] = z[q][2] - z[q][3]; y7[2] = z[q][4] - z[q][5];
+            y7[3] = z[q][6]; y7[4] = -z[q][7]; y7[5] = z[q][8]; y7[6] = -z[q][9];
+          }
+        }
+        if (lane == 0) P.ipm_refine_valid[prob] = 1;
+      }
       if (lam_box != nullptr) {
         double *lb = lam_box + (size_t)prob * N * 12, *lg = lam_g + (size_t)prob * N * 16;
         for (int e = lane; e < N * 12; e += 32) lb[e] = 0.0;
@@ -918,6 +935,7 @@ __global__ void __launch_bounds__(32) mpc_pcw_kernel(const MpcParams P, int npro
       // solved, but only by the stall rule (residual between the target and the tolerance): these carry the GRF error tail of the
       // interior-point path (degenerate vertices, cost flat along directions only alpha penalises) - ask the active-set kernel
       // ... and so do the problems it gave up on (iteration cap, step collapse): a failure then needs both kernels to fail
+      if (P.ipm_refine_valid != nullptr && status != B200QP_ACADOS_SUCCESS) P.ipm_refine_valid[prob] = 0;  // gave up: the second kernel starts cold
       if (P.ipm_refine_list != nullptr && ((status == B200QP_ACADOS_SUCCESS && fmax(k_stat, k_comp) > P.ipm_refine_thr) ||
                                            status == B200QP_ACADOS_MAXITER || status == B200QP_ACADOS_MINSTEP))
         P.ipm_refine_list[atomicAdd(P.ipm_refine_count, 1)] = prob;

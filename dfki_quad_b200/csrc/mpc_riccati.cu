@@ -737,6 +737,7 @@ __global__ void __launch_bounds__(BS, MINB) mpc_riccati_kernel(const MpcParams P
       inf.kkt[2] = k_ineq;
       inf.kkt[3] = k_comp;
       info[prob] = inf;
+      if (P.ipm_refine_valid != nullptr) P.ipm_refine_valid[prob] = 0;  // this kernel hands no starting point over: cold second opinion
       if (P.ipm_refine_list != nullptr && ((status == B200QP_ACADOS_SUCCESS && fmax(k_stat, k_comp) > P.ipm_refine_thr) ||
                                            status == B200QP_ACADOS_MAXITER || status == B200QP_ACADOS_MINSTEP))
         P.ipm_refine_list[atomicAdd(P.ipm_refine_count, 1)] = prob;  // second opinion by the active-set kernel (see mpc_pcw.cu)
