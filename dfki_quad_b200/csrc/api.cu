@@ -38,6 +38,7 @@ cudaError_t launch_mpc_pcw(const MpcParams &P, int n, const double *in, const ui
 int pcw_grid(int num_sms, int N, int fs, int condN);
 cudaError_t launch_smem_polluter(int num_sms, cudaStream_t st);
 size_t pcw_scratch_doubles(int N, int fs);
+void pcw_hot_region(int N, int fs, int grid, double *scratch, double **ptr, size_t *bytes);
 size_t pcond_scratch_doubles(int N);
 cudaError_t launch_sequencer(int n, const SeqModel &M, const double *seq_in, const uint8_t *measured, double *rec_out,
                              uint8_t *contact_out, int in_stride, cudaStream_t st);
@@ -127,6 +128,8 @@ struct b200qp_mpc {
   int *d_refine = nullptr;   // [max_batch] list + [16] counters (list length, 4 bin counts, 4 work counters) at the end
   double *d_refine_x = nullptr, *d_refine_y = nullptr;  // hot start of the second opinion: forces / duals of the interior-point answer
   uint8_t *d_refine_valid = nullptr;
+  size_t l2_window_max = 0;
+  size_t l2_persist = 0;     // bytes of L2 set aside for persisting accesses (hot scratch of the warp Riccati kernel), 0: not available
   int in_chunks = 4;         // record chunks of the streamed H2D copy (B200QP_IN_CHUNKS, 1..16)
   bool ric_legacy = false;   // B200QP_RICCATI_LEGACY=1: block kernel only (A/B runs)
   // pinned staging
@@ -325,6 +328,13 @@ int32_t b200qp_mpc_create(const b200qp_mpc_config *cfg, b200qp_mpc **out) {
   }
   if (cfg->solver == B200QP_SOLVER_SPARSE_RICCATI) {
     h->ipm_refine = !(getenv("B200QP_IPM_REFINE") && atoi(getenv("B200QP_IPM_REFINE")) == 0) && getenv("B200QP_RICCATI_LEGACY") == nullptr;
+    if (!getenv("B200QP_NO_L2_PERSIST") && prop.persistingL2CacheMaxSize > 0) {
+      size_t want = (size_t)32 << 20;
+      if (want > (size_t)prop.persistingL2CacheMaxSize) want = (size_t)prop.persistingL2CacheMaxSize;
+      if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) h->l2_persist = want;
+      else cudaGetLastError();
+      h->l2_window_max = (size_t)prop.accessPolicyMaxWindowSize;
+    }
     if (h->ipm_refine) {
       CK(cudaMalloc(&h->d_refine, (nb + 16) * sizeof(int)));
       if (!(getenv("B200QP_IPM_REFINE_COLD"))) {
@@ -363,14 +373,8 @@ int32_t b200qp_mpc_create(const b200qp_mpc_config *cfg, b200qp_mpc **out) {
       if ((size_t)g > nb) g = (int)nb;
       h->pcw_grid[v] = g;
       CK(cudaMalloc(&h->d_pcw_scratch[v], (size_t)g * pcw_scratch_doubles(cfg->horizon, v + 1) * sizeof(double)));
-      if (const char *po = getenv("B200QP_POISON_SCRATCH")) {  // development: NaN-fill [lo, hi) doubles counted from the END of every block's scratch
-        const size_t stride = pcw_scratch_doubles(cfg->horizon, v + 1);
-        long lo = 0, hi = (long)stride;
-        sscanf(po, "%ld:%ld", &lo, &hi);
-        if (hi > (long)stride) hi = (long)stride;
-        if (lo < hi)
-          CK(cudaMemset2D(h->d_pcw_scratch[v] + (stride - (size_t)hi), stride * sizeof(double), 0xFF, (size_t)(hi - lo) * sizeof(double), (size_t)g));
-      }
+      if (getenv("B200QP_POISON_SCRATCH"))  // development: NaN-fill the whole scratch (read-before-write hunts)
+        CK(cudaMemset(h->d_pcw_scratch[v], 0xFF, (size_t)g * pcw_scratch_doubles(cfg->horizon, v + 1) * sizeof(double)));
     }
     CK(cudaMalloc(&h->d_pcw_rej, 2 * nb * sizeof(int)));
   }
@@ -589,8 +593,29 @@ static int32_t solve_device_impl(b200qp_mpc *h, int32_t n, const double *d_in, c
       Pw.ipm_refine_y = h->d_refine_y;
       Pw.ipm_refine_valid = h->d_refine_valid;
     }
+    bool window = false;
+    if (h->l2_persist > 0) {  // keep the per-iteration scratch of the resident warps in L2 for the duration of the launch
+      double *hp = nullptr;
+      size_t hb = 0;
+      pcw_hot_region(N, 1, h->pcw_grid[0] < n ? h->pcw_grid[0] : n, h->d_pcw_scratch[0], &hp, &hb);
+      cudaStreamAttrValue av;
+      memset(&av, 0, sizeof(av));
+      av.accessPolicyWindow.base_ptr = hp;
+      av.accessPolicyWindow.num_bytes = hb < h->l2_window_max ? hb : h->l2_window_max;
+      av.accessPolicyWindow.hitRatio = hb <= h->l2_persist ? 1.0f : (float)((double)h->l2_persist / (double)hb);
+      av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+      av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+      window = cudaStreamSetAttribute(h->stream, cudaStreamAttributeAccessPolicyWindow, &av) == cudaSuccess;
+      if (!window) cudaGetLastError();
+    }
     CK(launch_mpc_pcw(Pw, n, d_in, d_contact, d_forces, d_xpred, d_info, lb, lg, h->d_pcw_scratch[0], h->d_bin_count + 14, h->pcw_grid[0],
                       h->stream, nullptr, nullptr, rej0, h->d_bin_count + 12, h->pcw_cond, 1, h->d_dbg_cycles));
+    if (window) {  // later launches on this stream run without the window
+      cudaStreamAttrValue av;
+      memset(&av, 0, sizeof(av));
+      av.accessPolicyWindow.num_bytes = 0;
+      cudaStreamSetAttribute(h->stream, cudaStreamAttributeAccessPolicyWindow, &av);
+    }
     (void)rej1;
     CK(launch_mpc_riccati(Pw, n, d_in, d_contact, d_forces, d_xpred, d_info, lb, lg, h->d_ric_scratch, h->d_bin_count + 9, h->ric_grid,
                           h->stream, nullptr, rej0, h->d_bin_count + 12));

@@ -1,5 +1,4 @@
-"""Read-before-write hunt in the warp Riccati kernel: NaN-fill slices of the per-block scratch (B200QP_POISON_SCRATCH=lo:hi, doubles from
-the end of the block's region) and see whether a batch that is solved 100 % otherwise changes."""
+"""Read-before-write hunt in the warp Riccati kernel: NaN-fill the scratch (B200QP_POISON_SCRATCH=1) or every SM's shared memory (B200QP_POISON_SMEM=1) and see whether a batch that is solved 100 % otherwise changes."""
 import os, subprocess, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 if len(sys.argv) > 1:
@@ -15,8 +14,6 @@ if len(sys.argv) > 1:
         m.close()
     print(sys.argv[1], " | ".join(out))
 else:
-    ranges = ["0:0", "0:100000", "0:736", "736:940", "940:1228", "1228:1388", "1388:1484", "1484:1592", "1592:1796", "1796:1892", "1892:1988", "1988:2084",
-              "2084:2400", "2400:100000"]
-    for r in ranges:
-        env = dict(os.environ, B200QP_POISON_SCRATCH=r)
-        subprocess.run([sys.executable, __file__, r], env=env)
+    subprocess.run([sys.executable, __file__, "clean"], env=dict(os.environ))
+    subprocess.run([sys.executable, __file__, "scratch NaN-filled"], env=dict(os.environ, B200QP_POISON_SCRATCH="1"))
+    subprocess.run([sys.executable, __file__, "shared memory NaN-filled"], env=dict(os.environ, B200QP_POISON_SMEM="1"))
