@@ -1,6 +1,6 @@
 import os, subprocess, sys
 sys.path.insert(0, ".")
-if len(sys.argv) > 1:
+if len(sys.argv) > 2 and sys.argv[1] == "--run":
     import numpy as np
     from dfki_quad_b200 import wbc
     import torch
@@ -23,8 +23,11 @@ if len(sys.argv) > 1:
         ext.synchronize()
         best = min(best, e0.elapsed_time(e1))
     st = np.frombuffer(di.cpu().numpy().tobytes(), dtype=np.dtype([("status", "i4"), ("it", "i4"), ("a", "i4"), ("b", "i4"), ("kkt", "f8", (4,))]))
-    print(sys.argv[1], f"{B / best / 1e3 * 1e3:.0f} solves/s  {best:.2f} ms  ok {(st['status'] == 0).mean():.4f} it {st['it'].mean():.2f}")
+    print(sys.argv[2], f"{B / best / 1e3 * 1e3:.0f} solves/s  {best:.2f} ms  ok {(st['status'] == 0).mean():.4f} it {st['it'].mean():.2f}")
 else:
-    for v in ("head", "dot4"):
-        env = dict(os.environ, B200QP_LIB=f"/root/repo/dfki_quad_b200/libb200qp_wbcv{v}.so")
-        subprocess.run([sys.executable, __file__, "variant" + v], env=env)
+    # usage: python scripts/dbg_wbc_ab.py build_a.so build_b.so ...   (absolute paths of library builds to compare on this box)
+    for lib in sys.argv[1:] or [""]:
+        env = dict(os.environ)
+        if lib:
+            env["B200QP_LIB"] = lib
+        subprocess.run([sys.executable, __file__, "--run", os.path.basename(lib) or "default"], env=env)
