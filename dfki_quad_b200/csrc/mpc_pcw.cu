@@ -377,7 +377,7 @@ __global__ void __launch_bounds__(32) mpc_pcw_kernel(const MpcParams P, int npro
 #pragma unroll
       for (int r = 0; r < 10; ++r) {
         s[q][r] = fmax(hh[r] - g0[r], 1e-2);
-        z[q][r] = (warm ? P.ipm_warm_mu : 1.0) / s[q][r];
+        z[q][r] = (warm ? P.ipm_warm_mu : P.ipm_cold_mu) / s[q][r];
         inv_s[q][r] = 1.0;
       }
     }
