@@ -190,6 +190,7 @@ static void fill_params(b200qp_mpc *h) {
   P.ipm_warm_x = nullptr;
   P.ipm_warm_valid = nullptr;
   P.ipm_warm_mu = 1.0;
+  P.ipm_tau = (getenv("B200QP_IPM_TAU") && atof(getenv("B200QP_IPM_TAU")) > 0) ? atof(getenv("B200QP_IPM_TAU")) : 0.9999;
   P.ipm_cold_mu = (getenv("B200QP_IPM_COLD_MU") && atof(getenv("B200QP_IPM_COLD_MU")) > 0) ? atof(getenv("B200QP_IPM_COLD_MU")) : 0.2;
   P.ipm_refine_list = nullptr;
   P.ipm_refine_count = nullptr;

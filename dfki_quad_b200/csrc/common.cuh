@@ -24,6 +24,7 @@ struct MpcParams {
   double *ipm_warm_x;        // [max_batch][N][12] or nullptr
   uint8_t *ipm_warm_valid;   // [max_batch]
   double ipm_warm_mu;        // complementarity the warm-started slack / multiplier pairs begin at
+  double ipm_tau;            // fraction of the step to the boundary that is taken
   double ipm_cold_mu;        // ... and the cold-started ones (z = mu / s at the interior starting point)
   // second opinion for the interior-point path (solver SPARSE_RICCATI): solved problems whose final residual is above ipm_refine_thr are
   // listed here and re-solved by the condensed ADMM + active-set polish kernel, which overwrites the outputs only if it succeeds

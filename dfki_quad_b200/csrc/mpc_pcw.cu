@@ -831,7 +831,7 @@ __global__ void __launch_bounds__(32) mpc_pcw_kernel(const MpcParams P, int npro
           sigma_mu = ratio * ratio * ratio * mu_c;
           if (damp > 0) sigma_mu = fmax(sigma_mu, 0.2 * mu_c);
         } else {
-          double a = fmin(1.0, 0.995 * stp), az = fmin(1.0, 0.995 * stq);
+          double a = fmin(1.0, P.ipm_tau * stp), az = fmin(1.0, P.ipm_tau * stq);
           if (damp > 0) --damp;
           if (r0 < r1) {  // monotone-gap safeguard (see mpc_riccati.cu)
             double c1 = 0.0, c2 = 0.0;
