@@ -16,6 +16,7 @@ struct WbcParams {
   int nq, neq, nin;
   double kkt_tol;
   int max_iter;
+  double tau;  // fraction of the step to the boundary that is taken
 };
 
 namespace {
@@ -341,7 +342,7 @@ __global__ void __launch_bounds__(64, 5) wbc_qp_kernel(const WbcParams P, int np
     }
     __syncthreads();
 
-    int status = B200QP_ACADOS_MAXITER, iter = 0;
+    int status = B200QP_ACADOS_MAXITER, iter = 0, iter_first = 0;
 #ifdef B200QP_WBC_TIMING
     long long wcyc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, wlast = clock64();
 #define WPHW(idx) do { if (tid == 0) { const long long t__ = clock64(); wcyc[idx] += t__ - wlast; wlast = t__; } } while (0)
@@ -351,6 +352,12 @@ __global__ void __launch_bounds__(64, 5) wbc_qp_kernel(const WbcParams P, int np
     WPHW(0);
     double k_stat = 0.0, k_eq = 0.0, k_ineq = 0.0, k_comp = 0.0, bk[4] = {0.0, 0.0, 0.0, 0.0};
     const double target = 1e-4 * P.kkt_tol;
+    // The step takes P.tau (0.9999) of the way to the boundary: 8.5 instead of 10.1 iterations, but about one QP in 30 000 then stalls
+    // near a face; that one is solved again from the start with the conservative 0.995 (everything it needs is still in shared memory)
+    double tau = P.tau;
+#pragma unroll 1
+    for (int attempt = 0; attempt < 2; ++attempt) {
+    status = B200QP_ACADOS_MAXITER;
     double best = WBIG;
     int stall = 0;
     double rpl = 0.0, rpu = 0.0, mu_c = 1.0, mu_prev = WBIG;
@@ -551,7 +558,7 @@ __global__ void __launch_bounds__(64, 5) wbc_qp_kernel(const WbcParams P, int np
           if (damp > 0) sigma_mu = fmax(sigma_mu, 0.2 * mu_c);
           dsl = nsl; dsu = nsu; dzl = nzl; dzu = nzu;
         } else {
-          const double a = fmin(1.0, 0.995 * stp), ad = fmin(1.0, 0.995 * stq);
+          const double a = fmin(1.0, tau * stp), ad = fmin(1.0, tau * stq);
           sl += a * nsl; su += a * nsu; zl += ad * nzl; zu += ad * nzu;
           for (int i = tid; i < nq; i += BS) sx[i] += a * sdx[i];
           for (int r = tid; r < me; r += BS) snu[r] += ad * sdnu[r];
@@ -562,6 +569,11 @@ __global__ void __launch_bounds__(64, 5) wbc_qp_kernel(const WbcParams P, int np
       WPHW(7);
     }
     __syncthreads();
+    if (status == B200QP_ACADOS_SUCCESS || status == B200QP_ACADOS_NAN_DETECTED || tau <= 0.995) break;
+    tau = 0.995;
+    iter_first = iter;
+    }  // attempt
+    __syncthreads();
     if (status == B200QP_ACADOS_SUCCESS)
       for (int i = tid; i < nq; i += BS) xout[(size_t)prob * nq + i] = sbx[i];
 #ifdef B200QP_WBC_TIMING
@@ -570,7 +582,7 @@ __global__ void __launch_bounds__(64, 5) wbc_qp_kernel(const WbcParams P, int np
     if (tid == 0) {
       b200qp_solver_info inf;
       inf.status = status;
-      inf.iterations = iter > 0 ? iter - 1 : 0;
+      inf.iterations = (iter > 0 ? iter - 1 : 0) + iter_first;
       inf.polish_rounds = 0;
       inf.n_free = nq;
       inf.kkt[0] = k_stat;
