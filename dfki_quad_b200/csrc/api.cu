@@ -1275,8 +1275,9 @@ int32_t b200qp_gait_schedule(int32_t device, int32_t n, int32_t steps, double dt
 struct b200qp_wbc {
   b200qp_wbc_config cfg;
   WbcParams P;
-  cudaStream_t stream = nullptr, copy_stream = nullptr;
+  cudaStream_t stream = nullptr, copy_stream = nullptr, aux_stream = nullptr;  // aux: odd chunks of the host-buffer call
   cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   int grid = 0;
   double *d_H = nullptr, *d_g = nullptr, *d_A = nullptr, *d_lo = nullptr, *d_hi = nullptr, *d_x = nullptr;
   b200qp_solver_info *d_info = nullptr, *h_info = nullptr;
@@ -1323,7 +1324,10 @@ int32_t b200qp_wbc_create(const b200qp_wbc_config *cfg, b200qp_wbc **out) {
   const size_t nb = cfg->max_batch, nq = cfg->nq, nc = cfg->neq + cfg->nin;
   CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   CK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking));
   for (int c = 0; c < 8; ++c) CK(cudaEventCreateWithFlags(&h->ev[c], cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
   CK(cudaMallocHost(&h->h_info, (size_t)cfg->max_batch * sizeof(b200qp_solver_info)));
   CK(cudaMalloc(&h->d_H, nb * nq * nq * sizeof(double)));
   CK(cudaMalloc(&h->d_g, nb * nq * sizeof(double)));
@@ -1332,7 +1336,7 @@ int32_t b200qp_wbc_create(const b200qp_wbc_config *cfg, b200qp_wbc **out) {
   CK(cudaMalloc(&h->d_hi, nb * nc * sizeof(double)));
   CK(cudaMalloc(&h->d_x, nb * nq * sizeof(double)));
   CK(cudaMalloc(&h->d_info, nb * sizeof(b200qp_solver_info)));
-  CK(cudaMalloc(&h->d_next, sizeof(int)));
+  CK(cudaMalloc(&h->d_next, 8 * sizeof(int)));  // one work counter per chunk in flight
   guard.h = nullptr;
   *out = h;
   return B200QP_OK;
@@ -1356,7 +1360,10 @@ void b200qp_wbc_destroy(b200qp_wbc *h) {
   cudaFreeHost(h->h_info);
   for (int c = 0; c < 8; ++c)
     if (h->ev[c]) cudaEventDestroy(h->ev[c]);
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->ev_join) cudaEventDestroy(h->ev_join);
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+  if (h->aux_stream) cudaStreamDestroy(h->aux_stream);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
 }
@@ -1382,8 +1389,14 @@ int32_t b200qp_wbc_solve_batch(b200qp_wbc *h, int32_t n, const double *H, const 
   CK(cudaSetDevice(h->cfg.device));
   const size_t nn = n, nq = h->cfg.nq, nc = h->cfg.neq + h->cfg.nin;
   // Large batches are cut into chunks: the H2D copy of chunk c+1 (19.5 KB per QP - this call is PCIe-bound) runs on the
-  // copy stream while chunk c is being solved; results go back per chunk behind its kernel.
-  const int chunks = (n >= 8192) ? 4 : (n >= 2048 ? 2 : 1);
+  // copy stream while chunk c is being solved. Even and odd chunks are solved on two streams, so the blocks of chunk c+1
+  // fill the SMs the tail of chunk c leaves idle (4096 QPs are only 4.6 per resident block); each chunk has its own work counter.
+  static const int wbc_chunks = [] {
+    const char *e = getenv("B200QP_WBC_CHUNKS");
+    const int v = e ? atoi(e) : 8;
+    return (v >= 1 && v <= 8) ? v : 8;
+  }();
+  const int chunks = (n >= 8192) ? wbc_chunks : (n >= 2048 ? (wbc_chunks < 2 ? wbc_chunks : 2) : 1);
   for (int c = 0; c < chunks; ++c) {  // all copies are queued first: a D2H into pageable memory would block the host
     const size_t lo = nn * c / chunks, hi = nn * (c + 1) / chunks, m = hi - lo;
     if (m == 0) continue;
@@ -1395,14 +1408,23 @@ int32_t b200qp_wbc_solve_batch(b200qp_wbc *h, int32_t n, const double *H, const 
     CK(cudaMemcpyAsync(h->d_x + lo * nq, x + lo * nq, m * nq * sizeof(double), cudaMemcpyHostToDevice, h->copy_stream));  // keep caller's x on failure
     CK(cudaEventRecord(h->ev[c], h->copy_stream));
   }
+  CK(cudaMemsetAsync(h->d_next, 0, 8 * sizeof(int), h->stream));
+  if (chunks > 1) {
+    CK(cudaEventRecord(h->ev_fork, h->stream));
+    CK(cudaStreamWaitEvent(h->aux_stream, h->ev_fork, 0));
+  }
   for (int c = 0; c < chunks; ++c) {
     const size_t lo = nn * c / chunks, hi = nn * (c + 1) / chunks, m = hi - lo;
     if (m == 0) continue;
-    CK(cudaStreamWaitEvent(h->stream, h->ev[c], 0));
-    CK(cudaMemsetAsync(h->d_next, 0, sizeof(int), h->stream));
+    cudaStream_t ks = (c & 1) ? h->aux_stream : h->stream;
+    CK(cudaStreamWaitEvent(ks, h->ev[c], 0));
     CK(launch_wbc_qp(h->P, (int)m, h->d_H + lo * nq * nq, h->d_g + lo * nq, h->d_A + lo * nc * nq, h->d_lo + lo * nc, h->d_hi + lo * nc,
-                     h->d_x + lo * nq, h->d_info + lo, h->d_next, h->grid, h->stream));
-    CK(cudaMemcpyAsync(h->h_info + lo, h->d_info + lo, m * sizeof(b200qp_solver_info), cudaMemcpyDeviceToHost, h->stream));
+                     h->d_x + lo * nq, h->d_info + lo, h->d_next + c, h->grid, ks));
+    CK(cudaMemcpyAsync(h->h_info + lo, h->d_info + lo, m * sizeof(b200qp_solver_info), cudaMemcpyDeviceToHost, ks));
+  }
+  if (chunks > 1) {
+    CK(cudaEventRecord(h->ev_join, h->aux_stream));
+    CK(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
   }
   CK(cudaMemcpyAsync(x, h->d_x, nn * nq * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
