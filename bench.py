@@ -710,7 +710,7 @@ def extra_config4(args, dev, rank, world, steps=3):
            "ms_per_step": ms_m / steps, "e2e": {"value": c2 / e2e_m, "unit": "solves/s", "h2d_bytes_per_step": int(B * 19512), "d2h_bytes_per_step": int(B * 288)},
            "converged_fraction": c1 / (B * steps * world), "mean_iterations": float(info["iterations"].mean()),
            "kkt_max_converged": float(info["kkt"][(info["status"] == 0)].max()),
-           "e2e_scene_on_device": {"value": c3 / scene_m, "unit": "solves/s", "h2d_bytes_per_step": int(B * (576 + 240)), "d2h_bytes_per_step": int(B * (240 + 96 + 48)),
+           "e2e_scene_on_device": {"value": c3 / scene_m, "unit": "solves/s", "h2d_bytes_per_step": int(B * 576), "d2h_bytes_per_step": int(B * (240 + 96 + 48)),
                                    "note": "b200qp_wbc_scene_solve_batch: robot state in (576 B), rigid-body terms + TSID scene assembled by kernel K6, x + joint torques out"},
            "config": {"workload": wl["name"], "batch_per_gpu": B, "steps": steps, "l2": "256 MiB flush between timed iterations"}}
     if rank == 0 and not args.no_cpu_baseline:

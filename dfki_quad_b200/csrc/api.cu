@@ -1462,11 +1462,16 @@ int32_t b200qp_wbc_scene_configure(b200qp_wbc *h, const b200qp_wbc_scene_config 
   return B200QP_OK;
 }
 
-static int32_t wbc_scene_queue(b200qp_wbc *h, int32_t n, const double *d_scene, double *d_x, double *d_tau, b200qp_solver_info *d_info) {
-  CK(launch_wbc_scene(n, h->scene, d_scene, h->d_H, h->d_g, h->d_A, h->d_lo, h->d_hi, h->d_feet, h->stream));
-  CK(cudaMemsetAsync(h->d_next, 0, sizeof(int), h->stream));
-  CK(launch_wbc_qp(h->P, n, h->d_H, h->d_g, h->d_A, h->d_lo, h->d_hi, d_x, d_info, h->d_next, h->grid, h->stream));
-  if (d_tau) CK(launch_wbc_torque(n, h->d_A, h->d_lo, h->d_hi, d_x, d_tau, h->stream));
+// Rows [lo, lo + n) of the handle's QP buffers are assembled, solved and turned into torques on stream st with work counter `slot`.
+static int32_t wbc_scene_queue(b200qp_wbc *h, int32_t n, const double *d_scene, double *d_x, double *d_tau, b200qp_solver_info *d_info,
+                               size_t lo = 0, cudaStream_t st = nullptr, int slot = 0) {
+  if (!st) st = h->stream;
+  const size_t nq = 30, nc = 46;
+  double *H = h->d_H + lo * nq * nq, *g = h->d_g + lo * nq, *A = h->d_A + lo * nc * nq, *l = h->d_lo + lo * nc, *u = h->d_hi + lo * nc;
+  CK(launch_wbc_scene(n, h->scene, d_scene, H, g, A, l, u, h->d_feet + lo * 24, st));
+  CK(cudaMemsetAsync(h->d_next + slot, 0, sizeof(int), st));
+  CK(launch_wbc_qp(h->P, n, H, g, A, l, u, d_x, d_info, h->d_next + slot, h->grid, st));
+  if (d_tau) CK(launch_wbc_torque(n, A, l, u, d_x, d_tau, st));
   return B200QP_OK;
 }
 
@@ -1493,29 +1498,54 @@ int32_t b200qp_wbc_scene_solve_batch(b200qp_wbc *h, int32_t n, const double *sce
   }
   if (n == 0) return B200QP_OK;
   CK(cudaSetDevice(h->cfg.device));
-  const size_t nn = n, sb = nn * B200QP_WBC_SCENE_IN_DOUBLES * sizeof(double);
-  double *st_in = h->h_stage, *st_x = h->h_stage + (size_t)h->cfg.max_batch * B200QP_WBC_SCENE_IN_DOUBLES;
-  double *st_tau = st_x + (size_t)h->cfg.max_batch * 30;
-  memcpy(st_in, scene_in, sb);
-  memcpy(st_x, x, nn * 30 * sizeof(double));  // a failed QP keeps the caller's row
-  if (tau) memcpy(st_tau, tau, nn * 12 * sizeof(double));
-  CK(cudaMemcpyAsync(h->d_scene, st_in, sb, cudaMemcpyHostToDevice, h->stream));
-  CK(cudaMemcpyAsync(h->d_x, st_x, nn * 30 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-  const int32_t rc = wbc_scene_queue(h, n, h->d_scene, h->d_x, tau ? h->d_tau : nullptr, h->d_info);
-  if (rc != B200QP_OK) return rc;
-  CK(cudaMemcpyAsync(st_x, h->d_x, nn * 30 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-  CK(cudaMemcpyAsync(h->h_info, h->d_info, nn * sizeof(b200qp_solver_info), cudaMemcpyDeviceToHost, h->stream));
-  double *st_tau_new = nullptr;
-  if (tau) {
-    st_tau_new = st_in;  // the input staging area is free again once the kernels are queued behind its copy
-    CK(cudaMemcpyAsync(st_tau_new, h->d_tau, nn * 12 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  const size_t nn = n, rin = B200QP_WBC_SCENE_IN_DOUBLES, nq = 30, nc = 46;
+  double *st_in = h->h_stage, *st_x = h->h_stage + (size_t)h->cfg.max_batch * rin;
+  // The robot states go up in two halves (staged into pinned memory; K6 assembles half 0 while the host stages half 1 - K6 is a
+  // thread-per-robot kernel whose duration barely depends on the rows it is given, so it is not cut finer). The QPs are then solved
+  // in 8 chunks that alternate between two streams: the blocks of chunk c+1 fill the SMs the tail of chunk c leaves idle, and the
+  // host copies the results of chunk c-1 out meanwhile. The torques of a chunk come back into its (by then consumed) staging rows.
+  const int in_chunks = (n >= 8192) ? 2 : 1, chunks = (n >= 8192) ? 8 : (n >= 2048 ? 2 : 1);
+  for (int c = 0; c < in_chunks; ++c) {
+    const size_t lo = nn * c / in_chunks, hi = nn * (c + 1) / in_chunks, m = hi - lo;
+    memcpy(st_in + lo * rin, scene_in + lo * rin, m * rin * sizeof(double));
+    CK(cudaMemcpyAsync(h->d_scene + lo * rin, st_in + lo * rin, m * rin * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CK(launch_wbc_scene((int)m, h->scene, h->d_scene + lo * rin, h->d_H + lo * nq * nq, h->d_g + lo * nq, h->d_A + lo * nc * nq,
+                        h->d_lo + lo * nc, h->d_hi + lo * nc, h->d_feet + lo * 24, h->stream));
   }
-  CK(cudaStreamSynchronize(h->stream));
-  memcpy(x, st_x, nn * 30 * sizeof(double));
-  memcpy(info, h->h_info, nn * sizeof(b200qp_solver_info));
-  if (tau)
-    for (size_t p = 0; p < nn; ++p)
-      if (h->h_info[p].status == B200QP_ACADOS_SUCCESS) memcpy(tau + 12 * p, st_tau_new + 12 * p, 12 * sizeof(double));
+  CK(cudaMemsetAsync(h->d_next, 0, 8 * sizeof(int), h->stream));
+  CK(cudaEventRecord(h->ev_fork, h->stream));
+  CK(cudaStreamWaitEvent(h->aux_stream, h->ev_fork, 0));
+  for (int c = 0; c < chunks; ++c) {
+    const size_t lo = nn * c / chunks, hi = nn * (c + 1) / chunks, m = hi - lo;
+    cudaStream_t ks = (c & 1) ? h->aux_stream : h->stream;
+    CK(launch_wbc_qp(h->P, (int)m, h->d_H + lo * nq * nq, h->d_g + lo * nq, h->d_A + lo * nc * nq, h->d_lo + lo * nc, h->d_hi + lo * nc,
+                     h->d_x + lo * nq, h->d_info + lo, h->d_next + c, h->grid, ks));
+    if (tau) CK(launch_wbc_torque((int)m, h->d_A + lo * nc * nq, h->d_lo + lo * nc, h->d_hi + lo * nc, h->d_x + lo * nq, h->d_tau + lo * 12, ks));
+    CK(cudaMemcpyAsync(st_x + lo * nq, h->d_x + lo * nq, m * nq * sizeof(double), cudaMemcpyDeviceToHost, ks));
+    CK(cudaMemcpyAsync(h->h_info + lo, h->d_info + lo, m * sizeof(b200qp_solver_info), cudaMemcpyDeviceToHost, ks));
+    if (tau) CK(cudaMemcpyAsync(st_in + lo * rin, h->d_tau + lo * 12, m * 12 * sizeof(double), cudaMemcpyDeviceToHost, ks));
+    CK(cudaEventRecord(h->ev[c], ks));
+  }
+  CK(cudaEventRecord(h->ev_join, h->aux_stream));  // later work on the handle's stream stays behind the odd chunks
+  CK(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
+  for (int c = 0; c < chunks; ++c) {
+    const size_t lo = nn * c / chunks, hi = nn * (c + 1) / chunks, m = hi - lo;
+    CK(cudaEventSynchronize(h->ev[c]));
+    memcpy(info + lo, h->h_info + lo, m * sizeof(b200qp_solver_info));
+    size_t solved = 0;
+    for (size_t p = 0; p < m; ++p) solved += h->h_info[lo + p].status == B200QP_ACADOS_SUCCESS;
+    const double *tn = st_in + lo * rin;
+    if (solved == m) {
+      memcpy(x + lo * nq, st_x + lo * nq, m * nq * sizeof(double));
+      if (tau) memcpy(tau + 12 * lo, tn, m * 12 * sizeof(double));
+    } else {  // a failed QP keeps the caller's rows (the kernel leaves its row of d_x as it was, which is not the caller's here)
+      for (size_t p = 0; p < m; ++p) {
+        if (h->h_info[lo + p].status != B200QP_ACADOS_SUCCESS) continue;
+        memcpy(x + nq * (lo + p), st_x + nq * (lo + p), nq * sizeof(double));
+        if (tau) memcpy(tau + 12 * (lo + p), tn + 12 * p, 12 * sizeof(double));
+      }
+    }
+  }
   return B200QP_OK;
 }
 
