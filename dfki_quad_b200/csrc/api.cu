@@ -48,7 +48,7 @@ struct WbcParams {
   int nq, neq, nin;
   double kkt_tol;
   int max_iter;
-  double tau;  // fraction of the step to the boundary that is taken
+  double tau, sig0;  // first attempt: fraction of the step to the boundary that is taken, end-game centring floor
 };
 struct WbcSceneConfig {
   double mu, com_pose_weight[6], foot_force_weight[3], foot_pose_weight[3], hessian_regularizer, tau_max[12];
@@ -1314,6 +1314,7 @@ int32_t b200qp_wbc_create(const b200qp_wbc_config *cfg, b200qp_wbc **out) {
   h->P.kkt_tol = cfg->kkt_tol > 0 ? cfg->kkt_tol : 1e-6;
   h->P.max_iter = cfg->max_iter > 0 ? cfg->max_iter : 40;
   h->P.tau = (getenv("B200QP_WBC_TAU") && atof(getenv("B200QP_WBC_TAU")) > 0) ? atof(getenv("B200QP_WBC_TAU")) : 0.9999;
+  h->P.sig0 = getenv("B200QP_WBC_SIG0") ? atof(getenv("B200QP_WBC_SIG0")) : 0.01;
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, cfg->device));
   h->grid = wbc_grid(h->P, prop.multiProcessorCount);

@@ -21,7 +21,7 @@ for s in range(nb):
     st = np.asarray(info["status"])
     bad = np.nonzero(st != 0)[0]
     tot += bad.size
-    print(f"seed {seed}: {bad.size} of {B} not converged; status {np.bincount(st)}; iterations mean {np.mean(info["iterations"]):.2f} max {np.max(info["iterations"])}",
+    print(f"seed {seed}: {bad.size} of {B} not converged; status {np.bincount(st)}; iterations mean {np.mean(info["iterations"]):.2f} max {np.max(info["iterations"])}, {int((np.asarray(info["iterations"]) > 20).sum())} second attempts; kkt max {np.max(np.asarray(info["kkt"])[st == 0]):.2e}",
           flush=True)
     good = np.nonzero(st == 0)[0][:8]
     for i in list(bad) + list(good):

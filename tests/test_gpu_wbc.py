@@ -128,7 +128,10 @@ def test_every_config4_qp_converges():
     x, info = s.solve(b["qp"])
     assert (info["status"] == 0).all(), np.bincount(info["status"])
     assert info["kkt"].max() <= 1e-6
-    assert info["iterations"].max() <= 30
+    # a QP whose first attempt (step fraction 0.9999, light end-game centring, given up after 20 iterations) stalls is solved again
+    # conservatively inside the kernel; its count is the sum of both attempts
+    assert info["iterations"].max() <= 45
+    assert (info["iterations"] > 21).mean() < 1e-3
     s.close()
 
 
@@ -144,7 +147,7 @@ def test_hard_wbc_qps_regression():
     s = wbc.BatchedWBCSolver(max_batch=n)
     x, info = s.solve_abi(d["H"], d["g"], d["A"], d["lo"], d["hi"])
     assert (info["status"] == 0).all(), info["status"]
-    assert info["iterations"].max() <= 30
+    assert info["iterations"].max() <= 45  # the sum of both attempts where the aggressive first one is given up (wbc_qp.cu)
     scale = np.abs(d["x"]).max(axis=1, keepdims=True)
     assert (np.abs(x - d["x"]) / scale).max() <= 1e-7
     s.close()
