@@ -558,7 +558,7 @@ __global__ void __launch_bounds__(64, 5) wbc_qp_kernel(const WbcParams P, int np
           sigma_mu = ratio * ratio * ratio * mu_c;
           // end game: keep some centring once the gap is small - with sigma -> 0 single pairs run ahead of the path (s z << mu), W
           // reaches 1e16 and the factorisation of Phi loses the stationarity residual at the 1e-6 level
-          if (mu_c < 1e-4) sigma_mu = fmax(sigma_mu, (attempt == 0 ? P.sig0 : 0.05) * mu_c);
+          if (mu_c < 1e-4) sigma_mu = fmax(sigma_mu, (tau > 0.995 ? P.sig0 : 0.05) * mu_c);
           if (damp > 0) sigma_mu = fmax(sigma_mu, 0.2 * mu_c);
           dsl = nsl; dsu = nsu; dzl = nzl; dzu = nzu;
         } else {
