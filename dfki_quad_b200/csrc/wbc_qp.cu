@@ -57,6 +57,26 @@ __device__ __forceinline__ void wblock_min2(double &a, double &b, double *red) {
   a = ma;
   b = mb;
 }
+// five maxima (m[0..4]) and one sum (m[5]) over the block with one pair of barriers; the kernel runs 64 threads, so red's 16 doubles
+// hold the 6 partial results of both warps
+__device__ __forceinline__ void wblock_max5_sum1(double (&m)[6], double *red) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+    for (int k = 0; k < 5; ++k) m[k] = fmax(m[k], __shfl_xor_sync(0xffffffffu, m[k], o));
+    m[5] += __shfl_xor_sync(0xffffffffu, m[5], o);
+  }
+  __syncthreads();
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < 6; ++k) red[warp * 6 + k] = m[k];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 5; ++k) m[k] = fmax(red[k], red[6 + k]);
+  m[5] = red[5] + red[11];
+}
 struct WMax { __device__ double operator()(double a, double b) const { return fmax(a, b); } };
 struct WMin { __device__ double operator()(double a, double b) const { return fmin(a, b); } };
 struct WSum { __device__ double operator()(double a, double b) const { return a + b; } };
@@ -395,13 +415,15 @@ __global__ void __launch_bounds__(64, 5) wbc_qp_kernel(const WbcParams P, int np
       for (int e = tid; e < me; e += BS) le = fmax(le, fabs(sre[e]));
       const bool bad = !(lm < WBIG) || !(fabs(y) < WBIG);
       const int anybad = __syncthreads_or(bad ? 1 : 0);
-      k_stat = wblock_reduce(lm, red, WMax());
-      k_eq = wblock_reduce(le, red, WMax());
-      const double rpm = wblock_reduce(fmax(fabs(rpl), fabs(rpu)), red, WMax());
-      k_comp = wblock_reduce(fmax(hasl ? sl * zl : 0.0, hasu ? su * zu : 0.0), red, WMax());
-      k_ineq = wblock_reduce(fmax(hasl ? lo - y : 0.0, hasu ? y - hi : 0.0), red, WMax());
-      k_ineq = fmax(k_ineq, 0.0);
-      const double gap = wblock_reduce((hasl ? sl * zl : 0.0) + (hasu ? su * zu : 0.0), red, WSum());
+      double m6[6] = {lm, le, fmax(fabs(rpl), fabs(rpu)), fmax(hasl ? sl * zl : 0.0, hasu ? su * zu : 0.0),
+                      fmax(fmax(hasl ? lo - y : 0.0, hasu ? y - hi : 0.0), 0.0), (hasl ? sl * zl : 0.0) + (hasu ? su * zu : 0.0)};
+      wblock_max5_sum1(m6, red);
+      k_stat = m6[0];
+      k_eq = m6[1];
+      const double rpm = m6[2];
+      k_comp = m6[3];
+      k_ineq = m6[4];
+      const double gap = m6[5];
       const double rmax = anybad ? WBIG : fmax(fmax(k_stat, k_eq), fmax(rpm, k_comp));
       if (rmax <= target) {
         status = B200QP_ACADOS_SUCCESS;
@@ -483,8 +505,8 @@ __global__ void __launch_bounds__(64, 5) wbc_qp_kernel(const WbcParams P, int np
         if (row)
           for (int j = 0; j < nq; ++j) y0 = fma(sAi[tid * nq + j], sx[j], y0);
         const double zu0 = y0 - hi, zl0 = -y0 + lo;  // z = G x - h, s = -z
-        const double smin = wblock_reduce(fmin(hasu ? -zu0 : WBIG, hasl ? -zl0 : WBIG), red, WMin());
-        const double zmin = wblock_reduce(fmin(hasu ? zu0 : WBIG, hasl ? zl0 : WBIG), red, WMin());
+        double smin = fmin(hasu ? -zu0 : WBIG, hasl ? -zl0 : WBIG), zmin = fmin(hasu ? zu0 : WBIG, hasl ? zl0 : WBIG);
+        wblock_min2(smin, zmin, red);
         const double sh = smin > 0.0 ? 0.0 : 1.0 - smin, zh = zmin > 0.0 ? 0.0 : 1.0 - zmin;
         su = hasu ? -zu0 + sh : 1.0;
         sl = hasl ? -zl0 + sh : 1.0;
