@@ -77,6 +77,18 @@ __device__ __forceinline__ void wblock_max5_sum1(double (&m)[6], double *red) {
   for (int k = 0; k < 5; ++k) m[k] = fmax(red[k], red[6 + k]);
   m[5] = red[5] + red[11];
 }
+__device__ __forceinline__ void wwarp_min2(double &a, double &b) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a = fmin(a, __shfl_xor_sync(0xffffffffu, a, o));
+    b = fmin(b, __shfl_xor_sync(0xffffffffu, b, o));
+  }
+}
+__device__ __forceinline__ double wwarp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
 struct WMax { __device__ double operator()(double a, double b) const { return fmax(a, b); } };
 struct WMin { __device__ double operator()(double a, double b) const { return fmin(a, b); } };
 struct WSum { __device__ double operator()(double a, double b) const { return a + b; } };
@@ -228,45 +240,52 @@ __device__ __noinline__ void chol_and_inverse_warp(double *A, double *dinv) {
 }
 
 // dx, dnu from r~ (srt) and re (sre):  u1 = -L^-1 r~,  dnu = S^-1 (re + Y'u1),  dx = L^-T (u1 - Y dnu)
+// W1: called by warp 0 alone (every vector fits its 32 lanes' strides), __syncwarp instead of block barriers
+template <bool W1>
+__device__ __forceinline__ void wsync() {
+  if constexpr (W1) __syncwarp();
+  else __syncthreads();
+}
+template <bool W1>
 __device__ void kkt_solve(int nq, int me, const double *sLi, const double *sY, const double *sSi, const double *srt,
                           const double *sre, double *su1, double *sv, double *sdx, double *sdnu) {
-  const int tid = threadIdx.x, BS = blockDim.x;
+  const int tid = threadIdx.x, BS = W1 ? 32 : blockDim.x;
   for (int i = tid; i < nq; i += BS) {
     double a = 0.0;
     for (int k = 0; k <= i; ++k) a = fma(sLi[i * nq + k], srt[k], a);
     su1[i] = -a;
   }
-  __syncthreads();
+  wsync<W1>();
   for (int r = tid; r < me; r += BS) {
     double a = sre[r];
     for (int i = 0; i < nq; ++i) a = fma(sY[i * me + r], su1[i], a);
     sv[r] = a;
   }
-  __syncthreads();
+  wsync<W1>();
   for (int r = tid; r < me; r += BS) {
     double a = 0.0;
     for (int k = 0; k <= r; ++k) a = fma(sSi[r * me + k], sv[k], a);
     sdnu[r] = a;
   }
-  __syncthreads();
+  wsync<W1>();
   double dn = 0.0;
   if (tid < me)
     for (int k = tid; k < me; ++k) dn = fma(sSi[k * me + tid], sdnu[k], dn);
-  __syncthreads();
+  wsync<W1>();
   if (tid < me) sdnu[tid] = dn;
-  __syncthreads();
+  wsync<W1>();
   for (int i = tid; i < nq; i += BS) {
     double a = su1[i];
     for (int r = 0; r < me; ++r) a = fma(-sY[i * me + r], sdnu[r], a);
     sv[i] = a;
   }
-  __syncthreads();
+  wsync<W1>();
   for (int i = tid; i < nq; i += BS) {
     double a = 0.0;
     for (int k = i; k < nq; ++k) a = fma(sLi[k * nq + i], sv[k], a);
     sdx[i] = a;
   }
-  __syncthreads();
+  wsync<W1>();
 }
 }  // namespace
 
@@ -308,6 +327,8 @@ __global__ void __launch_bounds__(64, 5) wbc_qp_kernel(const WbcParams P, int np
   double *red = sre2 + me;          // [16]
   __shared__ int sSlot;
   const int tid = threadIdx.x, BS = blockDim.x;
+  constexpr bool ONEW = (NQ_ > 0 && NQ_ <= 32 && ME_ <= 32 && MI_ <= 32);
+  const int BSW = ONEW ? 32 : BS;
 
   for (;;) {
     __syncthreads();
@@ -497,7 +518,7 @@ __global__ void __launch_bounds__(64, 5) wbc_qp_kernel(const WbcParams P, int np
           srt[i] = a;
         }
         __syncthreads();
-        kkt_solve(nq, me, sLi, sY, sSi, srt, sre, su1, sv, sdx, sdnu);
+        kkt_solve<false>(nq, me, sLi, sY, sSi, srt, sre, su1, sv, sdx, sdnu);
         for (int i = tid; i < nq; i += BS) sx[i] = sdx[i];
         for (int r = tid; r < me; r += BS) snu[r] = sdnu[r];
         __syncthreads();
@@ -517,19 +538,22 @@ __global__ void __launch_bounds__(64, 5) wbc_qp_kernel(const WbcParams P, int np
       }
       WPHW(6);
       // predictor / corrector ---------------------------------------------------------------------------------------------
+      // With every row and vector inside one warp's reach (Go2: 28 rows, 30 + 18 unknowns) the whole section runs on warp 0 with warp
+      // barriers and shuffle reductions; warp 1, which would only wait at ~30 block barriers, waits once at the end.
       double dsl = 0.0, dsu = 0.0, dzl = 0.0, dzu = 0.0, sigma_mu = 0.0;
+      if (!ONEW || tid < 32)
       for (int pass = 0; pass < 2; ++pass) {
         const double rcl = (pass == 0) ? sl * zl : (sl * zl + dsl * dzl - sigma_mu);
         const double rcu = (pass == 0) ? su * zu : (su * zu + dsu * dzu - sigma_mu);
         if (row) sw[tid] = (hasu ? (zu * rpu - rcu) / su : 0.0) - (hasl ? (zl * rpl - rcl) / sl : 0.0);
-        __syncthreads();
-        for (int i = tid; i < nq; i += BS) {  // r~ = rd + Ain' t
+        wsync<ONEW>();
+        for (int i = tid; i < nq; i += BSW) {  // r~ = rd + Ain' t
           double a = srd[i];
           for (int r = 0; r < mi; ++r) a = fma(sAi[r * nq + i], sw[r], a);
           srt[i] = a;
         }
-        __syncthreads();
-        kkt_solve(nq, me, sLi, sY, sSi, srt, sre, su1, sv, sdx, sdnu);
+        wsync<ONEW>();
+        kkt_solve<ONEW>(nq, me, sLi, sY, sSi, srt, sre, su1, sv, sdx, sdnu);
         if (pass == 1 && mu_c < 1e-3) {
           // one step of iterative refinement on the Newton system (Phi dx + Aeq'dnu = -r~, Aeq dx = -re): with W up to
           // 1e12 the factored solve alone stalls the stationarity residual at the 1e-6 level on large-scale data
@@ -538,24 +562,24 @@ __global__ void __launch_bounds__(64, 5) wbc_qp_kernel(const WbcParams P, int np
             for (int j = 0; j < nq; ++j) q = fma(sAi[tid * nq + j], sdx[j], q);
             sw[tid] = q * ((hasl ? zl / sl : 0.0) + (hasu ? zu / su : 0.0));
           }
-          __syncthreads();
-          for (int i = tid; i < nq; i += BS) {
+          wsync<ONEW>();
+          for (int i = tid; i < nq; i += BSW) {
             double a = srt[i];
             for (int j = 0; j < nq; ++j) a = fma(sH[i * nq + j], sdx[j], a);
             for (int r = 0; r < mi; ++r) a = fma(sAi[r * nq + i], sw[r], a);
             for (int r = 0; r < me; ++r) a = fma(sAe[r * nq + i], sdnu[r], a);
             sd0[i] = a;  // = -(residual of the first block row)
           }
-          for (int e = tid; e < me; e += BS) {
+          for (int e = tid; e < me; e += BSW) {
             double a = sre[e];
             for (int j = 0; j < nq; ++j) a = fma(sAe[e * nq + j], sdx[j], a);
             sre2[e] = a;
           }
-          __syncthreads();
-          kkt_solve(nq, me, sLi, sY, sSi, sd0, sre2, su1, sv, sdx2, sdnu2);
-          for (int i = tid; i < nq; i += BS) sdx[i] += sdx2[i];
-          for (int e = tid; e < me; e += BS) sdnu[e] += sdnu2[e];
-          __syncthreads();
+          wsync<ONEW>();
+          kkt_solve<ONEW>(nq, me, sLi, sY, sSi, sd0, sre2, su1, sv, sdx2, sdnu2);
+          for (int i = tid; i < nq; i += BSW) sdx[i] += sdx2[i];
+          for (int e = tid; e < me; e += BSW) sdnu[e] += sdnu2[e];
+          wsync<ONEW>();
         }
         double dy = 0.0;
         if (row)
@@ -573,9 +597,13 @@ __global__ void __launch_bounds__(64, 5) wbc_qp_kernel(const WbcParams P, int np
           if (nsu < 0.0) stp = fmin(stp, -su / nsu);
           if (nzu < 0.0) stq = fmin(stq, -zu / nzu);
         }
-        wblock_min2(stp, stq, red);
+        if constexpr (ONEW) wwarp_min2(stp, stq);
+        else wblock_min2(stp, stq, red);
         if (pass == 0) {
-          const double g2 = wblock_reduce((hasl ? (sl + stp * nsl) * (zl + stq * nzl) : 0.0) + (hasu ? (su + stp * nsu) * (zu + stq * nzu) : 0.0), red, WSum());
+          const double g2l = (hasl ? (sl + stp * nsl) * (zl + stq * nzl) : 0.0) + (hasu ? (su + stp * nsu) * (zu + stq * nzu) : 0.0);
+          double g2;
+          if constexpr (ONEW) g2 = wwarp_sum(g2l);
+          else g2 = wblock_reduce(g2l, red, WSum());
           const double ratio = (g2 / mtot) / fmax(mu_c, 1e-300);
           sigma_mu = ratio * ratio * ratio * mu_c;
           // end game: keep some centring once the gap is small - with sigma -> 0 single pairs run ahead of the path (s z << mu), W
@@ -586,12 +614,13 @@ __global__ void __launch_bounds__(64, 5) wbc_qp_kernel(const WbcParams P, int np
         } else {
           const double a = fmin(1.0, tau * stp), ad = fmin(1.0, tau * stq);
           sl += a * nsl; su += a * nsu; zl += ad * nzl; zu += ad * nzu;
-          for (int i = tid; i < nq; i += BS) sx[i] += a * sdx[i];
-          for (int r = tid; r < me; r += BS) snu[r] += ad * sdnu[r];
+          for (int i = tid; i < nq; i += BSW) sx[i] += a * sdx[i];
+          for (int r = tid; r < me; r += BSW) snu[r] += ad * sdnu[r];
           if (damp > 0) --damp;
         }
-        __syncthreads();
+        wsync<ONEW>();
       }
+      if constexpr (ONEW) __syncthreads();
       WPHW(7);
     }
     __syncthreads();
