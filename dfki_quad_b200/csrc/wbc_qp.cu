@@ -142,13 +142,16 @@ __device__ void chol_and_inverse(double *A, int n, double *diag0) {
 //   of three per column - is exactly as fast as the column version, 1005 vs 1014 k/s: the barriers are not what the step waits for.)
 // Called by every thread of the block.
 #ifndef B200QP_WBC_VARIANT
-#define B200QP_WBC_VARIANT 2  // bit 0: warp Cholesky (slower: 884 k vs 975 k/s), bit 1: column-parallel inverse (faster: 1010 k/s); A/B builds
+#define B200QP_WBC_VARIANT 2  // Phi (30 x 30). bit 0: warp Cholesky, bit 1: column-parallel inverse; A/B builds
 #endif
-template <int N>
+#ifndef B200QP_WBC_VARIANT_S
+#define B200QP_WBC_VARIANT_S 2  // S (18 x 18)
+#endif
+template <int N, int V>
 __device__ __noinline__ void chol_and_inverse_warp(double *A, double *dinv) {
   static_assert(N <= 32, "one lane per row / column");
   const int tid = threadIdx.x, BS = blockDim.x;
-  if (B200QP_WBC_VARIANT & 1) {
+  if (V & 1) {
     if (threadIdx.x < 32) {
       const int i = threadIdx.x;
       const double d0 = (i < N) ? A[i * N + i] : 1.0;
@@ -200,7 +203,7 @@ __device__ __noinline__ void chol_and_inverse_warp(double *A, double *dinv) {
       __syncthreads();
     }
   }
-  if (B200QP_WBC_VARIANT & 2) {
+  if (V & 2) {
     if (threadIdx.x < 32) {
       const int j = threadIdx.x;
       double x[N];
@@ -247,7 +250,7 @@ __device__ __forceinline__ void wsync() {
   else __syncthreads();
 }
 template <bool W1>
-__device__ void kkt_solve(int nq, int me, const double *sLi, const double *sY, const double *sSi, const double *srt,
+__device__ __noinline__ void kkt_solve(int nq, int me, const double *sLi, const double *sY, const double *sSi, const double *srt,
                           const double *sre, double *su1, double *sv, double *sdx, double *sdnu) {
   const int tid = threadIdx.x, BS = W1 ? 32 : blockDim.x;
   for (int i = tid; i < nq; i += BS) {
@@ -410,35 +413,58 @@ __global__ void __launch_bounds__(64, 5) wbc_qp_kernel(const WbcParams P, int np
     for (iter = 0; iter <= cap + 1; ++iter) {
       const bool init = (iter == 0);  // iteration 0 computes the starting point (least-squares point + shifts)
       if (!init) {
-      // residuals ---------------------------------------------------------------------------------------------------
-      double y = 0.0;
-      if (row)
-        for (int j = 0; j < nq; ++j) y = fma(sAi[tid * nq + j], sx[j], y);
-      rpl = hasl ? (-y + sl + lo) : 0.0;
-      rpu = hasu ? (y + su - hi) : 0.0;
-      if (row) sw[tid] = zu - zl;
-      for (int e = tid; e < me; e += BS) {
-        double a = -sbe[e];
-        for (int j = 0; j < nq; ++j) a = fma(sAe[e * nq + j], sx[j], a);
-        sre[e] = a;
+      // residuals (warp 0 alone where everything fits its lanes, then one block barrier hands the six norms to both warps) --------
+      double y = 0.0, lm = 0.0, le = 0.0;
+      bool bad = false;
+      if (!ONEW || tid < 32) {
+        if (row)
+          for (int j = 0; j < nq; ++j) y = fma(sAi[tid * nq + j], sx[j], y);
+        rpl = hasl ? (-y + sl + lo) : 0.0;
+        rpu = hasu ? (y + su - hi) : 0.0;
+        if (row) sw[tid] = zu - zl;
+        for (int e = tid; e < me; e += BSW) {
+          double a = -sbe[e];
+          for (int j = 0; j < nq; ++j) a = fma(sAe[e * nq + j], sx[j], a);
+          sre[e] = a;
+        }
+        wsync<ONEW>();
+        for (int i = tid; i < nq; i += BSW) {
+          double a = sg[i];
+          for (int j = 0; j < nq; ++j) a = fma(sH[i * nq + j], sx[j], a);
+          for (int r = 0; r < me; ++r) a = fma(sAe[r * nq + i], snu[r], a);
+          for (int r = 0; r < mi; ++r) a = fma(sAi[r * nq + i], sw[r], a);
+          srd[i] = a;
+          lm = fmax(lm, fabs(a));
+        }
+        for (int e = tid; e < me; e += BSW) le = fmax(le, fabs(sre[e]));
+        bad = !(lm < WBIG) || !(fabs(y) < WBIG);
       }
-      __syncthreads();
-      double lm = 0.0;
-      for (int i = tid; i < nq; i += BS) {
-        double a = sg[i];
-        for (int j = 0; j < nq; ++j) a = fma(sH[i * nq + j], sx[j], a);
-        for (int r = 0; r < me; ++r) a = fma(sAe[r * nq + i], snu[r], a);
-        for (int r = 0; r < mi; ++r) a = fma(sAi[r * nq + i], sw[r], a);
-        srd[i] = a;
-        lm = fmax(lm, fabs(a));
-      }
-      double le = 0.0;
-      for (int e = tid; e < me; e += BS) le = fmax(le, fabs(sre[e]));
-      const bool bad = !(lm < WBIG) || !(fabs(y) < WBIG);
-      const int anybad = __syncthreads_or(bad ? 1 : 0);
       double m6[6] = {lm, le, fmax(fabs(rpl), fabs(rpu)), fmax(hasl ? sl * zl : 0.0, hasu ? su * zu : 0.0),
                       fmax(fmax(hasl ? lo - y : 0.0, hasu ? y - hi : 0.0), 0.0), (hasl ? sl * zl : 0.0) + (hasu ? su * zu : 0.0)};
-      wblock_max5_sum1(m6, red);
+      int anybad;
+      if constexpr (ONEW) {
+        if (tid < 32) {
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+            for (int k = 0; k < 5; ++k) m6[k] = fmax(m6[k], __shfl_xor_sync(0xffffffffu, m6[k], o));
+            m6[5] += __shfl_xor_sync(0xffffffffu, m6[5], o);
+          }
+          const int ab = __any_sync(0xffffffffu, bad);
+          if (tid == 0) {
+#pragma unroll
+            for (int k = 0; k < 6; ++k) red[k] = m6[k];
+            red[6] = ab ? 1.0 : 0.0;
+          }
+        }
+        __syncthreads();  // also publishes srd / sre; red is not written again before the barriers of the factorisation
+#pragma unroll
+        for (int k = 0; k < 6; ++k) m6[k] = red[k];
+        anybad = red[6] != 0.0;
+      } else {
+        anybad = __syncthreads_or(bad ? 1 : 0);
+        wblock_max5_sum1(m6, red);
+      }
       k_stat = m6[0];
       k_eq = m6[1];
       const double rpm = m6[2];
@@ -485,7 +511,7 @@ __global__ void __launch_bounds__(64, 5) wbc_qp_kernel(const WbcParams P, int np
       }
       __syncthreads();
       WPHW(2);
-      if constexpr (NQ_ > 0 && NQ_ <= 32) chol_and_inverse_warp<(NQ_ > 0 ? NQ_ : 1)>(sPhi, sd0);
+      if constexpr (NQ_ > 0 && NQ_ <= 32) chol_and_inverse_warp<(NQ_ > 0 ? NQ_ : 1), B200QP_WBC_VARIANT>(sPhi, sd0);
       else chol_and_inverse(sPhi, nq, sd0);
       WPHW(3);
       for (int e = tid; e < nq * me; e += BS) {  // Y[i][r] = sum_{k<=i} Li[i][k] Aeq[r][k]
@@ -504,7 +530,7 @@ __global__ void __launch_bounds__(64, 5) wbc_qp_kernel(const WbcParams P, int np
       }
       __syncthreads();
       WPHW(4);
-      if constexpr (NQ_ > 0 && ME_ <= 32) chol_and_inverse_warp<(ME_ > 0 ? ME_ : 1)>(sS, sd0);
+      if constexpr (NQ_ > 0 && ME_ <= 32) chol_and_inverse_warp<(ME_ > 0 ? ME_ : 1), B200QP_WBC_VARIANT_S>(sS, sd0);
       else chol_and_inverse(sS, me, sd0);
       WPHW(5);
 
@@ -542,6 +568,7 @@ __global__ void __launch_bounds__(64, 5) wbc_qp_kernel(const WbcParams P, int np
       // barriers and shuffle reductions; warp 1, which would only wait at ~30 block barriers, waits once at the end.
       double dsl = 0.0, dsu = 0.0, dzl = 0.0, dzu = 0.0, sigma_mu = 0.0;
       if (!ONEW || tid < 32)
+#pragma unroll 1
       for (int pass = 0; pass < 2; ++pass) {
         const double rcl = (pass == 0) ? sl * zl : (sl * zl + dsl * dzl - sigma_mu);
         const double rcu = (pass == 0) ? su * zu : (su * zu + dsu * dzu - sigma_mu);
