@@ -192,10 +192,12 @@ __device__ __noinline__ void chol_and_inverse_warp(double *A, double *dinv) {
       const double piv0 = A[p * N + p];
       const double piv = piv0 > flo ? piv0 : flo;
       const double rd = fast_rsqrt(piv);
+      // two barriers per column: the diagonal of L is never read again (the inverse takes 1 / L_pp from dinv), so it is not written
+      // and the pivot can be read without a barrier of its own; dinv[p] changes from "original diagonal" to 1 / L_pp only after
+      // every thread has passed the barrier behind its read
+      for (int i = p + 1 + tid; i < N; i += BS) A[i * N + p] *= rd;
       __syncthreads();
-      for (int i = p + tid; i < N; i += BS) A[i * N + p] = (i == p) ? piv * rd : A[i * N + p] * rd;
       if (tid == 0) dinv[p] = rd;
-      __syncthreads();
       for (int i = p + 1 + (tid >> 3); i < N; i += 8) {
         const double lip = A[i * N + p];
         for (int j = p + 1 + (tid & 7); j <= i; j += 8) A[i * N + j] -= lip * A[j * N + p];
