@@ -5,8 +5,9 @@
  * The reference hands the TSID QP to a `wbc::QPSolver` plugin of ARC-OPT (wbc_arc_opt.cpp:51-74,297; default
  * EiquadprogSolver, alternatives ProxQP / qpOASES / OSQP / qpSWIFT / HPIPM).  Those are third-party libraries that are not
  * in /root/reference and cannot be built here; this file restates a textbook dense primal-dual interior-point method
- * (Mehrotra predictor-corrector, Nocedal & Wright ch. 16.6; the same method, safeguards and stopping rule as the device
- * kernel wbc_qp.cu, in scalar C) for
+ * (Mehrotra predictor-corrector, Nocedal & Wright ch. 16.6; the same method, safeguards and stopping rule as the
+ * conservative attempt of the device kernel wbc_qp.cu - step fraction 0.995, end-game centring floor 0.05 - in scalar C;
+ * the device kernel's aggressive first attempt is a speed measure that this file does not need) for
  *     min 1/2 x'Hx + g'x   s.t.  A[0:neq] x = b,   lo <= A[neq:] x <= hi        (|bound| >= 1e19: absent)
  * with the layouts of ARC-OPT's wbc::QuadraticProgram as they cross include/b200qp.h (column-major H and A).
  * One problem per thread, OpenMP over the batch.  Never linked into the product.
