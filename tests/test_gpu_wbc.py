@@ -151,3 +151,44 @@ def test_hard_wbc_qps_regression():
     scale = np.abs(d["x"]).max(axis=1, keepdims=True)
     assert (np.abs(x - d["x"]) / scale).max() <= 1e-7
     s.close()
+
+
+def test_chunked_host_calls_equal_the_single_launch():
+    """Batches >= 8192 go through the host-buffer calls in 8 chunks on two streams (scene states in two halves): same bits as one launch
+    over device buffers, and a failed QP in the middle of a chunk keeps the caller's rows."""
+    import torch
+
+    from dfki_quad_b200 import wbc
+
+    n = 9000
+    b = wbc.random_wbc_batch(n, seed=4242)
+    mb = b["mpc_batch"]
+    scene = wbc.pack_scene(mb["pos"], mb["quat"], mb["vel"], mb["omega"], b["q"], b["qd"], b["contacts"], b["a_body"], b["a_foot"], b["f_ref"])
+    s = wbc.BatchedWBCSolver(max_batch=n)
+    s.scene_configure()
+    H, g, A, lo, hi = s.abi_arrays(b["qp"])
+    ext = torch.cuda.ExternalStream(s.stream())
+    with torch.cuda.stream(ext):
+        d = [torch.from_numpy(np.ascontiguousarray(a)).cuda() for a in (H, g, A, lo, hi)]
+        dsc = torch.from_numpy(scene).cuda()
+        dx = torch.zeros((n, 30), dtype=torch.float64, device="cuda")
+        dt = torch.zeros((n, 12), dtype=torch.float64, device="cuda")
+        di = torch.zeros((n, 48), dtype=torch.uint8, device="cuda")
+    ext.synchronize()
+    s.solve_device(n, *[t.data_ptr() for t in d], dx.data_ptr(), di.data_ptr(), sync=True)
+    x_one = dx.cpu().numpy().copy()
+    x_chunked, info = s.solve_abi(H, g, A, lo, hi)
+    assert (info["status"] == 0).all()
+    assert np.array_equal(x_chunked, x_one)
+    s.scene_solve_device(n, dsc.data_ptr(), dx.data_ptr(), dt.data_ptr(), di.data_ptr(), sync=True)
+    xs_one, tau_one = dx.cpu().numpy().copy(), dt.cpu().numpy().copy()
+    bad = scene.copy()
+    bad[5000, 13] = np.nan
+    x0, t0 = np.full((n, 30), 7.0), np.full((n, 12), -3.0)
+    xs, tau, info_s = s.scene_solve(bad, x0, t0)
+    ok = np.ones(n, dtype=bool)
+    ok[5000] = False
+    assert info_s["status"][5000] != 0 and (info_s["status"][ok] == 0).all()
+    assert (xs[5000] == 7.0).all() and (tau[5000] == -3.0).all()
+    assert np.array_equal(xs[ok], xs_one[ok]) and np.array_equal(tau[ok], tau_one[ok])
+    s.close()
