@@ -89,6 +89,14 @@ __device__ __forceinline__ double wwarp_sum(double v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
+// e-th entry of a lower triangle stored by rows: e = i (i + 1) / 2 + j, 0 <= j <= i
+__device__ __forceinline__ void tri_index(int e, int &i, int &j) {
+  int r = (int)((sqrtf(8.0f * (float)e + 1.0f) - 1.0f) * 0.5f);
+  if (r * (r + 1) / 2 > e) --r;
+  else if ((r + 1) * (r + 2) / 2 <= e) ++r;
+  i = r;
+  j = e - r * (r + 1) / 2;
+}
 struct WMax { __device__ double operator()(double a, double b) const { return fmax(a, b); } };
 struct WMin { __device__ double operator()(double a, double b) const { return fmin(a, b); } };
 struct WSum { __device__ double operator()(double a, double b) const { return a + b; } };
@@ -504,12 +512,27 @@ __global__ void __launch_bounds__(64, 5) wbc_qp_kernel(const WbcParams P, int np
       // Phi = H + Ain' W Ain ------------------------------------------------------------------------------------------
       if (row) sw[tid] = init ? ((hasl ? 1.0 : 0.0) + (hasu ? 1.0 : 0.0)) : ((hasl ? zl / sl : 0.0) + (hasu ? zu / su : 0.0));
       __syncthreads();
-      for (int e = tid; e < nq * nq; e += BS) {
-        const int i = e / nq, j = e - i * nq;
-        if (j > i) continue;
-        double a = sH[e];
-        for (int r = 0; r < mi; ++r) a = fma(sAi[r * nq + i] * sw[r], sAi[r * nq + j], a);
-        sPhi[e] = a;
+      if constexpr (NQ_ > 0 && MI_ * NQ_ <= NQ_ * ME_ + ME_ * ME_) {
+        // the rows scaled once (W Ain, into the not yet needed Y / S area), then only the 465 lower-triangle entries are walked
+        // (the square walk skipped every second slot and left half the lanes idle); same roundings as the generic loop below
+        double *sT = sY;
+        for (int e = tid; e < mi * nq; e += BS) sT[e] = sAi[e] * sw[e / nq];
+        __syncthreads();
+        for (int e = tid; e < nq * (nq + 1) / 2; e += BS) {
+          int i, j;
+          tri_index(e, i, j);
+          double a = sH[i * nq + j];
+          for (int r = 0; r < mi; ++r) a = fma(sT[r * nq + i], sAi[r * nq + j], a);
+          sPhi[i * nq + j] = a;
+        }
+      } else {
+        for (int e = tid; e < nq * nq; e += BS) {
+          const int i = e / nq, j = e - i * nq;
+          if (j > i) continue;
+          double a = sH[e];
+          for (int r = 0; r < mi; ++r) a = fma(sAi[r * nq + i] * sw[r], sAi[r * nq + j], a);
+          sPhi[e] = a;
+        }
       }
       __syncthreads();
       WPHW(2);
@@ -523,12 +546,12 @@ __global__ void __launch_bounds__(64, 5) wbc_qp_kernel(const WbcParams P, int np
         sY[e] = a;
       }
       __syncthreads();
-      for (int e = tid; e < me * me; e += BS) {  // S = Y'Y
-        const int r = e / me, c = e - r * me;
-        if (c > r) continue;
+      for (int e = tid; e < me * (me + 1) / 2; e += BS) {  // S = Y'Y, lower triangle
+        int r, c;
+        tri_index(e, r, c);
         double a = 0.0;
         for (int i = 0; i < nq; ++i) a = fma(sY[i * me + r], sY[i * me + c], a);
-        sS[e] = a;
+        sS[r * me + c] = a;
       }
       __syncthreads();
       WPHW(4);
