@@ -300,7 +300,10 @@ int32_t b200qp_wbc_create(const b200qp_wbc_config *cfg, b200qp_wbc **out);
 void b200qp_wbc_destroy(b200qp_wbc *h);
 /* HOST buffers; x [n][nq] is written only for problems with info.status == 0 (on a solver failure the reference
  * falls back to zero torque, wbc_arc_opt.cpp:298-309 - the caller's job).  info.kkt = stationarity, equality,
- * inequality, complementarity inf-norms. */
+ * inequality, complementarity inf-norms.  info.iterations counts both attempts where the kernel's aggressive first
+ * attempt was given up and the QP solved again conservatively (a few QPs per 10 000).  Batches >= 8192 are cut into
+ * chunks that alternate between two internal streams; the call returns after everything has landed, and work queued on
+ * b200qp_wbc_stream() before / after the call stays ordered before / after it. */
 int32_t b200qp_wbc_solve_batch(b200qp_wbc *h, int32_t n, const double *H, const double *g, const double *A,
                                const double *lower_y, const double *upper_y, double *x, b200qp_solver_info *info);
 /* DEVICE pointers, asynchronous on the handle's stream unless sync != 0 */
