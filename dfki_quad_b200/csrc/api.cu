@@ -578,7 +578,7 @@ static int32_t solve_device_impl(b200qp_mpc *h, int32_t n, const double *d_in, c
     // warp-per-problem kernel: <= 32 stance foot-stages first, what does not fit is handed on to the two-per-lane instantiation and
     // from there to the block kernel (d_bin_count[12], [13] = lengths of the hand-over lists, [14], [15], [9] = work counters)
     double *lb = h->want_duals ? h->d_lam_box : nullptr, *lg = h->want_duals ? h->d_lam_g : nullptr;
-    int *rej0 = h->d_pcw_rej, *rej1 = h->d_pcw_rej + n;
+    int *rej0 = h->d_pcw_rej;
     if (h->poison_smem) CK(launch_smem_polluter(148, h->stream));
     MpcParams Pw = h->P;
     if (h->cfg.warm_start > 0 && h->d_warm_x != nullptr && dbg_index < 0) {  // IPM warm start: previous forces of the slot
@@ -619,7 +619,6 @@ static int32_t solve_device_impl(b200qp_mpc *h, int32_t n, const double *d_in, c
       av.accessPolicyWindow.num_bytes = 0;
       cudaStreamSetAttribute(h->stream, cudaStreamAttributeAccessPolicyWindow, &av);
     }
-    (void)rej1;
     CK(launch_mpc_riccati(Pw, n, d_in, d_contact, d_forces, d_xpred, d_info, lb, lg, h->d_ric_scratch, h->d_bin_count + 9, h->ric_grid,
                           h->stream, nullptr, rej0, h->d_bin_count + 12));
     launches += 2;

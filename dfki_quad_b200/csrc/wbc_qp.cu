@@ -97,8 +97,6 @@ __device__ __forceinline__ void tri_index(int e, int &i, int &j) {
   i = r;
   j = e - r * (r + 1) / 2;
 }
-struct WMax { __device__ double operator()(double a, double b) const { return fmax(a, b); } };
-struct WMin { __device__ double operator()(double a, double b) const { return fmin(a, b); } };
 struct WSum { __device__ double operator()(double a, double b) const { return a + b; } };
 
 // In-place lower Cholesky of the n x n row-major matrix A (ld = n) by the whole block, then A <- L^-1 (lower triangle, row-major).
